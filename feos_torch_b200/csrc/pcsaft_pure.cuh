@@ -1,0 +1,189 @@
+// Pure-component PC-SAFT reduced residual Helmholtz energy density a = A/(V kT) [1/A^3].
+//
+// Device-side, in-register replacement for PcSaftPure.helmholtz_energy
+// (/root/reference/feos_torch/pcsaft_pure.py:106-178) and the parameter preprocessing of
+// PcSaftPure.__init__ (:90-103).  The evaluation is split in two stages:
+//   pure_coef<P>()      everything that depends on (parameters, T) only -- evaluated once per
+//                       state and kept in registers across all Newton iterations;
+//   pure_helmholtz<P,R> the density dependent part, templated on the number type R of the density
+//                       (double, D2 = value+1st+2nd density derivative, DN<K> = parameter
+//                       directions, D2T<DN<K>> = both).
+#pragma once
+#include "ad.cuh"
+
+namespace feos {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kKB = 1.380649e-23;          // J/K (exact, CODATA 2018; si_units.KB)
+constexpr double kNAV = 6.02214076e23;        // 1/mol
+constexpr double kDipoleScale = 1e-19 / kKB;  // pcsaft_pure.py:95-100
+constexpr double kPaPerRed = kKB / 1e-30;     // p[Pa] = p_red * T * kPaPerRed  (pcsaft_pure.py:215)
+constexpr double kKmolM3PerRed = 1.0 / (1.0e3 * kNAV * 1e-30);  // pcsaft_pure.py:199
+constexpr double kMaxEta = 0.5;               // feos PC-SAFT: rho_max = 0.5 / (pi/6 m sigma^3)
+
+// universal constants, pcsaft_pure.py:10-86 (Gross & Sadowski 2001; Gross & Vrabec 2006)
+__constant__ double cA0[7] = {0.91056314451539, 0.63612814494991, 2.68613478913903, -26.5473624914884,
+                              97.7592087835073, -159.591540865600, 91.2977740839123};
+__constant__ double cA1[7] = {-0.30840169182720, 0.18605311591713, -2.50300472586548, 21.4197936296668,
+                              -65.2558853303492, 83.3186804808856, -33.7469229297323};
+__constant__ double cA2[7] = {-0.09061483509767, 0.45278428063920, 0.59627007280101, -1.72418291311787,
+                              -4.13021125311661, 13.7766318697211, -8.67284703679646};
+__constant__ double cB0[7] = {0.72409469413165, 2.23827918609380, -4.00258494846342, -21.00357681484648,
+                              26.8556413626615, 206.5513384066188, -355.60235612207947};
+__constant__ double cB1[7] = {-0.57554980753450, 0.69950955214436, 3.89256733895307, -17.21547164777212,
+                              192.6722644652495, -161.8264616487648, -165.2076934555607};
+__constant__ double cB2[7] = {0.09768831158356, -0.25575749816100, -9.15585615297321, 20.64207597439724,
+                              -38.80443005206285, 93.6267740770146, -29.66690558514725};
+__constant__ double cAD[5][3] = {{0.30435038064, 0.95346405973, -1.16100802773},
+                                 {-0.13585877707, -1.83963831920, 4.52586067320},
+                                 {1.44933285154, 2.01311801180, 0.97512223853},
+                                 {0.35569769252, -7.37249576667, -12.2810377713},
+                                 {-2.06533084541, 8.23741345333, 5.93975747420}};
+__constant__ double cBD[3][3] = {{0.21879385627, -0.58731641193, 3.48695755800},
+                                 {-1.18964307357, 1.24891317047, -14.9159739347},
+                                 {1.16268885692, -0.50852797392, 15.3720218600}};  // rows 3,4 are zero
+__constant__ double cCD[4][3] = {{-0.06467735252, -0.95208758351, -0.62609792333},
+                                 {0.19758818347, 2.99242575222, 1.29246858189},
+                                 {-0.80875619458, -2.38026356489, 1.65427830900},
+                                 {0.69028490492, -0.27012609786, -3.43967436378}};
+
+template <class X>
+FD double ad_primal(const X& x);
+template <>
+FD double ad_primal<double>(const double& x) { return x; }
+template <int N>
+FD double ad_primal(const DN<N>& x) { return x.re; }
+template <class T>
+FD double ad_primal(const D2T<T>& x) { return ad_primal(x.re); }
+template <class T>
+FD double ad_primal(const H2<T>& x) { return ad_primal(x.re); }
+
+// torch.clamp(max=c): passes the derivative where x <= c (pcsaft_pure.py:146)
+template <class X>
+FD X ad_clamp_max(const X& x, double c) { return (ad_primal(x) <= c) ? x : X(c); }
+
+template <class P>
+struct PureCoef {
+  P m, mm1, c_eta, w1, w2, k1, k2;  // hard sphere / chain / dispersion
+  P mu2t, v1, v2, e, inv_s3;        // dipole
+  P delta0, na, nb;                 // association
+  bool dipolar, assoc;
+};
+
+// Stage 1: (parameters, T) -> coefficients.  `grad_mode` keeps terms whose value vanishes but whose
+// parameter derivative does not (kappa = 0 or eps_ab = 0 with sites present).
+template <class P>
+FD PureCoef<P> pure_coef(const P& m, const P& sigma, const P& eps, const P& mu, const P& kappa, const P& eps_ab,
+                         const P& na, const P& nb, const P& T, bool grad_mode) {
+  PureCoef<P> c;
+  P s3 = sigma * sigma * sigma;
+  P e = eps / T;
+  P d = sigma * (1.0 - 0.12 * ad_exp(-3.0 * e));  // pcsaft_pure.py:108
+  c.m = m;
+  c.mm1 = m - 1.0;
+  c.c_eta = (kPi / 6.0) * m * (d * d * d);  // eta = c_eta * rho   (:110)
+  P m1 = (m - 1.0) / m;
+  P m2 = (m - 2.0) / m;
+  c.w1 = m1;
+  c.w2 = m1 * m2;  // (m1*(m2*A2+A1)+A0)  (:129-133)
+  P mes = m * m * e * s3;
+  c.k1 = (-2.0 * kPi) * mes;  // disp = rho^2 (k1 I1 + k2 C1 I2)   (:141-142)
+  c.k2 = (-kPi) * mes * m * e;
+  c.e = e;
+  // dipole (:145-160)
+  double mu0 = ad_primal(mu);
+  c.dipolar = (mu0 != 0.0);
+  if (c.dipolar) {
+    P mu2 = mu * mu / (m * s3 * eps) * kDipoleScale;
+    c.mu2t = mu2 * e * s3;
+    P mc = ad_clamp_max(m, 2.0);
+    c.v1 = (mc - 1.0) / mc;
+    c.v2 = c.v1 * (mc - 2.0) / mc;
+    c.inv_s3 = 1.0 / s3;
+  }
+  // association (:163-176).  Value and density derivatives vanish identically when any of
+  // kappa, eps_ab (Delta = 0) or both site counts are zero; parameter derivatives only when
+  // na = nb = 0.
+  double na0 = ad_primal(na), nb0 = ad_primal(nb);
+  bool sites = (na0 != 0.0) || (nb0 != 0.0);
+  bool strength = (ad_primal(kappa) != 0.0) && (ad_primal(eps_ab) != 0.0);
+  c.assoc = grad_mode ? sites : (sites && strength && na0 != 0.0 && nb0 != 0.0);
+  if (c.assoc) {
+    c.delta0 = (ad_exp(eps_ab / T) - 1.0) * s3 * kappa;
+    c.na = na;
+    c.nb = nb;
+  }
+  return c;
+}
+
+template <class R>
+FD R site_term(const R& x) { return ad_log(x) - 0.5 * x + 0.5; }
+
+// Stage 2: a(rho).  pcsaft_pure.py:110-178.
+template <class P, class R>
+FD R pure_helmholtz(const PureCoef<P>& c, const R& rho) {
+  R eta = rho * c.c_eta;
+  R e2 = eta * eta;
+  R e3 = e2 * eta;
+  R e4 = e2 * e2;
+  R e5 = e2 * e3;
+  R e6 = e3 * e3;
+  R om = 1.0 - eta;
+  R omi = ad_recip(om);
+  R omi2 = omi * omi;
+
+  // hard sphere (:118) and hard chain (:121-122)
+  R a = (rho * c.m) * ((4.0 * eta - 3.0 * e2) * omi2);
+  R g = (1.0 - 0.5 * eta) * (omi * omi2);
+  a = a - (rho * c.mm1) * ad_log(g);
+
+  // dispersion (:125-142)
+  R i1 = eta * (cA0[1] + c.w1 * cA1[1] + c.w2 * cA2[1]) + (cA0[0] + c.w1 * cA1[0] + c.w2 * cA2[0]);
+  R i2 = eta * (cB0[1] + c.w1 * cB1[1] + c.w2 * cB2[1]) + (cB0[0] + c.w1 * cB1[0] + c.w2 * cB2[0]);
+  i1 = i1 + e2 * (cA0[2] + c.w1 * cA1[2] + c.w2 * cA2[2]);
+  i2 = i2 + e2 * (cB0[2] + c.w1 * cB1[2] + c.w2 * cB2[2]);
+  i1 = i1 + e3 * (cA0[3] + c.w1 * cA1[3] + c.w2 * cA2[3]);
+  i2 = i2 + e3 * (cB0[3] + c.w1 * cB1[3] + c.w2 * cB2[3]);
+  i1 = i1 + e4 * (cA0[4] + c.w1 * cA1[4] + c.w2 * cA2[4]);
+  i2 = i2 + e4 * (cB0[4] + c.w1 * cB1[4] + c.w2 * cB2[4]);
+  i1 = i1 + e5 * (cA0[5] + c.w1 * cA1[5] + c.w2 * cA2[5]);
+  i2 = i2 + e5 * (cB0[5] + c.w1 * cB1[5] + c.w2 * cB2[5]);
+  i1 = i1 + e6 * (cA0[6] + c.w1 * cA1[6] + c.w2 * cA2[6]);
+  i2 = i2 + e6 * (cB0[6] + c.w1 * cB1[6] + c.w2 * cB2[6]);
+  R tmi = ad_recip(2.0 - eta);
+  R c1 = ad_recip(1.0 + ((8.0 * eta - 2.0 * e2) * (omi2 * omi2)) * c.m -
+                  ((20.0 * eta - 27.0 * e2 + 12.0 * e3 - 2.0 * e4) * (omi2 * (tmi * tmi))) * c.mm1);
+  R rho2 = rho * rho;
+  a = a + rho2 * (i1 * c.k1 + (c1 * i2) * c.k2);
+
+  // dipole (:145-160)
+  if (c.dipolar) {
+    R j1 = ((cAD[0][0] + c.v1 * cAD[0][1] + c.v2 * cAD[0][2]) + c.e * (cBD[0][0] + c.v1 * cBD[0][1] + c.v2 * cBD[0][2])) +
+           eta * ((cAD[1][0] + c.v1 * cAD[1][1] + c.v2 * cAD[1][2]) + c.e * (cBD[1][0] + c.v1 * cBD[1][1] + c.v2 * cBD[1][2])) +
+           e2 * ((cAD[2][0] + c.v1 * cAD[2][1] + c.v2 * cAD[2][2]) + c.e * (cBD[2][0] + c.v1 * cBD[2][1] + c.v2 * cBD[2][2])) +
+           e3 * (cAD[3][0] + c.v1 * cAD[3][1] + c.v2 * cAD[3][2]) + e4 * (cAD[4][0] + c.v1 * cAD[4][1] + c.v2 * cAD[4][2]);
+    R j2 = (cCD[0][0] + c.v1 * cCD[0][1] + c.v2 * cCD[0][2]) + eta * (cCD[1][0] + c.v1 * cCD[1][1] + c.v2 * cCD[1][2]) +
+           e2 * (cCD[2][0] + c.v1 * cCD[2][1] + c.v2 * cCD[2][2]) + e3 * (cCD[3][0] + c.v1 * cCD[3][1] + c.v2 * cCD[3][2]);
+    R phi2 = (rho2 * j1) * (c.inv_s3 * (-kPi));
+    R phi3 = (rho2 * rho * j2) * (c.inv_s3 * (-4.0 / 3.0 * kPi * kPi));
+    R num = (phi2 * phi2) * (c.mu2t * c.mu2t);
+    a = a + num / (phi2 - phi3 * c.mu2t);
+  }
+
+  // association, closed-form two-site solution (:163-176)
+  if (c.assoc) {
+    R k = eta * omi;
+    R delta = ((1.0 + k * (1.5 + 0.5 * k)) * omi) * c.delta0;
+    R ra = rho * c.na;
+    R rb = rho * c.nb;
+    R dd = (rb - ra) * delta;
+    R aux = 1.0 - dd;
+    R sq = ad_sqrt(aux * aux + 4.0 * (rb * delta));
+    R xa = 2.0 / (sq + 1.0 + dd);
+    R xb = 2.0 / (sq + 1.0 - dd);
+    a = a + ra * site_term(xa) + rb * site_term(xb);
+  }
+  return a;
+}
+
+}  // namespace feos
