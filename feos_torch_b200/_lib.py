@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI declared in ``include/feos_b200.h`` (``libfeos_b200.so``).
+
+This is the only place the Python layer touches native code.  There is deliberately NO fallback:
+if the CUDA library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfeos_b200.so")
+
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+
+# name -> argument types; every symbol include/feos_b200.h declares (tests check the export list)
+SIGNATURES = {
+    "feos_b200_version": ([], ctypes.c_char_p),
+    "feos_b200_last_error": ([], ctypes.c_char_p),
+    "feos_b200_launch_count": ([], _i64),
+    "feos_b200_measure_fp64_peak": ([ctypes.c_int, _vp], ctypes.c_int),
+    "feos_dev_pure_vle_fwd": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_vle_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_rho_tp_fwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_rho_tp_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_state": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_host_pcsaft_vapor_pressure": ([_vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
+    "feos_host_pcsaft_liquid_density": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
+}
+
+_lib = None
+
+
+class FeosB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load ``libfeos_b200.so`` (built by ``__graft_entry__.build()``); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FeosB200Error(
+                f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "feos_torch_b200 has no CPU fallback."
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (args, res) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Call an ``int``-returning entry point and raise with the library's error text on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise FeosB200Error(f"{name} failed ({rc}): {lib.feos_b200_last_error().decode()}")
+
+
+TIMINGS = None  # set to {} by bench.py: entry point -> [(start_event, end_event), ...]
+
+
+def timed_call(name, *args):
+    """``call`` bracketed by CUDA events on the current torch stream when ``TIMINGS`` is enabled
+    (per-kernel shares inside bench.py's timed region); plain ``call`` otherwise."""
+    if TIMINGS is None:
+        return call(name, *args)
+    import torch
+
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, *args)
+    e1.record()
+    TIMINGS.setdefault(name, []).append((e0, e1))
+
+
+def measure_fp64_peak(iters=20000):
+    out = ctypes.c_double(0.0)
+    call("feos_b200_measure_fp64_peak", iters, ctypes.cast(ctypes.byref(out), ctypes.c_void_p))
+    return out.value
+
+
+def launch_count():
+    return int(load().feos_b200_launch_count())
+
+
+def ptr(t):
+    """Device (or host) pointer of a contiguous tensor / numpy array, ``None`` -> NULL."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)

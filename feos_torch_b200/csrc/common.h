@@ -1,0 +1,42 @@
+// Host-side helpers shared by the C-ABI translation units: error text, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace feos {
+
+void set_error(const char* fmt, ...);
+void clear_error();
+void count_launch(int64_t k = 1);
+
+// evaluates a CUDA runtime call; on failure records the text and returns -2 from the caller
+#define FEOS_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t err__ = (call);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      feos::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+      return -2;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+#define FEOS_LAUNCH_OK()                                                                  \
+  do {                                                                                    \
+    cudaError_t err__ = cudaGetLastError();                                               \
+    if (err__ != cudaSuccess) {                                                           \
+      feos::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(err__), __FILE__, __LINE__); \
+      return -3;                                                                          \
+    }                                                                                     \
+    feos::count_launch();                                                                 \
+  } while (0)
+
+#define FEOS_ARG(cond)                                                                    \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      feos::set_error("invalid argument: %s (%s:%d)", #cond, __FILE__, __LINE__);         \
+      return -1;                                                                          \
+    }                                                                                     \
+  } while (0)
+
+inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+}  // namespace feos

@@ -7,7 +7,7 @@
 //                       state and kept in registers across all Newton iterations;
 //   pure_helmholtz<P,R> the density dependent part, templated on the number type R of the density
 //                       (double, D2 = value+1st+2nd density derivative, DN<K> = parameter
-//                       directions, D2T<DN<K>> = both).
+//                       directions, D1T<DN<K>> = both).
 #pragma once
 #include "ad.cuh"
 
@@ -19,48 +19,33 @@ constexpr double kNAV = 6.02214076e23;        // 1/mol
 constexpr double kDipoleScale = 1e-19 / kKB;  // pcsaft_pure.py:95-100
 constexpr double kPaPerRed = kKB / 1e-30;     // p[Pa] = p_red * T * kPaPerRed  (pcsaft_pure.py:215)
 constexpr double kKmolM3PerRed = 1.0 / (1.0e3 * kNAV * 1e-30);  // pcsaft_pure.py:199
-constexpr double kMaxEta = 0.5;               // feos PC-SAFT: rho_max = 0.5 / (pi/6 m sigma^3)
+constexpr double kMaxEta = 0.5;               // rho_max = 0.5 / (pi/6 m sigma^3), as feos' PC-SAFT
 
 // universal constants, pcsaft_pure.py:10-86 (Gross & Sadowski 2001; Gross & Vrabec 2006)
-__constant__ double cA0[7] = {0.91056314451539, 0.63612814494991, 2.68613478913903, -26.5473624914884,
-                              97.7592087835073, -159.591540865600, 91.2977740839123};
-__constant__ double cA1[7] = {-0.30840169182720, 0.18605311591713, -2.50300472586548, 21.4197936296668,
-                              -65.2558853303492, 83.3186804808856, -33.7469229297323};
-__constant__ double cA2[7] = {-0.09061483509767, 0.45278428063920, 0.59627007280101, -1.72418291311787,
-                              -4.13021125311661, 13.7766318697211, -8.67284703679646};
-__constant__ double cB0[7] = {0.72409469413165, 2.23827918609380, -4.00258494846342, -21.00357681484648,
-                              26.8556413626615, 206.5513384066188, -355.60235612207947};
-__constant__ double cB1[7] = {-0.57554980753450, 0.69950955214436, 3.89256733895307, -17.21547164777212,
-                              192.6722644652495, -161.8264616487648, -165.2076934555607};
-__constant__ double cB2[7] = {0.09768831158356, -0.25575749816100, -9.15585615297321, 20.64207597439724,
-                              -38.80443005206285, 93.6267740770146, -29.66690558514725};
-__constant__ double cAD[5][3] = {{0.30435038064, 0.95346405973, -1.16100802773},
-                                 {-0.13585877707, -1.83963831920, 4.52586067320},
-                                 {1.44933285154, 2.01311801180, 0.97512223853},
-                                 {0.35569769252, -7.37249576667, -12.2810377713},
-                                 {-2.06533084541, 8.23741345333, 5.93975747420}};
-__constant__ double cBD[3][3] = {{0.21879385627, -0.58731641193, 3.48695755800},
-                                 {-1.18964307357, 1.24891317047, -14.9159739347},
-                                 {1.16268885692, -0.50852797392, 15.3720218600}};  // rows 3,4 are zero
-__constant__ double cCD[4][3] = {{-0.06467735252, -0.95208758351, -0.62609792333},
-                                 {0.19758818347, 2.99242575222, 1.29246858189},
-                                 {-0.80875619458, -2.38026356489, 1.65427830900},
-                                 {0.69028490492, -0.27012609786, -3.43967436378}};
-
-template <class X>
-FD double ad_primal(const X& x);
-template <>
-FD double ad_primal<double>(const double& x) { return x; }
-template <int N>
-FD double ad_primal(const DN<N>& x) { return x.re; }
-template <class T>
-FD double ad_primal(const D2T<T>& x) { return ad_primal(x.re); }
-template <class T>
-FD double ad_primal(const H2<T>& x) { return ad_primal(x.re); }
-
-// torch.clamp(max=c): passes the derivative where x <= c (pcsaft_pure.py:146)
-template <class X>
-FD X ad_clamp_max(const X& x, double c) { return (ad_primal(x) <= c) ? x : X(c); }
+FEOS_CONSTANT double cA0[7] = {0.91056314451539, 0.63612814494991, 2.68613478913903, -26.5473624914884,
+                               97.7592087835073, -159.591540865600, 91.2977740839123};
+FEOS_CONSTANT double cA1[7] = {-0.30840169182720, 0.18605311591713, -2.50300472586548, 21.4197936296668,
+                               -65.2558853303492, 83.3186804808856, -33.7469229297323};
+FEOS_CONSTANT double cA2[7] = {-0.09061483509767, 0.45278428063920, 0.59627007280101, -1.72418291311787,
+                               -4.13021125311661, 13.7766318697211, -8.67284703679646};
+FEOS_CONSTANT double cB0[7] = {0.72409469413165, 2.23827918609380, -4.00258494846342, -21.00357681484648,
+                               26.8556413626615, 206.5513384066188, -355.60235612207947};
+FEOS_CONSTANT double cB1[7] = {-0.57554980753450, 0.69950955214436, 3.89256733895307, -17.21547164777212,
+                               192.6722644652495, -161.8264616487648, -165.2076934555607};
+FEOS_CONSTANT double cB2[7] = {0.09768831158356, -0.25575749816100, -9.15585615297321, 20.64207597439724,
+                               -38.80443005206285, 93.6267740770146, -29.66690558514725};
+FEOS_CONSTANT double cAD[5][3] = {{0.30435038064, 0.95346405973, -1.16100802773},
+                                  {-0.13585877707, -1.83963831920, 4.52586067320},
+                                  {1.44933285154, 2.01311801180, 0.97512223853},
+                                  {0.35569769252, -7.37249576667, -12.2810377713},
+                                  {-2.06533084541, 8.23741345333, 5.93975747420}};
+FEOS_CONSTANT double cBD[3][3] = {{0.21879385627, -0.58731641193, 3.48695755800},
+                                  {-1.18964307357, 1.24891317047, -14.9159739347},
+                                  {1.16268885692, -0.50852797392, 15.3720218600}};  // rows 3,4 are zero
+FEOS_CONSTANT double cCD[4][3] = {{-0.06467735252, -0.95208758351, -0.62609792333},
+                                  {0.19758818347, 2.99242575222, 1.29246858189},
+                                  {-0.80875619458, -2.38026356489, 1.65427830900},
+                                  {0.69028490492, -0.27012609786, -3.43967436378}};
 
 template <class P>
 struct PureCoef {
@@ -70,50 +55,50 @@ struct PureCoef {
   bool dipolar, assoc;
 };
 
-// Stage 1: (parameters, T) -> coefficients.  `grad_mode` keeps terms whose value vanishes but whose
-// parameter derivative does not (kappa = 0 or eps_ab = 0 with sites present).
+// Stage 1: (parameters, T) -> coefficients.  `grad_mode` keeps association terms whose value
+// vanishes but whose parameter derivative does not (kappa = 0 or eps_ab = 0 with sites present).
 template <class P>
-FD PureCoef<P> pure_coef(const P& m, const P& sigma, const P& eps, const P& mu, const P& kappa, const P& eps_ab,
-                         const P& na, const P& nb, const P& T, bool grad_mode) {
-  PureCoef<P> c;
+FD void pure_coef(PureCoef<P>& c, const P& m, const P& sigma, const P& eps, const P& mu, const P& kappa,
+                  const P& eps_ab, const P& na, const P& nb, const P& T, bool grad_mode) {
   P s3 = sigma * sigma * sigma;
-  P e = eps / T;
+  P ti = ad_recip(T);
+  P e = eps * ti;
   P d = sigma * (1.0 - 0.12 * ad_exp(-3.0 * e));  // pcsaft_pure.py:108
   c.m = m;
   c.mm1 = m - 1.0;
   c.c_eta = (kPi / 6.0) * m * (d * d * d);  // eta = c_eta * rho   (:110)
-  P m1 = (m - 1.0) / m;
-  P m2 = (m - 2.0) / m;
+  P mi = ad_recip(m);
+  P m1 = (m - 1.0) * mi;
+  P m2 = (m - 2.0) * mi;
   c.w1 = m1;
   c.w2 = m1 * m2;  // (m1*(m2*A2+A1)+A0)  (:129-133)
   P mes = m * m * e * s3;
   c.k1 = (-2.0 * kPi) * mes;  // disp = rho^2 (k1 I1 + k2 C1 I2)   (:141-142)
   c.k2 = (-kPi) * mes * m * e;
   c.e = e;
-  // dipole (:145-160)
-  double mu0 = ad_primal(mu);
-  c.dipolar = (mu0 != 0.0);
+  // dipole (:145-160); identically zero with zero gradient for mu = 0 (README.md:28)
+  c.dipolar = (ad_primal(mu) != 0.0);
   if (c.dipolar) {
-    P mu2 = mu * mu / (m * s3 * eps) * kDipoleScale;
+    P mu2 = mu * mu / (m * s3 * eps) * kDipoleScale;  // :94-99
     c.mu2t = mu2 * e * s3;
     P mc = ad_clamp_max(m, 2.0);
-    c.v1 = (mc - 1.0) / mc;
-    c.v2 = c.v1 * (mc - 2.0) / mc;
-    c.inv_s3 = 1.0 / s3;
+    P mci = ad_recip(mc);
+    c.v1 = (mc - 1.0) * mci;
+    c.v2 = c.v1 * (mc - 2.0) * mci;
+    c.inv_s3 = ad_recip(s3);
   }
-  // association (:163-176).  Value and density derivatives vanish identically when any of
-  // kappa, eps_ab (Delta = 0) or both site counts are zero; parameter derivatives only when
-  // na = nb = 0.
+  // association (:163-176).  Value and density derivatives vanish identically when kappa or
+  // eps_ab is zero (Delta = 0) or when a site count is zero; all parameter derivatives vanish only
+  // when na = nb = 0.
   double na0 = ad_primal(na), nb0 = ad_primal(nb);
   bool sites = (na0 != 0.0) || (nb0 != 0.0);
   bool strength = (ad_primal(kappa) != 0.0) && (ad_primal(eps_ab) != 0.0);
-  c.assoc = grad_mode ? sites : (sites && strength && na0 != 0.0 && nb0 != 0.0);
+  c.assoc = grad_mode ? sites : (strength && na0 != 0.0 && nb0 != 0.0);
   if (c.assoc) {
-    c.delta0 = (ad_exp(eps_ab / T) - 1.0) * s3 * kappa;
+    c.delta0 = (ad_exp(eps_ab * ti) - 1.0) * s3 * kappa;
     c.na = na;
     c.nb = nb;
   }
-  return c;
 }
 
 template <class R>
@@ -162,10 +147,10 @@ FD R pure_helmholtz(const PureCoef<P>& c, const R& rho) {
            eta * ((cAD[1][0] + c.v1 * cAD[1][1] + c.v2 * cAD[1][2]) + c.e * (cBD[1][0] + c.v1 * cBD[1][1] + c.v2 * cBD[1][2])) +
            e2 * ((cAD[2][0] + c.v1 * cAD[2][1] + c.v2 * cAD[2][2]) + c.e * (cBD[2][0] + c.v1 * cBD[2][1] + c.v2 * cBD[2][2])) +
            e3 * (cAD[3][0] + c.v1 * cAD[3][1] + c.v2 * cAD[3][2]) + e4 * (cAD[4][0] + c.v1 * cAD[4][1] + c.v2 * cAD[4][2]);
-    R j2 = (cCD[0][0] + c.v1 * cCD[0][1] + c.v2 * cCD[0][2]) + eta * (cCD[1][0] + c.v1 * cCD[1][1] + c.v2 * cCD[1][2]) +
+    R j2 = eta * (cCD[1][0] + c.v1 * cCD[1][1] + c.v2 * cCD[1][2]) + (cCD[0][0] + c.v1 * cCD[0][1] + c.v2 * cCD[0][2]) +
            e2 * (cCD[2][0] + c.v1 * cCD[2][1] + c.v2 * cCD[2][2]) + e3 * (cCD[3][0] + c.v1 * cCD[3][1] + c.v2 * cCD[3][2]);
     R phi2 = (rho2 * j1) * (c.inv_s3 * (-kPi));
-    R phi3 = (rho2 * rho * j2) * (c.inv_s3 * (-4.0 / 3.0 * kPi * kPi));
+    R phi3 = ((rho2 * rho) * j2) * (c.inv_s3 * (-4.0 / 3.0 * kPi * kPi));
     R num = (phi2 * phi2) * (c.mu2t * c.mu2t);
     a = a + num / (phi2 - phi3 * c.mu2t);
   }
@@ -184,6 +169,21 @@ FD R pure_helmholtz(const PureCoef<P>& c, const R& rho) {
     a = a + ra * site_term(xa) + rb * site_term(xb);
   }
   return a;
+}
+
+// (p/kT, d(p/kT)/drho, a, a') from one second-order evaluation (pcsaft_pure.py:180-182)
+struct PureEval {
+  double a, a1, p, dp;
+};
+FD PureEval pure_eval(const PureCoef<double>& c, double rho) {
+  D2 r(rho, 1.0, 0.0);
+  D2 a = pure_helmholtz<double, D2>(c, r);
+  PureEval o;
+  o.a = a.re;
+  o.a1 = a.d1;
+  o.p = rho - a.re + rho * a.d1;
+  o.dp = 1.0 + rho * a.d2;
+  return o;
 }
 
 }  // namespace feos

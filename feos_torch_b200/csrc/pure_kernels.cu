@@ -1,0 +1,394 @@
+// sm_100a kernels and C-ABI entry points of the pure-component hot path
+// (include/feos_b200.h: feos_dev_pure_*, feos_host_pcsaft_vapor_pressure / _liquid_density).
+//
+// Roofline: FP64 FMA pipe (no tensor cores: not a contraction).  I/O per state is 72 B in and
+// <= 41 B out against ~2e4 FP64 operations, i.e. far right of the HBM ridge.
+//
+//   pure_vle_fwd_kernel      one thread per state, fast path (pure_solver.cuh); states the fast path
+//                            cannot finish are appended to a retry list (atomic counter), so the
+//                            expensive robust path never stalls the 31 neighbours of a warp;
+//   pure_vle_retry_kernel    robust path over the compacted retry list;
+//   pure_vle_bwd_kernel      implicit-function-theorem gradients, 3 passes of 3 dual directions;
+//   pure_rho_tp_*            liquid density at (T, p), forward and gradient;
+//   pure_state_kernel        a, p, dp/drho at given (T, rho).
+#include <vector>
+
+#include "../../include/feos_b200.h"
+#include "common.h"
+#include "pure_grad.cuh"
+#include "pure_solver.cuh"
+
+namespace feos {
+
+constexpr int kBlock = 128;
+
+struct PureRow {
+  double v[8];
+};
+
+__device__ __forceinline__ PureRow load_row(const double* __restrict__ params, int64_t i) {
+  // one 64 B row = 4 x 16 B vector loads; neighbouring threads read neighbouring rows
+  const double2* p = reinterpret_cast<const double2*>(params + 8 * i);
+  PureRow r;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double2 t = __ldg(p + k);
+    r.v[2 * k] = t.x;
+    r.v[2 * k + 1] = t.y;
+  }
+  return r;
+}
+
+__device__ __forceinline__ void make_coef(const PureRow& r, double T, PureCoef<double>& c, double& rho_max) {
+  pure_coef<double>(c, r.v[0], r.v[1], r.v[2], r.v[3], r.v[4], r.v[5], r.v[6], r.v[7], T, false);
+  rho_max = kMaxEta / (kPi / 6.0 * r.v[0] * r.v[1] * r.v[1] * r.v[1]);
+}
+
+__device__ __forceinline__ void store_vle(int64_t i, int st, double rho_l, double u, const PureEval& el,
+                                          const PureEval& ev, double rle, double rve, double T, double* rho,
+                                          double* vp, double* rleq, uint8_t* failed) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double o_v = nan, o_l = nan, o_vp = nan, o_rl = nan;
+  if (st == kStatusOk) {
+    o_v = exp(u);
+    o_l = rho_l;
+    pure_vle_properties(el, ev, rle, rve, T, o_vp, o_rl);
+  }
+  reinterpret_cast<double2*>(rho)[i] = make_double2(o_v, o_l);
+  if (vp) vp[i] = o_vp;
+  if (rleq) rleq[i] = o_rl;
+  failed[i] = (st == kStatusOk) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(kBlock)
+pure_vle_fwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature, int64_t n,
+                    double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
+                    uint8_t* __restrict__ failed, int32_t* __restrict__ evals, int32_t* __restrict__ retry_list,
+                    int32_t* __restrict__ retry_count) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PureRow r = load_row(params, i);
+  double T = temperature[i];
+  PureCoef<double> c;
+  double rho_max;
+  make_coef(r, T, c, rho_max);
+  double rho_l, u, rle, rve;
+  PureEval el, ev;
+  int ne = 0;
+  int st = pure_vle_fast(c, rho_max, rho_l, u, el, ev, rle, rve, ne);
+  if (evals) evals[i] = ne;
+  if (st == kStatusRetry) {
+    int slot = atomicAdd(retry_count, 1);
+    retry_list[slot] = (int32_t)i;
+    return;
+  }
+  store_vle(i, st, rho_l, u, el, ev, rle, rve, T, rho, vp, rleq, failed);
+}
+
+__global__ void __launch_bounds__(64)
+pure_vle_retry_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
+                      double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
+                      uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
+                      const int32_t* __restrict__ retry_list, const int32_t* __restrict__ retry_count) {
+  int count = *retry_count;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    int64_t i = retry_list[k];
+    PureRow r = load_row(params, i);
+    double T = temperature[i];
+    PureCoef<double> c;
+    double rho_max;
+    make_coef(r, T, c, rho_max);
+    double rho_l, u, rle, rve;
+    PureEval el, ev;
+    int ne = 0;
+    int st = pure_vle_robust(c, rho_max, rho_l, u, el, ev, rle, rve, ne);
+    if (evals) evals[i] += ne;
+    store_vle(i, st, rho_l, u, el, ev, rle, rve, T, rho, vp, rleq, failed);
+  }
+}
+
+template <bool NEED_RLEQ>
+__global__ void __launch_bounds__(kBlock)
+pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
+                    const double* __restrict__ rho, const uint8_t* __restrict__ failed,
+                    const double* __restrict__ g_vp, const double* __restrict__ g_rho, int64_t n,
+                    double* __restrict__ grad_params, double* __restrict__ grad_t) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (failed[i]) {
+    double2* gp = reinterpret_cast<double2*>(grad_params + 8 * i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gp[k] = make_double2(0.0, 0.0);
+    if (grad_t) grad_t[i] = 0.0;
+    return;
+  }
+  PureRow r = load_row(params, i);
+  double T = temperature[i];
+  double2 rr = reinterpret_cast<const double2*>(rho)[i];
+  double gv = g_vp ? g_vp[i] : 0.0;
+  double gr = 0.0, dpl = 1.0;
+  if (NEED_RLEQ) {
+    gr = g_rho[i];
+    PureCoef<double> c;
+    double rho_max;
+    make_coef(r, T, c, rho_max);
+    dpl = pure_eval(c, rr.y).dp;
+  }
+#pragma unroll 1
+  for (int f = 0; f < 9; f += 3) {
+    double g3[3];
+    pure_vle_grad_pass<3, NEED_RLEQ>(r.v, T, rr.x, rr.y, dpl, f, gv, gr, g3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (f + k < 8) grad_params[8 * i + f + k] = g3[k];
+      else if (grad_t) grad_t[i] = g3[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+pure_rho_tp_fwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
+                       const double* __restrict__ pressure, int64_t n, double* __restrict__ rho,
+                       double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PureRow r = load_row(params, i);
+  double T = temperature[i];
+  PureCoef<double> c;
+  double rho_max;
+  make_coef(r, T, c, rho_max);
+  double p_t = pressure[i] / (T * kPaPerRed);  // pcsaft_pure.py:196
+  double x;
+  PureEval e;
+  int ne = 0;
+  int st = pure_liquid_density(c, rho_max, p_t, x, e, ne);
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double rn = (st == kStatusOk) ? x - (e.p - p_t) / e.dp : nan;  // pcsaft_pure.py:198
+  rho[i] = rn;
+  if (value) value[i] = rn * kKmolM3PerRed;
+  failed[i] = (st == kStatusOk) ? 0 : 1;
+  if (evals) evals[i] = ne;
+}
+
+__global__ void __launch_bounds__(kBlock)
+pure_rho_tp_bwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
+                       const double* __restrict__ pressure, const double* __restrict__ rho,
+                       const uint8_t* __restrict__ failed, const double* __restrict__ g, int64_t n,
+                       double* __restrict__ grad_params, double* __restrict__ grad_t, double* __restrict__ grad_p) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (failed[i]) {
+    if (grad_params) {
+      double2* gp = reinterpret_cast<double2*>(grad_params + 8 * i);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) gp[k] = make_double2(0.0, 0.0);
+    }
+    if (grad_t) grad_t[i] = 0.0;
+    if (grad_p) grad_p[i] = 0.0;
+    return;
+  }
+  PureRow r = load_row(params, i);
+  double T = temperature[i];
+  PureCoef<double> c;
+  double rho_max;
+  make_coef(r, T, c, rho_max);
+  double x = rho[i];
+  double dp = pure_eval(c, x).dp;
+  double p_t = pressure[i] / (T * kPaPerRed);
+  double gi = g[i];
+  if (grad_p) grad_p[i] = gi / dp / (T * kPaPerRed) * kKmolM3PerRed;
+  if (!grad_params && !grad_t) return;
+#pragma unroll 1
+  for (int f = 0; f < 9; f += 3) {
+    double g3[3];
+    pure_rho_tp_grad_pass<3>(r.v, T, x, p_t, dp, f, gi, g3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (f + k < 8) {
+        if (grad_params) grad_params[8 * i + f + k] = g3[k];
+      } else if (grad_t) grad_t[i] = g3[k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock)
+pure_state_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
+                  const double* __restrict__ density, int64_t n, double* __restrict__ a, double* __restrict__ p,
+                  double* __restrict__ dp) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PureRow r = load_row(params, i);
+  PureCoef<double> c;
+  double rho_max;
+  make_coef(r, temperature[i], c, rho_max);
+  PureEval e = pure_eval(c, density[i]);
+  if (a) a[i] = e.a;
+  if (p) p[i] = e.p;
+  if (dp) dp[i] = e.dp;
+}
+
+}  // namespace feos
+
+using namespace feos;
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -2; }
+  template <class T>
+  T* as() { return (T*)p; }
+};
+}  // namespace
+
+extern "C" {
+
+int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64_t n, double* rho,
+                          double* vapor_pressure, double* liquid_density, uint8_t* failed, int32_t* evals,
+                          void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  FEOS_ARG(params && temperature && rho && failed);
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* ws = nullptr;  // [0] = retry counter, [1..n] = retry list
+  FEOS_CUDA(cudaMallocAsync((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s));
+  FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
+  pure_vle_fwd_kernel<<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, n, rho, vapor_pressure,
+                                                           liquid_density, failed, evals, ws + 1, ws);
+  FEOS_LAUNCH_OK();
+  int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
+  pure_vle_retry_kernel<<<retry_grid, 64, 0, s>>>(params, temperature, rho, vapor_pressure, liquid_density, failed,
+                                                 evals, ws + 1, ws);
+  FEOS_LAUNCH_OK();
+  FEOS_CUDA(cudaFreeAsync(ws, s));
+  return 0;
+}
+
+int feos_dev_pure_vle_bwd(const double* params, const double* temperature, const double* rho,
+                          const uint8_t* failed, const double* g_vp, const double* g_rho, int64_t n,
+                          double* grad_params, double* grad_temperature, void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  FEOS_ARG(params && temperature && rho && failed && grad_params);
+  FEOS_ARG(g_vp || g_rho);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g_rho)
+    pure_vle_bwd_kernel<true><<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, rho, failed, g_vp, g_rho, n,
+                                                                   grad_params, grad_temperature);
+  else
+    pure_vle_bwd_kernel<false><<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, rho, failed, g_vp, g_rho, n,
+                                                                    grad_params, grad_temperature);
+  FEOS_LAUNCH_OK();
+  return 0;
+}
+
+int feos_dev_pure_rho_tp_fwd(const double* params, const double* temperature, const double* pressure,
+                             int64_t n, double* rho, double* liquid_density, uint8_t* failed, int32_t* evals,
+                             void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  FEOS_ARG(params && temperature && pressure && rho && failed);
+  pure_rho_tp_fwd_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(params, temperature, pressure, n, rho,
+                                                                                 liquid_density, failed, evals);
+  FEOS_LAUNCH_OK();
+  return 0;
+}
+
+int feos_dev_pure_rho_tp_bwd(const double* params, const double* temperature, const double* pressure,
+                             const double* rho, const uint8_t* failed, const double* g, int64_t n,
+                             double* grad_params, double* grad_temperature, double* grad_pressure,
+                             void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  FEOS_ARG(params && temperature && pressure && rho && failed && g);
+  pure_rho_tp_bwd_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+      params, temperature, pressure, rho, failed, g, n, grad_params, grad_temperature, grad_pressure);
+  FEOS_LAUNCH_OK();
+  return 0;
+}
+
+int feos_dev_pure_state(const double* params, const double* temperature, const double* density, int64_t n,
+                        double* a, double* p, double* dp, void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  FEOS_ARG(params && temperature && density);
+  pure_state_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(params, temperature, density, n, a, p, dp);
+  FEOS_LAUNCH_OK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer entry points (reference native signatures)
+// ---------------------------------------------------------------------------------------------
+
+int feos_host_pcsaft_vapor_pressure(const double* params, const double* temperature, int64_t n,
+                                    double* rho_out, uint8_t* status, int64_t* n_ok) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31 && n_ok);
+  *n_ok = 0;
+  if (n == 0) return 0;
+  FEOS_ARG(params && temperature && rho_out && status);
+  DevBuf dp, dt, drho, dfail;
+  if (dp.alloc(64 * n) || dt.alloc(8 * n) || drho.alloc(16 * n) || dfail.alloc(n)) {
+    set_error("cudaMalloc failed for %lld states", (long long)n);
+    return -2;
+  }
+  FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 64 * n, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
+  int rc = feos_dev_pure_vle_fwd(dp.as<double>(), dt.as<double>(), n, drho.as<double>(), nullptr, nullptr,
+                                 dfail.as<uint8_t>(), nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<double> rho(2 * (size_t)n);
+  FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 16 * n, cudaMemcpyDeviceToHost, 0));
+  FEOS_CUDA(cudaMemcpyAsync(status, dfail.p, n, cudaMemcpyDeviceToHost, 0));
+  FEOS_CUDA(cudaStreamSynchronize(0));
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (status[i]) continue;
+    rho_out[4 * k] = rho[2 * i];
+    rho_out[4 * k + 1] = rho[2 * i + 1];
+    rho_out[4 * k + 2] = 0.0;  // src/pcsaft.rs:95-101 leaves columns 2, 3 at zero
+    rho_out[4 * k + 3] = 0.0;
+    ++k;
+  }
+  *n_ok = k;
+  return 0;
+}
+
+int feos_host_pcsaft_liquid_density(const double* params, const double* temperature, const double* pressure,
+                                    int64_t n, double* rho_out, uint8_t* status, int64_t* n_ok) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31 && n_ok);
+  *n_ok = 0;
+  if (n == 0) return 0;
+  FEOS_ARG(params && temperature && pressure && rho_out && status);
+  DevBuf dp, dt, dpr, drho, dfail;
+  if (dp.alloc(64 * n) || dt.alloc(8 * n) || dpr.alloc(8 * n) || drho.alloc(8 * n) || dfail.alloc(n)) {
+    set_error("cudaMalloc failed for %lld states", (long long)n);
+    return -2;
+  }
+  FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 64 * n, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dpr.p, pressure, 8 * n, cudaMemcpyHostToDevice, 0));
+  int rc = feos_dev_pure_rho_tp_fwd(dp.as<double>(), dt.as<double>(), dpr.as<double>(), n, drho.as<double>(), nullptr,
+                                    dfail.as<uint8_t>(), nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<double> rho((size_t)n);
+  FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 8 * n, cudaMemcpyDeviceToHost, 0));
+  FEOS_CUDA(cudaMemcpyAsync(status, dfail.p, n, cudaMemcpyDeviceToHost, 0));
+  FEOS_CUDA(cudaStreamSynchronize(0));
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (!status[i]) rho_out[k++] = rho[i];
+  *n_ok = k;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+"""``PcSaftPure`` -- same public API as the reference (`/root/reference/feos_torch/pcsaft_pure.py:89-243`),
+computed by the sm_100a kernels behind ``include/feos_b200.h``.
+
+The reference runs a CPU solve (Rust/feos) and then re-evaluates the Helmholtz energy in PyTorch to
+obtain gradients.  Here one forward kernel solves and evaluates the property, and one backward kernel
+applies the implicit-function-theorem gradient; both are wrapped in ``torch.autograd.Function``.
+
+Differences that are not observable through returned values: the model object is not mutated
+(`reduce`, pcsaft_pure.py:235-243), and tensors may live on the CPU -- they are moved to the
+current CUDA device for the computation and the results are returned on the parameters' device.
+"""
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _cuda_device(t):
+    return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+
+def _prep(t, dev):
+    return t.to(device=dev, dtype=torch.float64).contiguous()
+
+
+class _PureVle(torch.autograd.Function):
+    """which = 0: vapor pressure [Pa]; which = 1: saturated liquid density [kmol/m^3]."""
+
+    @staticmethod
+    def forward(ctx, params, temperature, which):
+        n = temperature.shape[0]
+        rho = torch.empty((n, 2), dtype=torch.float64, device=params.device)
+        val = torch.empty((n,), dtype=torch.float64, device=params.device)
+        failed = torch.empty((n,), dtype=torch.uint8, device=params.device)
+        with torch.cuda.device(params.device):
+            _lib.timed_call(
+                "feos_dev_pure_vle_fwd", _lib.ptr(params), _lib.ptr(temperature), n, _lib.ptr(rho),
+                _lib.ptr(val) if which == 0 else None, _lib.ptr(val) if which == 1 else None,
+                _lib.ptr(failed), None, _stream(),
+            )
+        ctx.save_for_backward(params, temperature, rho, failed)
+        ctx.which = which
+        ctx.mark_non_differentiable(rho, failed)
+        return val, rho, failed
+
+    @staticmethod
+    def backward(ctx, g_val, _g_rho, _g_failed):
+        params, temperature, rho, failed = ctx.saved_tensors
+        n = temperature.shape[0]
+        g = g_val.contiguous()
+        grad_params = torch.empty_like(params)
+        grad_t = torch.empty_like(temperature) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(params.device):
+            _lib.timed_call(
+                "feos_dev_pure_vle_bwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(rho), _lib.ptr(failed),
+                _lib.ptr(g) if ctx.which == 0 else None, _lib.ptr(g) if ctx.which == 1 else None, n,
+                _lib.ptr(grad_params), _lib.ptr(grad_t), _stream(),
+            )
+        return grad_params, grad_t, None
+
+
+class _PureRhoTp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, params, temperature, pressure):
+        n = temperature.shape[0]
+        rho = torch.empty((n,), dtype=torch.float64, device=params.device)
+        val = torch.empty((n,), dtype=torch.float64, device=params.device)
+        failed = torch.empty((n,), dtype=torch.uint8, device=params.device)
+        with torch.cuda.device(params.device):
+            _lib.timed_call(
+                "feos_dev_pure_rho_tp_fwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(pressure), n,
+                _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None, _stream(),
+            )
+        ctx.save_for_backward(params, temperature, pressure, rho, failed)
+        ctx.mark_non_differentiable(rho, failed)
+        return val, rho, failed
+
+    @staticmethod
+    def backward(ctx, g_val, _g_rho, _g_failed):
+        params, temperature, pressure, rho, failed = ctx.saved_tensors
+        n = temperature.shape[0]
+        g = g_val.contiguous()
+        need_p, need_t, need_pr = ctx.needs_input_grad
+        grad_params = torch.empty_like(params) if need_p else None
+        grad_t = torch.empty_like(temperature) if need_t else None
+        grad_pr = torch.empty_like(pressure) if need_pr else None
+        with torch.cuda.device(params.device):
+            _lib.timed_call(
+                "feos_dev_pure_rho_tp_bwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(pressure),
+                _lib.ptr(rho), _lib.ptr(failed), _lib.ptr(g), n, _lib.ptr(grad_params), _lib.ptr(grad_t),
+                _lib.ptr(grad_pr), _stream(),
+            )
+        return grad_params, grad_t, grad_pr
+
+
+class PcSaftPure:
+    """parameters [N, 8] = m, sigma, epsilon_k, mu, kappa_ab, epsilon_k_ab, na, nb (README.md:12)."""
+
+    def __init__(self, parameters):
+        if parameters.dim() != 2 or parameters.shape[1] != 8:
+            raise ValueError("parameters must have shape [N, 8]")
+        _lib.load()  # fail loudly before any work if the CUDA extension is missing
+        self._out_device = parameters.device
+        self._dev = _cuda_device(parameters)
+        self._params = _prep(parameters, self._dev)
+        self._source = parameters
+
+    @property
+    def parameters(self):
+        """numpy copy of the parameters (pcsaft_pure.py:104), made on demand: the kernels read the
+        device tensor, so no device->host copy happens on the hot path."""
+        return self._source.detach().cpu().numpy()
+
+    def _back(self, t):
+        return t.to(self._out_device)
+
+    # ---- properties on the phase-equilibrium hot path ------------------------------------------
+    def vapor_pressure(self, temperature):
+        """(failed mask [N], p_sat [n_ok] in Pa) -- pcsaft_pure.py:201-215."""
+        t = _prep(temperature, self._dev)
+        val, _, failed = _PureVle.apply(self._params, t, 0)
+        nans = failed.bool()
+        return self._back(nans), self._back(val[~nans])
+
+    def equilibrium_liquid_density(self, temperature):
+        """(failed mask [N], rho_L^sat [n_ok] in kmol/m^3) -- pcsaft_pure.py:217-233."""
+        t = _prep(temperature, self._dev)
+        val, _, failed = _PureVle.apply(self._params, t, 1)
+        nans = failed.bool()
+        return self._back(nans), self._back(val[~nans])
+
+    def liquid_density(self, temperature, pressure):
+        """(failed mask [N], rho_L(T, p) [n_ok] in kmol/m^3) -- pcsaft_pure.py:184-199."""
+        t = _prep(temperature, self._dev)
+        p = _prep(pressure, self._dev)
+        val, _, failed = _PureRhoTp.apply(self._params, t, p)
+        nans = failed.bool()
+        return self._back(nans), self._back(val[~nans])
+
+    # ---- state functions (values only for now) -----------------------
+    def derivatives(self, temperature, density):
+        """(a, p/kT, d(p/kT)/drho) at (T, rho [1/A^3]) -- pcsaft_pure.py:180-182."""
+        t = _prep(temperature, self._dev)
+        r = _prep(density, self._dev)
+        n = t.shape[0]
+        a, p, dp = (torch.empty((n,), dtype=torch.float64, device=self._dev) for _ in range(3))
+        with torch.cuda.device(self._dev):
+            _lib.call("feos_dev_pure_state", _lib.ptr(self._params.detach()), _lib.ptr(t.detach()), _lib.ptr(r.detach()),
+                      n, _lib.ptr(a), _lib.ptr(p), _lib.ptr(dp), _stream())
+        return self._back(a), self._back(p), self._back(dp)
+
+    def helmholtz_energy(self, temperature, density):
+        """a = A/(V kT) in 1/A^3 -- pcsaft_pure.py:106-178."""
+        return self.derivatives(temperature, density)[0]

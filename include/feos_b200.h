@@ -1,0 +1,99 @@
+/* feos_b200 -- C ABI of the B200-native batched PC-SAFT phase-equilibrium hot path.
+ *
+ * Drop-in boundary for the native layer of feos-torch (Rust/PyO3, /root/reference/src/):
+ * every entry point below replaces one function a maintainer's FFI for this path would bind.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the ABI.  Return value 0 = success,
+ *     negative = error (argument / CUDA runtime / launch); feos_b200_last_error() gives the text
+ *     (thread local).
+ *   - `feos_dev_*`  : all array pointers are DEVICE pointers (current device), work is enqueued on
+ *                     `stream` (a cudaStream_t passed as void*, NULL = legacy default stream) and
+ *                     the call returns without synchronising.  Outputs are FULL LENGTH (n rows):
+ *                     rows of failed states hold NaN and `failed[i] = 1`.
+ *   - `feos_host_*` : array pointers are HOST pointers with exactly the reference's native
+ *                     signature semantics (compacted outputs, bool mask); the call copies to the
+ *                     device, runs the kernels, compacts, copies back and synchronises.
+ *   - parameter rows are [m, sigma/A, epsilon_k/K, mu/D, kappa_ab, epsilon_k_ab/K, na, nb]
+ *     (README.md:12), densities are number densities in 1/Angstrom^3, T in K, pressures in Pa.
+ *   - status / failed: 1 = the solver failed for this state (reference: `status = true`,
+ *     src/pcsaft.rs:93).
+ */
+#ifndef FEOS_B200_H
+#define FEOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* library                                                                                     */
+/* ------------------------------------------------------------------------------------------ */
+const char* feos_b200_version(void);    /* replaces __version__ registered at src/lib.rs:13 */
+const char* feos_b200_last_error(void); /* text of the last error on this thread ("" if none) */
+/* number of kernel launches issued by this process through the library (bench accounting) */
+int64_t feos_b200_launch_count(void);
+/* FP64 FMA-pipe peak of the current device in TFLOP/s from a register-resident DFMA chain kernel on
+ * all SMs (bench.py roofline denominator; blocks until measured). */
+int feos_b200_measure_fp64_peak(int iters, double* tflops);
+
+/* ------------------------------------------------------------------------------------------ */
+/* pure component: PcSaft.vapor_pressure / PcSaft.liquid_density                               */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Pure-component vapour-liquid equilibrium at T.
+ * Replaces PyPcSaft::vapor_pressure -> vapor_pressure_ (src/pcsaft.rs:19-26, :82-103) and fuses the
+ * Newton-step property formulas of PcSaftPure.vapor_pressure / equilibrium_liquid_density
+ * (feos_torch/pcsaft_pure.py:201-233).
+ *   params [n,8], temperature [n]                       in
+ *   rho [n,2]   (rho_V, rho_L) in 1/A^3                  out
+ *   vapor_pressure [n] in Pa            (may be NULL)    out
+ *   liquid_density [n] in kmol/m^3      (may be NULL)    out  (saturated liquid density)
+ *   failed [n]                                           out
+ *   evals [n]  Helmholtz evaluations used (may be NULL)  out  (roofline accounting) */
+int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64_t n, double* rho,
+                          double* vapor_pressure, double* liquid_density, uint8_t* failed, int32_t* evals,
+                          void* stream);
+
+/* Gradient of  sum_i g_vp[i] * vapor_pressure[i] + g_rho[i] * liquid_density[i]  with respect to the
+ * parameters and the temperature at the converged densities (implicit-function theorem); replaces
+ * torch autograd through pcsaft_pure.py:210-215 / :226-233.  g_vp or g_rho may be NULL (= 0).
+ *   grad_params [n,8], grad_temperature [n] (may be NULL)   out; rows of failed states are 0 */
+int feos_dev_pure_vle_bwd(const double* params, const double* temperature, const double* rho,
+                          const uint8_t* failed, const double* g_vp, const double* g_rho, int64_t n,
+                          double* grad_params, double* grad_temperature, void* stream);
+
+/* Liquid density at (T, p).  Replaces PyPcSaft::liquid_density -> liquid_density_
+ * (src/pcsaft.rs:29-41, :105-129) fused with pcsaft_pure.py:196-199.
+ *   rho [n] converged density in 1/A^3, liquid_density [n] in kmol/m^3 (may be NULL) */
+int feos_dev_pure_rho_tp_fwd(const double* params, const double* temperature, const double* pressure,
+                             int64_t n, double* rho, double* liquid_density, uint8_t* failed, int32_t* evals,
+                             void* stream);
+
+/* Gradient of sum_i g[i] * liquid_density[i] w.r.t. parameters, T and p (any output may be NULL). */
+int feos_dev_pure_rho_tp_bwd(const double* params, const double* temperature, const double* pressure,
+                             const double* rho, const uint8_t* failed, const double* g, int64_t n,
+                             double* grad_params, double* grad_temperature, double* grad_pressure,
+                             void* stream);
+
+/* a, p/kT, d(p/kT)/drho at given (T, rho): PcSaftPure.derivatives (pcsaft_pure.py:180-182);
+ * any output may be NULL. */
+int feos_dev_pure_state(const double* params, const double* temperature, const double* density, int64_t n,
+                        double* a, double* p, double* dp, void* stream);
+
+/* Host-buffer entry points with the reference's native signatures.
+ * PcSaft.vapor_pressure(parameters f64[n,8], temperature f64[n]) -> (f64[n_ok,4], bool[n])
+ * (src/pcsaft.rs:19-26): rho_out must hold n*4 doubles, the first *n_ok rows are filled with
+ * (rho_V, rho_L, 0, 0) of the converged states in input order (src/pcsaft.rs:94-101). */
+int feos_host_pcsaft_vapor_pressure(const double* params, const double* temperature, int64_t n,
+                                    double* rho_out, uint8_t* status, int64_t* n_ok);
+/* PcSaft.liquid_density(parameters, temperature, pressure) -> (f64[n_ok], bool[n]) (src/pcsaft.rs:29-41) */
+int feos_host_pcsaft_liquid_density(const double* params, const double* temperature, const double* pressure,
+                                    int64_t n, double* rho_out, uint8_t* status, int64_t* n_ok);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEOS_B200_H */

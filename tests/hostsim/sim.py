@@ -1,0 +1,78 @@
+"""ctypes loader for tests/hostsim/libhostsim.so (CPU build of the kernels' device functions)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def build(force=False):
+    so = os.path.join(HERE, "libhostsim.so")
+    src = os.path.join(HERE, "hostsim.cpp")
+    csrc = os.path.join(HERE, "..", "..", "feos_torch_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-DFEOS_HOST_SIM", "-shared", "-fPIC", "-o", so, src])
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def c64(x):
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def pure_vle(params, T, robust=True):
+    params, T = c64(params), c64(T)
+    n = T.shape[0]
+    rho = np.empty((n, 2)); vp = np.empty(n); rleq = np.empty(n)
+    status = np.empty(n, dtype=np.uint8); evals = np.empty(n, dtype=np.int32)
+    lib().sim_pure_vle(_p(params), _p(T), ctypes.c_int64(n), ctypes.c_int(int(robust)), _p(rho), _p(vp), _p(rleq), _p(status), _p(evals))
+    return rho, vp, rleq, status, evals
+
+
+def pure_vle_bwd(params, T, rho, gv=None, gr=None):
+    params, T, rho = c64(params), c64(T), c64(rho)
+    n = T.shape[0]
+    grad = np.zeros((n, 9))
+    gv = c64(gv) if gv is not None else None
+    gr = c64(gr) if gr is not None else None
+    lib().sim_pure_vle_bwd(_p(params), _p(T), _p(rho), ctypes.c_int64(n), _p(gv), _p(gr), _p(grad))
+    return grad
+
+
+def pure_rho_tp(params, T, P):
+    params, T, P = c64(params), c64(T), c64(P)
+    n = T.shape[0]
+    rho = np.empty(n); val = np.empty(n)
+    status = np.empty(n, dtype=np.uint8); evals = np.empty(n, dtype=np.int32)
+    lib().sim_pure_rho_tp(_p(params), _p(T), _p(P), ctypes.c_int64(n), _p(rho), _p(val), _p(status), _p(evals))
+    return rho, val, status, evals
+
+
+def pure_rho_tp_bwd(params, T, P, rho, g):
+    params, T, P, rho, g = c64(params), c64(T), c64(P), c64(rho), c64(g)
+    n = T.shape[0]
+    grad = np.zeros((n, 9)); gp = np.zeros(n)
+    lib().sim_pure_rho_tp_bwd(_p(params), _p(T), _p(P), _p(rho), ctypes.c_int64(n), _p(g), _p(grad), _p(gp))
+    return grad, gp
+
+
+def pure_state(params, T, rho):
+    params, T, rho = c64(params), c64(T), c64(rho)
+    n = T.shape[0]
+    a = np.empty(n); p = np.empty(n); dp = np.empty(n)
+    lib().sim_pure_state(_p(params), _p(T), _p(rho), ctypes.c_int64(n), _p(a), _p(p), _p(dp))
+    return a, p, dp

@@ -1,0 +1,206 @@
+"""GPU parity tests of the pure-component hot path, through the public API / C ABI.
+
+Bar (BASELINE.json north_star): rel 1e-10 on pressures and densities, 1e-8 on parameter gradients,
+identical converged/failed mask on the test grids."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+def grad_err(got, want):
+    got, want = np.asarray(got), np.asarray(want)
+    scale = np.maximum(np.abs(want).max(axis=1, keepdims=True), 1e-300)
+    return float((np.abs(got - want) / scale).max())
+
+
+@pytest.fixture(scope="module")
+def ft():
+    import __graft_entry__ as g
+
+    g.build()
+    import feos_torch_b200
+
+    return feos_torch_b200
+
+
+def test_readme_known_answer(ft):
+    params = torch.tensor(cases.README_PARAMS, dtype=F64, device="cuda", requires_grad=True)
+    model = ft.PcSaftPure(params.repeat(5, 1))
+    nans, vp = model.vapor_pressure(torch.tensor(cases.README_T, dtype=F64, device="cuda"))
+    assert not nans.any()
+    for got, want in zip(vp.tolist(), cases.README_VP):
+        assert f"{got:.4f}" == f"{want:.4f}"
+    vp[0].backward()
+    for got, want in zip(params.grad.tolist(), cases.README_GRAD):
+        assert f"{got:.4e}" == f"{want:.4e}"
+
+
+@pytest.mark.parametrize("key", ["test_grid", "readme", "seeded_grid"])
+def test_golden_parity(ft, golden_pure, key):
+    e = golden_pure[key]
+    P0 = torch.tensor(e["params"], dtype=F64, device="cuda")
+    T0 = torch.tensor(e["T"], dtype=F64, device="cuda")
+    if "rho" in e:
+        a, p, dp = ft.PcSaftPure(P0).derivatives(T0, torch.tensor(e["rho"], dtype=F64, device="cuda"))
+        assert np.abs(a.cpu().numpy() - e["a"]).max() < 1e-14  # tests/test_pcsaft_pure.py:59-61: 1e-10
+        assert np.abs(p.cpu().numpy() - e["p_red"]).max() < 1e-14
+        assert np.abs(dp.cpu().numpy() - e["dp_red"]).max() < 1e-12
+    for prop in ("vapor_pressure", "liquid_density", "equilibrium_liquid_density"):
+        g = e[prop]
+        x = P0.clone().requires_grad_(True)
+        t = T0.clone().requires_grad_(True)
+        model = ft.PcSaftPure(x)
+        if prop == "liquid_density":
+            pp = torch.tensor(e["p"], dtype=F64, device="cuda", requires_grad=True)
+            nans, val = model.liquid_density(t, pp)
+        else:
+            nans, val = getattr(model, prop)(t)
+        assert nans.cpu().tolist() == g["failed"], prop
+        assert rel(val.detach().cpu(), g["value"]) < 1e-10, prop
+        val.sum().backward()
+        assert grad_err(x.grad.cpu(), g["grad_params"]) < 1e-8, prop
+        assert rel(t.grad.cpu(), g["grad_T"]) < 1e-8, prop
+        if prop == "liquid_density":
+            assert rel(pp.grad.cpu(), g["grad_p"]) < 1e-8
+
+
+def _c2_grid(n, seed, assoc=False):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda k=n: torch.rand(k, generator=g, dtype=F64)
+    m, s, e = 1 + 3 * r(), 3 + r(), 150 + 200 * r()
+    tc = e * (0.6380 + 0.7070 * m - 0.06418 * m * m)
+    tau = 0.5 + 0.45 * r()
+    P = torch.zeros((n, 8), dtype=F64)
+    P[:, 0], P[:, 1], P[:, 2] = m, s, e
+    if assoc:
+        P[:, 4] = torch.exp(np.log(0.003) + r() * np.log(0.1 / 0.003))
+        P[:, 5] = 1500 + 1500 * r()
+        P[:, 6] = 1.0
+        P[:, 7] = 1.0
+    return P, tau * tc, tau
+
+
+@pytest.mark.parametrize("assoc", [False, True])
+def test_matches_oracle_on_seeded_inputs(ft, assoc):
+    from oracle import models as om
+
+    P, T, _ = _c2_grid(192, 11 + int(assoc), assoc)
+    T[-8:] = T[-8:] * 3.0  # super-critical tail -> failed in both
+    if assoc:
+        T[:-8] = T[:-8] * 0.9
+    xo = P.clone().requires_grad_(True)
+    nans_o, vp_o = om.PcSaftPure(xo).vapor_pressure(T)
+    vp_o.sum().backward()
+    xg = P.cuda().requires_grad_(True)
+    nans_g, vp_g = ft.PcSaftPure(xg).vapor_pressure(T.cuda())
+    vp_g.sum().backward()
+    assert nans_g.cpu().tolist() == nans_o.tolist()
+    assert rel(vp_g.detach().cpu(), vp_o.detach()) < 1e-10
+    assert grad_err(xg.grad.cpu(), xo.grad) < 1e-8
+
+    xo = P.clone().requires_grad_(True)
+    nans_o, rl_o = om.PcSaftPure(xo).equilibrium_liquid_density(T)
+    rl_o.sum().backward()
+    xg = P.cuda().requires_grad_(True)
+    nans_g, rl_g = ft.PcSaftPure(xg).equilibrium_liquid_density(T.cuda())
+    rl_g.sum().backward()
+    assert nans_g.cpu().tolist() == nans_o.tolist()
+    assert rel(rl_g.detach().cpu(), rl_o.detach()) < 1e-10
+    assert grad_err(xg.grad.cpu(), xo.grad) < 1e-8
+
+
+def test_full_size_properties(ft):
+    """BASELINE config C2 at full size (1 M states): mask, equilibrium conditions, gradient vs central
+    finite differences of the kernel's own output on a sample."""
+    n = 1_000_000
+    P, T, tau = _c2_grid(n, 5)
+    n_sc = n // 100
+    T[:n_sc] = T[:n_sc] / tau[:n_sc] * 1.3
+    Pg, Tg = P.cuda(), T.cuda()
+    x = Pg.clone().requires_grad_(True)
+    model = ft.PcSaftPure(x)
+    nans, vp = model.vapor_pressure(Tg)
+    assert nans[:n_sc].all() and not nans[n_sc:].any()
+    assert vp.shape[0] == n - n_sc and torch.isfinite(vp).all()
+    vp.sum().backward()
+    assert torch.isfinite(x.grad).all() and (x.grad[:n_sc] == 0).all()
+    # equilibrium conditions at the returned densities (raw native API, numpy)
+    k = 200_000
+    rho, status = ft.PcSaft.vapor_pressure(P[:k].numpy(), T[:k].numpy())
+    assert status[:n_sc].all() and not status[n_sc:k].any()
+    assert rho.shape == (k - n_sc, 4) and (rho[:, 2:] == 0).all()
+    ok = torch.from_numpy(~status)
+    Pk, Tk = Pg[:k][ok.cuda()], Tg[:k][ok.cuda()]
+    m2 = ft.PcSaftPure(Pk)
+    rv, rl = torch.from_numpy(rho[:, 0]).cuda(), torch.from_numpy(rho[:, 1]).cuda()
+    aV, pV, _ = m2.derivatives(Tk, rv)
+    aL, pL, _ = m2.derivatives(Tk, rl)
+    assert ((pL - pV).abs() / pV).max().item() < 1e-9
+    gV = aV / rv + pV / rv + rv.log()
+    gL = aL / rl + pL / rl + rl.log()
+    assert (gV - gL).abs().max().item() < 1e-10
+    # finite-difference check of the gradient (tests/test_pcsaft_pure.py:91-137 uses rel 1e-4)
+    idx = torch.arange(n_sc, n_sc + 64, device="cuda")
+    for col in range(3):
+        h = 1e-6 * Pg[idx, col]
+        Pp, Pm = Pg[idx].clone(), Pg[idx].clone()
+        Pp[:, col] += h
+        Pm[:, col] -= h
+        _, vpp = ft.PcSaftPure(Pp).vapor_pressure(Tg[idx])
+        _, vpm = ft.PcSaftPure(Pm).vapor_pressure(Tg[idx])
+        fd = (vpp - vpm) / (2 * h)
+        assert ((fd - x.grad[idx, col]).abs() / fd.abs()).max().item() < 1e-5
+
+
+def test_liquid_density_full_size(ft):
+    n = 200_000
+    P, T, _ = _c2_grid(n, 6)
+    Pg, Tg = P.cuda(), T.cuda()
+    _, vp = ft.PcSaftPure(Pg).vapor_pressure(Tg)
+    pr = torch.maximum(torch.full_like(vp, 1e6), 1.05 * vp)
+    x = Pg.clone().requires_grad_(True)
+    nans, rho = ft.PcSaftPure(x).liquid_density(Tg, pr)
+    assert not nans.any()
+    # the returned density reproduces the target pressure
+    _, p_red, _ = ft.PcSaftPure(Pg).derivatives(Tg, rho.detach() * (1e3 * 6.02214076e23 * 1e-30))
+    p_pa = p_red * Tg * (1.380649e-23 / 1e-30)
+    assert ((p_pa - pr).abs() / pr).max().item() < 1e-8
+    rho.sum().backward()
+    assert torch.isfinite(x.grad).all()
+    # raw native API
+    rho_n, status = ft.PcSaft.liquid_density(P[:1000].numpy(), T[:1000].numpy(), pr[:1000].cpu().numpy())
+    assert not status.any()
+    assert rel(rho_n / (1e3 * 6.02214076e23 * 1e-30), rho[:1000].detach().cpu()) < 1e-12
+
+
+def test_edge_cases(ft):
+    empty = torch.zeros((0, 8), dtype=F64, device="cuda")
+    nans, vp = ft.PcSaftPure(empty).vapor_pressure(torch.zeros(0, dtype=F64, device="cuda"))
+    assert nans.shape == (0,) and vp.shape == (0,)
+    # a single state, host tensors in -> host tensors out, gradient reaches the host leaf
+    p = torch.tensor([cases.README_PARAMS], dtype=F64, requires_grad=True)
+    nans, vp = ft.PcSaftPure(p).vapor_pressure(torch.tensor([300.0], dtype=F64))
+    assert not vp.is_cuda and f"{vp.item():.4f}" == "216164.6184"
+    vp.sum().backward()
+    assert p.grad is not None and not p.grad.is_cuda
+    # expanded (stride 0) parameters and a failed state in the middle
+    row = torch.tensor(cases.README_PARAMS, dtype=F64, device="cuda", requires_grad=True)
+    T = torch.tensor([300.0, 900.0, 350.0], dtype=F64, device="cuda")
+    nans, vp = ft.PcSaftPure(row.expand(3, 8)).vapor_pressure(T)
+    assert nans.tolist() == [False, True, False] and vp.shape == (2,)
+    vp.sum().backward()
+    assert torch.isfinite(row.grad).all()
+    # all states failed
+    nans, vp = ft.PcSaftPure(row.detach().repeat(4, 1)).vapor_pressure(torch.full((4,), 2000.0, dtype=F64, device="cuda"))
+    assert nans.all() and vp.numel() == 0

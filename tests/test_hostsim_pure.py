@@ -1,0 +1,86 @@
+"""CPU tests of the kernels' per-state device functions (solver, property formulas, gradient passes),
+compiled for the host from the same headers (tests/hostsim), against the golden vectors produced by
+the reference Python.  This exercises the solver logic here in the GPU-less container; the `-m gpu`
+tests repeat the same comparisons through the C ABI on the device."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+import sim  # noqa: E402
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+def grad_err(got, want):
+    want = np.asarray(want)
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    return float((np.abs(got - want) / scale).max())
+
+
+@pytest.mark.parametrize("key", ["test_grid", "readme", "seeded_grid"])
+def test_pure_paths(golden_pure, key):
+    e = golden_pure[key]
+    P, T = np.array(e["params"]), np.array(e["T"])
+    if "rho" in e:
+        a, p, dp = sim.pure_state(P, T, np.array(e["rho"]))
+        assert np.abs(a - e["a"]).max() < 1e-15  # tests/test_pcsaft_pure.py:59-61 asks 1e-10
+        assert np.abs(p - e["p_red"]).max() < 1e-15
+        assert np.abs(dp - e["dp_red"]).max() < 1e-13
+    rho, vp, rleq, st, ev = sim.pure_vle(P, T)
+    failed = st != 0
+    gv, ge, gl = e["vapor_pressure"], e["equilibrium_liquid_density"], e["liquid_density"]
+    assert failed.tolist() == gv["failed"]
+    ok = ~failed
+    assert rel(vp[ok], gv["value"]) < 1e-10
+    assert rel(rleq[ok], ge["value"]) < 1e-10
+    one = np.ones(int(ok.sum()))
+    g = sim.pure_vle_bwd(P[ok], T[ok], rho[ok], gv=one)
+    # golden gradients are full length (rows of failed states are zero)
+    assert grad_err(g[:, :8], np.array(gv["grad_params"])[ok]) < 1e-8
+    assert rel(g[:, 8], np.array(gv["grad_T"])[ok]) < 1e-8
+    g = sim.pure_vle_bwd(P[ok], T[ok], rho[ok], gv=0 * one, gr=one)
+    assert grad_err(g[:, :8], np.array(ge["grad_params"])[ok]) < 1e-8
+    assert rel(g[:, 8], np.array(ge["grad_T"])[ok]) < 1e-8
+    Pr = np.array(e["p"])
+    rho1, val, st, ev = sim.pure_rho_tp(P, T, Pr)
+    failed = st != 0
+    assert failed.tolist() == gl["failed"]
+    ok = ~failed
+    assert rel(val[ok], gl["value"]) < 1e-10
+    g, gp = sim.pure_rho_tp_bwd(P[ok], T[ok], Pr[ok], rho1[ok], np.ones(int(ok.sum())))
+    assert grad_err(g[:, :8], np.array(gl["grad_params"])[ok]) < 1e-8
+    assert rel(g[:, 8], np.array(gl["grad_T"])[ok]) < 1e-8
+    assert rel(gp, np.array(gl["grad_p"])[ok]) < 1e-8
+
+
+def test_pure_vle_large_grid_self_consistent():
+    """BASELINE config C2 shape (non-associating, tau in [0.5, 0.95] plus a super-critical slice):
+    every sub-critical state converges, every super-critical state fails, and the returned densities
+    satisfy p_L = p_V and mu_L = mu_V."""
+    rng = np.random.default_rng(7)
+    n = 20000
+    m, s, e = rng.uniform(1, 4, n), rng.uniform(3, 4, n), rng.uniform(150, 350, n)
+    tc = e * (0.6380 + 0.7070 * m - 0.06418 * m * m)
+    tau = rng.uniform(0.5, 0.95, n)
+    tau[: n // 100] = rng.uniform(1.1, 1.5, n // 100)
+    P = np.zeros((n, 8))
+    P[:, 0], P[:, 1], P[:, 2] = m, s, e
+    T = tau * tc
+    rho, vp, rleq, st, ev = sim.pure_vle(P, T)
+    assert (st[: n // 100] == 1).all()
+    assert (st[n // 100:] == 0).all()
+    ok = st == 0
+    aV, pV, _ = sim.pure_state(P[ok], T[ok], rho[ok, 0])
+    aL, pL, _ = sim.pure_state(P[ok], T[ok], rho[ok, 1])
+    assert rel(pL, pV) < 1e-9
+    # Gibbs energy per molecule: a/rho + p/rho + ln rho (reduced)
+    gV = aV / rho[ok, 0] + pV / rho[ok, 0] + np.log(rho[ok, 0])
+    gL = aL / rho[ok, 1] + pL / rho[ok, 1] + np.log(rho[ok, 1])
+    assert np.abs(gV - gL).max() < 1e-10
+    assert ev[ok].mean() < 30
