@@ -145,15 +145,16 @@ def pure_vle(params, temperature):
     if N == 0:
         return rho_v, rho_l, ~ok
 
-    # 1) ideal-gas start: liquid at 0.75 rho_max -> p0 = rho kT exp(mu_res - p v)
+    # 1) ideal-gas start: p0 = rho kT exp(mu_res - p v) from a liquid-like state at 0.75 rho_max
+    #    (feos: starting_pressure_ideal_gas_bubble), then density iterations at p0 with the liquid
+    #    started at rho_max and the vapour at the ideal gas (feos: new_npt per phase)
     r0 = 0.75 * rho_max
-    p0l, dp0l, _, mu0 = _pure_p_dp(params, T, r0)
+    p0l, _, _, mu0 = _pure_p_dp(params, T, r0)
     p_start = r0 * torch.exp(mu0 - p0l / r0)
-    good = torch.isfinite(p_start) & (p_start > 0) & (dp0l > 0)
-    # density iterations at p_start (Newton with step clamp), vapour from the ideal gas
+    good = torch.isfinite(p_start) & (p_start > 0)
     rv = torch.where(good, p_start, torch.ones_like(p_start) * 1e-10)
-    rl = r0.clone()
-    for _ in range(30):
+    rl = rho_max.clone()
+    for _ in range(40):
         p_v, dp_v, _, _ = _pure_p_dp(params, T, rv)
         p_l, dp_l, _, _ = _pure_p_dp(params, T, rl)
         step_v = (p_start - p_v) / dp_v
