@@ -2,7 +2,8 @@
 phase-equilibrium hot path, exporting the reference's public names
 (`/root/reference/feos_torch/__init__.py:1-4`)."""
 from .native import PcSaft
+from .pcsaft_mix import PcSaftMix
 from .pcsaft_pure import PcSaftPure
 
 __version__ = "0.1.0"
-__all__ = ["PcSaft", "PcSaftPure"]
+__all__ = ["PcSaft", "PcSaftPure", "PcSaftMix"]

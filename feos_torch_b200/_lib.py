@@ -18,11 +18,17 @@ SIGNATURES = {
     "feos_b200_last_error": ([], ctypes.c_char_p),
     "feos_b200_launch_count": ([], _i64),
     "feos_b200_measure_fp64_peak": ([ctypes.c_int, _vp], ctypes.c_int),
+    "feos_dev_compact": ([_vp, _i64, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp], ctypes.c_int),
     "feos_dev_pure_vle_fwd": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_pure_vle_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_vle_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_rho_tp_fwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_pure_rho_tp_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_rho_tp_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_state": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_fwd": ([_vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_state": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_host_pcsaft_bubble_point": ([_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
+    "feos_host_pcsaft_dew_point": ([_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
     "feos_host_pcsaft_vapor_pressure": ([_vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
     "feos_host_pcsaft_liquid_density": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
 }

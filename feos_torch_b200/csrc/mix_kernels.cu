@@ -1,0 +1,286 @@
+// sm_100a kernels and C-ABI entry points of the binary PC-SAFT bubble / dew point path
+// (include/feos_b200.h: feos_dev_mix_*, feos_host_pcsaft_bubble_point / _dew_point).
+//
+//   mix_point_fwd_kernel     one thread per state, fast path (mix_solver.cuh); states it cannot finish
+//                            go to a retry list handled by
+//   mix_point_retry_kernel   the robust path over the compacted retry list;
+//   mix_point_bwd_kernel     gradient of the Newton-step pressure w.r.t. 2x8 parameters, k_ij, eps_AiBj
+//                            and T: 7 passes of 3 dual directions (mix_grad.cuh);
+//   mix_state_kernel         a, p, mu_i, v_i at given (T, rho_1, rho_2)  (PcSaftMix.derivatives).
+#include <vector>
+
+#include "../../include/feos_b200.h"
+#include "common.h"
+#include "mix_grad.cuh"
+
+namespace feos {
+
+constexpr int kMixBlock = 128;
+
+__device__ __forceinline__ void load_mix(const double* __restrict__ params, const double* __restrict__ kij, int64_t i,
+                                         double (&prm)[16], double (&kk)[2]) {
+  const double2* p = reinterpret_cast<const double2*>(params + 16 * i);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double2 t = __ldg(p + k);
+    prm[2 * k] = t.x;
+    prm[2 * k + 1] = t.y;
+  }
+  double2 t = __ldg(reinterpret_cast<const double2*>(kij) + i);
+  kk[0] = t.x;
+  kk[1] = t.y;
+}
+
+template <class Model>
+__device__ __forceinline__ void store_point(int64_t i, int rc, bool bubble, double z0, double T, const PointState& st,
+                                            const PointState& se, const MixEval& es, const MixEval& ei,
+                                            double* __restrict__ rho, double* __restrict__ value,
+                                            uint8_t* __restrict__ failed) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double r[4] = {nan, nan, nan, nan};
+  double val = nan;
+  if (rc == kStatusOk) {
+    double re[4];
+    point_densities(st, bubble, z0, r);
+    point_densities(se, bubble, z0, re);
+    double spec[2], inc[2];
+    if (bubble) { spec[0] = re[2]; spec[1] = re[3]; inc[0] = re[0]; inc[1] = re[1]; }
+    else { spec[0] = re[0]; spec[1] = re[1]; inc[0] = re[2]; inc[1] = re[3]; }
+    val = point_pressure(es, ei.a, spec, inc) * T * kPaPerRed;  // pcsaft_mix.py:443-444
+  }
+  double2* o = reinterpret_cast<double2*>(rho + 4 * i);
+  o[0] = make_double2(r[0], r[1]);
+  o[1] = make_double2(r[2], r[3]);
+  if (value) value[i] = val;
+  failed[i] = (rc == kStatusOk) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(kMixBlock)
+mix_point_fwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
+                     const double* __restrict__ temperature, const double* __restrict__ molefrac, int64_t n, int bubble,
+                     double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
+                     int32_t* __restrict__ evals, int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double prm[16], kk[2];
+  load_mix(params, kij, i, prm, kk);
+  double T = temperature[i], z0 = molefrac[i];
+  PcSaftBinary b;
+  pcsaft_binary_init(b, prm, kk, T);
+  PointState st, se;
+  MixEval es, ei;
+  int ne = 0;
+  int rc = point_fast(b, bubble != 0, z0, st, es, ei, se, ne);
+  if (evals) evals[i] = ne;
+  if (rc == kStatusRetry) {
+    retry_list[atomicAdd(retry_count, 1)] = (int32_t)i;
+    return;
+  }
+  store_point<PcSaftBinary>(i, rc, bubble != 0, z0, T, st, se, es, ei, rho, value, failed);
+}
+
+__global__ void __launch_bounds__(64)
+mix_point_retry_kernel(const double* __restrict__ params, const double* __restrict__ kij,
+                       const double* __restrict__ temperature, const double* __restrict__ molefrac, int bubble,
+                       double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
+                       int32_t* __restrict__ evals, const int32_t* __restrict__ retry_list,
+                       const int32_t* __restrict__ retry_count) {
+  int count = *retry_count;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    int64_t i = retry_list[k];
+    double prm[16], kk[2];
+    load_mix(params, kij, i, prm, kk);
+    double T = temperature[i], z0 = molefrac[i];
+    PcSaftBinary b;
+    pcsaft_binary_init(b, prm, kk, T);
+    PointState st, se;
+    MixEval es, ei;
+    int ne = 0;
+    int rc = point_robust(b, bubble != 0, z0, st, es, ei, se, ne);
+    if (evals) evals[i] += ne;
+    store_point<PcSaftBinary>(i, rc, bubble != 0, z0, T, st, se, es, ei, rho, value, failed);
+  }
+}
+
+__global__ void __launch_bounds__(kMixBlock)
+mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
+                     const double* __restrict__ temperature, const double* __restrict__ rho,
+                     const uint8_t* __restrict__ failed, const int32_t* __restrict__ pos, const double* __restrict__ g,
+                     int64_t n, int bubble, double* __restrict__ grad_params, double* __restrict__ grad_kij,
+                     double* __restrict__ grad_t) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (failed[i]) {
+    if (grad_params) {
+      double2* gp = reinterpret_cast<double2*>(grad_params + 16 * i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gp[k] = make_double2(0.0, 0.0);
+    }
+    if (grad_kij) reinterpret_cast<double2*>(grad_kij)[i] = make_double2(0.0, 0.0);
+    if (grad_t) grad_t[i] = 0.0;
+    return;
+  }
+  double prm[16], kk[2];
+  load_mix(params, kij, i, prm, kk);
+  double T = temperature[i];
+  const double2* rp = reinterpret_cast<const double2*>(rho + 4 * i);
+  double2 rv = rp[0], rl = rp[1];
+  double spec[2], inc[2];
+  if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
+  else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
+  PointWeights q;
+  {
+    PcSaftBinary b;
+    pcsaft_binary_init(b, prm, kk, T);
+    MixEval es = b.eval(spec[0], spec[1]);
+    q = point_weights(es, spec, inc);
+  }
+  double gi = g[pos ? (int64_t)pos[i] : i];
+#pragma unroll 1
+  for (int f = 0; f < 21; f += 3) {
+    double g3[3];
+    mix_point_grad_pass<3>(prm, kk, T, spec, inc, q, f, gi, g3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int d = f + k;
+      if (d < 16) {
+        if (grad_params) grad_params[16 * i + d] = g3[k];
+      } else if (d < 18) {
+        if (grad_kij) grad_kij[2 * i + (d - 16)] = g3[k];
+      } else if (d == 18) {
+        if (grad_t) grad_t[i] = g3[k];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMixBlock)
+mix_state_kernel(const double* __restrict__ params, const double* __restrict__ kij,
+                 const double* __restrict__ temperature, const double* __restrict__ density, int64_t n,
+                 double* __restrict__ a, double* __restrict__ p, double* __restrict__ mu, double* __restrict__ v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double prm[16], kk[2];
+  load_mix(params, kij, i, prm, kk);
+  PcSaftBinary b;
+  pcsaft_binary_init(b, prm, kk, temperature[i]);
+  double2 r = reinterpret_cast<const double2*>(density)[i];
+  MixEval e = b.eval(r.x, r.y);
+  if (a) a[i] = e.a;
+  if (p) p[i] = e.p;
+  if (mu) reinterpret_cast<double2*>(mu)[i] = make_double2(e.mu[0], e.mu[1]);
+  if (v) reinterpret_cast<double2*>(v)[i] = make_double2(e.v[0], e.v[1]);
+}
+
+}  // namespace feos
+
+using namespace feos;
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -2; }
+  template <class T>
+  T* as() { return (T*)p; }
+};
+
+int host_point(const double* params, const double* kij, const double* temperature, const double* molefracs,
+               const double* pressure, int64_t n, int bubble, double* rho_out, uint8_t* status, int64_t* n_ok) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31 && n_ok);
+  *n_ok = 0;
+  if (n == 0) return 0;
+  FEOS_ARG(params && kij && temperature && molefracs && rho_out && status);
+  (void)pressure;  // initial pressure of the reference API: the solver builds its own starting point
+  DevBuf dp, dk, dt, dz, drho, dfail;
+  if (dp.alloc(128 * n) || dk.alloc(16 * n) || dt.alloc(8 * n) || dz.alloc(8 * n) || drho.alloc(32 * n) || dfail.alloc(n)) {
+    set_error("cudaMalloc failed for %lld states", (long long)n);
+    return -2;
+  }
+  FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 128 * n, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dk.p, kij, 16 * n, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dz.p, molefracs, 8 * n, cudaMemcpyHostToDevice, 0));
+  int rc = feos_dev_mix_point_fwd(dp.as<double>(), dk.as<double>(), dt.as<double>(), dz.as<double>(), n, bubble,
+                                  drho.as<double>(), nullptr, dfail.as<uint8_t>(), nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<double> rho(4 * (size_t)n);
+  FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 32 * n, cudaMemcpyDeviceToHost, 0));
+  FEOS_CUDA(cudaMemcpyAsync(status, dfail.p, n, cudaMemcpyDeviceToHost, 0));
+  FEOS_CUDA(cudaStreamSynchronize(0));
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (status[i]) continue;
+    for (int c = 0; c < 4; ++c) rho_out[4 * k + c] = rho[4 * i + c];  // filter_binary, src/pcsaft.rs:216-231
+    ++k;
+  }
+  *n_ok = k;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int feos_dev_mix_point_fwd(const double* params, const double* kij, const double* temperature,
+                           const double* molefracs, int64_t n, int bubble, double* rho, double* pressure,
+                           uint8_t* failed, int32_t* evals, void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  FEOS_ARG(params && kij && temperature && molefracs && rho && failed);
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* ws = nullptr;
+  FEOS_CUDA(cudaMallocAsync((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s));
+  FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
+  mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, s>>>(params, kij, temperature, molefracs, n, bubble, rho,
+                                                                  pressure, failed, evals, ws + 1, ws);
+  FEOS_LAUNCH_OK();
+  int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
+  mix_point_retry_kernel<<<retry_grid, 64, 0, s>>>(params, kij, temperature, molefracs, bubble, rho, pressure, failed,
+                                                  evals, ws + 1, ws);
+  FEOS_LAUNCH_OK();
+  FEOS_CUDA(cudaFreeAsync(ws, s));
+  return 0;
+}
+
+int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
+                           const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble,
+                           double* grad_params, double* grad_kij, double* grad_temperature, void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  FEOS_ARG(params && kij && temperature && rho && failed && g);
+  mix_point_bwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, (cudaStream_t)stream>>>(
+      params, kij, temperature, rho, failed, pos, g, n, bubble, grad_params, grad_kij, grad_temperature);
+  FEOS_LAUNCH_OK();
+  return 0;
+}
+
+int feos_dev_mix_state(const double* params, const double* kij, const double* temperature, const double* density,
+                       int64_t n, double* a, double* p, double* mu, double* v, void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  FEOS_ARG(params && kij && temperature && density);
+  mix_state_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, (cudaStream_t)stream>>>(params, kij, temperature, density, n,
+                                                                                 a, p, mu, v);
+  FEOS_LAUNCH_OK();
+  return 0;
+}
+
+int feos_host_pcsaft_bubble_point(const double* params, const double* kij, const double* temperature,
+                                  const double* liquid_molefracs, const double* pressure, int64_t n, double* rho_out,
+                                  uint8_t* status, int64_t* n_ok) {
+  return host_point(params, kij, temperature, liquid_molefracs, pressure, n, 1, rho_out, status, n_ok);
+}
+
+int feos_host_pcsaft_dew_point(const double* params, const double* kij, const double* temperature,
+                               const double* vapor_molefracs, const double* pressure, int64_t n, double* rho_out,
+                               uint8_t* status, int64_t* n_ok) {
+  return host_point(params, kij, temperature, vapor_molefracs, pressure, n, 0, rho_out, status, n_ok);
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+// Per-state binary bubble / dew point solver, shared by the PC-SAFT mixture kernels (and, through the
+// Model template parameter, by the group-contribution kernels).
+//
+// Replaces what the reference's native layer delegates to the un-vendored feos crate:
+//   PhaseEquilibrium::bubble_point / dew_point(eos, T, [z, 1-z], Some(p0), None, default)
+//   (/root/reference/src/pcsaft.rs:150-214, src/gc_pcsaft.rs:103-171).
+// The returned pressure is second-order insensitive to the solver path, so the
+// algorithm is designed for the GPU:
+//   "specified" phase = the phase whose composition is given (liquid for bubble, vapour for dew):
+//                       one unknown, its total density;
+//   "incipient" phase = the other one: two unknown partial densities.
+//   1. start: density iteration of a liquid at (nearly) zero pressure + ideal-vapour partial pressures
+//      with Poynting correction; for dew points a few successive-substitution rounds on x;
+//   2. Newton on (mu_1, mu_2, p) equalities in the logarithms of the three unknown densities, step
+//      limited to |d ln rho| <= 1, with back-tracking out of mechanically unstable states.
+// Model must provide:  Eval eval(rho0, rho1) (a, mu[2], h00, h01, h11, p, dp[2], v[2]) and
+//                      double max_density(x0) (total density at packing fraction 0.5).
+#pragma once
+#include "pcsaft_mix.cuh"
+#include "pure_solver.cuh"
+
+namespace feos {
+
+struct PointState {
+  double s;       // ln(total density of the specified phase)
+  double u[2];    // ln(partial densities of the incipient phase)
+};
+
+// densities in the order of the native API: (rho_V1, rho_V2, rho_L1, rho_L2), src/pcsaft.rs:225-228
+FD void point_densities(const PointState& st, bool bubble, double z0, double (&rho)[4]) {
+  double rs = exp(st.s);
+  double spec[2] = {rs * z0, rs * (1.0 - z0)};
+  double inc[2] = {exp(st.u[0]), exp(st.u[1])};
+  if (bubble) {
+    rho[0] = inc[0]; rho[1] = inc[1]; rho[2] = spec[0]; rho[3] = spec[1];
+  } else {
+    rho[0] = spec[0]; rho[1] = spec[1]; rho[2] = inc[0]; rho[3] = inc[1];
+  }
+}
+
+// Newton-step bubble/dew pressure (reduced) at fixed densities (pcsaft_mix.py:435-443, :459-467):
+// `es` = evaluation of the specified phase (with derivatives), `a_inc` = a of the incipient phase.
+FD double point_pressure(const MixEval& es, double a_inc, const double (&spec)[2], const double (&inc)[2]) {
+  double ri = inc[0] + inc[1];
+  double w0 = inc[0] / ri, w1 = inc[1] / ri;
+  double v = w0 * es.v[0] + w1 * es.v[1];
+  double g = w0 * (log(inc[0] / spec[0]) - es.mu[0]) + w1 * (log(inc[1] / spec[1]) - es.mu[1]);
+  return -(a_inc / ri + es.p * v + g - 1.0) / (1.0 / ri - v);
+}
+
+FD bool solve3(const double (&J)[3][3], const double (&F)[3], double (&dx)[3]) {
+  double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  if (!(fabs(det) > 0.0)) return false;
+  double id = 1.0 / det;
+  double r0 = -F[0], r1 = -F[1], r2 = -F[2];
+  dx[0] = (r0 * c00 + r1 * (J[0][2] * J[2][1] - J[0][1] * J[2][2]) + r2 * (J[0][1] * J[1][2] - J[0][2] * J[1][1])) * id;
+  dx[1] = (r0 * c01 + r1 * (J[0][0] * J[2][2] - J[0][2] * J[2][0]) + r2 * (J[0][2] * J[1][0] - J[0][0] * J[1][2])) * id;
+  dx[2] = (r0 * c02 + r1 * (J[0][1] * J[2][0] - J[0][0] * J[2][1]) + r2 * (J[0][0] * J[1][1] - J[0][1] * J[1][0])) * id;
+  return true;
+}
+
+// On return kStatusOk: `st` holds the accepted step; (es, ei, st_eval) the last evaluation point.
+template <class Model>
+FD int point_newton(const Model& mdl, bool bubble, double z0, PointState& st, MixEval& es, MixEval& ei,
+                    PointState& st_eval, int max_iter, double max_step, int& evals) {
+  const double z[2] = {z0, 1.0 - z0};
+  PointState prev = st;
+  double dx[3] = {0.0, 0.0, 0.0};
+  bool have_prev = false;
+  int halvings = 0;
+  for (int it = 0; it < max_iter; ++it) {
+    double rs = exp(st.s);
+    double spec[2] = {rs * z[0], rs * z[1]};
+    double inc[2] = {exp(st.u[0]), exp(st.u[1])};
+    es = mdl.eval(spec[0], spec[1]);
+    ei = mdl.eval(inc[0], inc[1]);
+    evals += 2;
+    double ri = inc[0] + inc[1];
+    double dps = z[0] * es.dp[0] + z[1] * es.dp[1];
+    double dpi = (inc[0] * ei.dp[0] + inc[1] * ei.dp[1]) / ri;
+    double rho_l = bubble ? rs : ri, rho_v = bubble ? ri : rs;
+    bool bad = !(dps > 0.0) || !(dpi > 0.0) || !(rho_l > rho_v);
+    if (bad) {
+      if (!have_prev || ++halvings > 10) return kStatusRetry;
+      st.s = prev.s + (dx[0] *= 0.5);
+      st.u[0] = prev.u[0] + (dx[1] *= 0.5);
+      st.u[1] = prev.u[1] + (dx[2] *= 0.5);
+      continue;
+    }
+    halvings = 0;
+    if (fabs(rho_l / rho_v - 1.0) < 1e-5 && fabs(inc[0] / ri - z[0]) < 1e-5) return kStatusRetry;  // trivial
+    double F[3] = {es.mu[0] + log(spec[0]) - ei.mu[0] - st.u[0], es.mu[1] + log(spec[1]) - ei.mu[1] - st.u[1],
+                   es.p - ei.p};
+    double J[3][3];
+    J[0][0] = rs * (z[0] * es.h00 + z[1] * es.h01) + 1.0;
+    J[1][0] = rs * (z[0] * es.h01 + z[1] * es.h11) + 1.0;
+    J[2][0] = rs * dps;
+    J[0][1] = -(ei.h00 * inc[0] + 1.0);
+    J[0][2] = -(ei.h01 * inc[1]);
+    J[1][1] = -(ei.h01 * inc[0]);
+    J[1][2] = -(ei.h11 * inc[1] + 1.0);
+    J[2][1] = -(ei.dp[0] * inc[0]);
+    J[2][2] = -(ei.dp[1] * inc[1]);
+    if (!solve3(J, F, dx)) return kStatusRetry;
+    double mx = fmax(fabs(dx[0]), fmax(fabs(dx[1]), fabs(dx[2])));
+    if (!(mx < 1e300)) return kStatusRetry;
+    if (mx > max_step) {
+      double sc = max_step / mx;
+      dx[0] *= sc; dx[1] *= sc; dx[2] *= sc;
+    }
+    prev = st;
+    st_eval = st;
+    have_prev = true;
+    st.s += dx[0];
+    st.u[0] += dx[1];
+    st.u[1] += dx[2];
+    if (mx <= kVleTol) return kStatusOk;
+  }
+  return kStatusRetry;
+}
+
+// Density iteration of a liquid of composition x towards the pressure of the ideal vapour it would be
+// in equilibrium with; returns ln of the ideal-vapour partial densities (Poynting corrected) in u.
+template <class Model>
+FD int liquid_start(const Model& mdl, double x0, double& rho, double (&u)[2], int max_iter, double tol, int& evals) {
+  const double x[2] = {x0, 1.0 - x0};
+  const double rho_max = mdl.max_density(x0);
+  for (int it = 0; it < max_iter; ++it) {
+    MixEval e = mdl.eval(rho * x[0], rho * x[1]);
+    evals += 1;
+    double dps = x[0] * e.dp[0] + x[1] * e.dp[1];
+    if (!(dps > 0.0)) {
+      // a warm start that landed in the mechanically unstable range: restart from the dense side
+      if (rho < 0.999 * rho_max) {
+        rho = rho_max;
+        continue;
+      }
+      return kStatusRetry;
+    }
+    u[0] = log(rho * x[0]) + e.mu[0] - e.v[0] * e.p;
+    u[1] = log(rho * x[1]) + e.mu[1] - e.v[1] * e.p;
+    double delta = (exp(u[0]) + exp(u[1]) - e.p) / dps;
+    delta = fmax(delta, -0.3 * rho);
+    rho += delta;
+    if (fabs(delta) < tol * rho) return kStatusOk;
+  }
+  return kStatusRetry;
+}
+
+// rounds = number of successive-substitution rounds on the liquid composition (dew point only)
+template <class Model>
+FD int point_solve(const Model& mdl, bool bubble, double z0, int ss_rounds, double start_tol, int newton_iter,
+                   double max_step, PointState& st, MixEval& es, MixEval& ei, PointState& st_eval, int& evals) {
+  if (!(z0 > 0.0) || !(z0 < 1.0)) return kStatusFailed;
+  double u[2];
+  if (bubble) {
+    double rho = mdl.max_density(z0);
+    int rc = liquid_start(mdl, z0, rho, u, 30, start_tol, evals);
+    if (rc != kStatusOk) return rc;
+    st.s = log(rho);
+    st.u[0] = u[0];
+    st.u[1] = u[1];
+  } else {
+    double x0 = z0;
+    double rho = mdl.max_density(x0);
+    double p = 0.0;
+    for (int r = 0; r <= ss_rounds; ++r) {
+      int rc = liquid_start(mdl, x0, rho, u, 30, start_tol, evals);
+      if (rc != kStatusOk) return rc;
+      // ideal vapour: y_i p = x_i kappa_i with kappa_i = exp(u_i) / x_i  ->  x_i = y_i p / kappa_i
+      double t0 = z0 * x0 / exp(u[0]), t1 = (1.0 - z0) * (1.0 - x0) / exp(u[1]);
+      p = 1.0 / (t0 + t1);
+      if (r == ss_rounds) break;
+      double xn = t0 * p;
+      if (!(xn > 0.0) || !(xn < 1.0)) return kStatusRetry;
+      bool done = fabs(xn - x0) < 1e-3 * fmin(xn, 1.0 - xn);
+      // warm start of the next density iteration at (slightly above) the same packing fraction
+      rho = fmin(1.05 * rho * mdl.max_density(xn) / mdl.max_density(x0), mdl.max_density(xn));
+      x0 = xn;
+      if (done) ss_rounds = r + 1;  // one more density iteration at the final composition
+    }
+    if (!(p > 0.0)) return kStatusRetry;
+    st.s = log(p);
+    st.u[0] = log(rho * x0);
+    st.u[1] = log(rho * (1.0 - x0));
+  }
+  return point_newton(mdl, bubble, z0, st, es, ei, st_eval, newton_iter, max_step, evals);
+}
+
+template <class Model>
+FD int point_fast(const Model& mdl, bool bubble, double z0, PointState& st, MixEval& es, MixEval& ei,
+                  PointState& st_eval, int& evals) {
+  return point_solve(mdl, bubble, z0, 2, 0.02, 30, 1.0, st, es, ei, st_eval, evals);
+}
+
+// Retry path: fully converged starting states, many successive-substitution rounds, short Newton steps.
+template <class Model>
+FD int point_robust(const Model& mdl, bool bubble, double z0, PointState& st, MixEval& es, MixEval& ei,
+                    PointState& st_eval, int& evals) {
+  int rc = point_solve(mdl, bubble, z0, 40, 1e-8, 100, 0.3, st, es, ei, st_eval, evals);
+  return rc == kStatusOk ? kStatusOk : kStatusFailed;
+}
+
+// PC-SAFT binary with k_ij as a Model
+struct PcSaftBinary {
+  MixCoef<double> c;
+  double msig3[2];  // pi/6 m_i sigma_i^3
+  FD MixEval eval(double r0, double r1) const { return mix_eval(c, r0, r1); }
+  FD double max_density(double x0) const { return kMaxEta / (x0 * msig3[0] + (1.0 - x0) * msig3[1]); }
+};
+
+FD void pcsaft_binary_init(PcSaftBinary& b, const double (&prm)[16], const double (&kij)[2], double T) {
+  mix_coef<double>(b.c, prm, kij, T, false);
+  b.msig3[0] = kPi / 6.0 * prm[0] * prm[1] * prm[1] * prm[1];
+  b.msig3[1] = kPi / 6.0 * prm[8] * prm[9] * prm[9] * prm[9];
+}
+
+}  // namespace feos

@@ -40,3 +40,26 @@ class PcSaft:
         _lib.call("feos_host_pcsaft_liquid_density", _lib.ptr(p), _lib.ptr(t), _lib.ptr(pr), n, _lib.ptr(rho),
                   _lib.ptr(status), ctypes.cast(ctypes.byref(n_ok), ctypes.c_void_p))
         return rho[: n_ok.value].copy(), status.astype(bool)
+
+    @staticmethod
+    def _point(name, parameters, kij, temperature, molefracs, pressure):
+        p, k, t, z, pr = _f64(parameters), _f64(kij), _f64(temperature), _f64(molefracs), _f64(pressure)
+        n = t.shape[0]
+        if p.shape != (n, 2, 8) or k.shape != (n, 2) or z.shape != (n,):
+            raise ValueError("parameters must have shape [n, 2, 8], kij [n, 2], molefracs [n]")
+        rho = np.empty((n, 4), dtype=np.float64)
+        status = np.empty((n,), dtype=np.uint8)
+        n_ok = ctypes.c_int64(0)
+        _lib.call(name, _lib.ptr(p), _lib.ptr(k), _lib.ptr(t), _lib.ptr(z), _lib.ptr(pr), n, _lib.ptr(rho),
+                  _lib.ptr(status), ctypes.cast(ctypes.byref(n_ok), ctypes.c_void_p))
+        return rho[: n_ok.value].copy(), status.astype(bool)
+
+    @staticmethod
+    def bubble_point(parameters, kij, temperature, liquid_molefracs, pressure):
+        """-> (rho f64[n_ok,4] = (rho_V1, rho_V2, rho_L1, rho_L2) in 1/A^3, failed bool[n]); src/pcsaft.rs:44-60."""
+        return PcSaft._point("feos_host_pcsaft_bubble_point", parameters, kij, temperature, liquid_molefracs, pressure)
+
+    @staticmethod
+    def dew_point(parameters, kij, temperature, vapor_molefracs, pressure):
+        """-> same tuple as bubble_point; src/pcsaft.rs:63-79."""
+        return PcSaft._point("feos_host_pcsaft_dew_point", parameters, kij, temperature, vapor_molefracs, pressure)

@@ -2,8 +2,9 @@
 computed by the sm_100a kernels behind ``include/feos_b200.h``.
 
 The reference runs a CPU solve (Rust/feos) and then re-evaluates the Helmholtz energy in PyTorch to
-obtain gradients.  Here one forward kernel solves and evaluates the property, and one backward kernel
-applies the implicit-function-theorem gradient; both are wrapped in ``torch.autograd.Function``.
+obtain gradients.  Here one forward kernel solves and evaluates the property, a three-launch
+compaction removes the rows of failed states (the reference's return convention), and one backward
+kernel applies the implicit-function-theorem gradient; all wrapped in ``torch.autograd.Function``.
 
 Differences that are not observable through returned values: the model object is not mutated
 (`reduce`, pcsaft_pure.py:235-243), and tensors may live on the CPU -- they are moved to the
@@ -26,29 +27,48 @@ def _prep(t, dev):
     return t.to(device=dev, dtype=torch.float64).contiguous()
 
 
+def compact(failed, values, out_cols=None):
+    """Rows of ``values`` [n] or [n, c] whose state converged, in input order, plus the row map
+    ``pos`` [n] (int32, -1 = failed).  One host synchronisation (the output length)."""
+    n = failed.shape[0]
+    dev = failed.device
+    in_cols = 1 if values.dim() == 1 else values.shape[1]
+    out_cols = in_cols if out_cols is None else out_cols
+    pos = torch.empty((n,), dtype=torch.int32, device=dev)
+    n_ok = torch.empty((1,), dtype=torch.int64, device=dev)
+    out = torch.empty((n, out_cols) if values.dim() == 2 else (n,), dtype=torch.float64, device=dev)
+    _lib.call("feos_dev_compact", _lib.ptr(failed), n, _lib.ptr(pos), _lib.ptr(n_ok), _lib.ptr(values), in_cols,
+              _lib.ptr(out), out_cols, _stream())
+    k = int(n_ok.item())
+    return out[:k], pos
+
+
 class _PureVle(torch.autograd.Function):
-    """which = 0: vapor pressure [Pa]; which = 1: saturated liquid density [kmol/m^3]."""
+    """which = 0: vapor pressure [Pa]; which = 1: saturated liquid density [kmol/m^3].
+    Returns (compacted values [n_ok], failed [n] uint8, rho [n, 2])."""
 
     @staticmethod
     def forward(ctx, params, temperature, which):
         n = temperature.shape[0]
-        rho = torch.empty((n, 2), dtype=torch.float64, device=params.device)
-        val = torch.empty((n,), dtype=torch.float64, device=params.device)
-        failed = torch.empty((n,), dtype=torch.uint8, device=params.device)
-        with torch.cuda.device(params.device):
+        dev = params.device
+        rho = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        val = torch.empty((n,), dtype=torch.float64, device=dev)
+        failed = torch.empty((n,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
             _lib.timed_call(
                 "feos_dev_pure_vle_fwd", _lib.ptr(params), _lib.ptr(temperature), n, _lib.ptr(rho),
                 _lib.ptr(val) if which == 0 else None, _lib.ptr(val) if which == 1 else None,
                 _lib.ptr(failed), None, _stream(),
             )
-        ctx.save_for_backward(params, temperature, rho, failed)
+            out, pos = compact(failed, val)
+        ctx.save_for_backward(params, temperature, rho, failed, pos)
         ctx.which = which
         ctx.mark_non_differentiable(rho, failed)
-        return val, rho, failed
+        return out, failed, rho
 
     @staticmethod
-    def backward(ctx, g_val, _g_rho, _g_failed):
-        params, temperature, rho, failed = ctx.saved_tensors
+    def backward(ctx, g_val, _g_failed, _g_rho):
+        params, temperature, rho, failed, pos = ctx.saved_tensors
         n = temperature.shape[0]
         g = g_val.contiguous()
         grad_params = torch.empty_like(params)
@@ -56,7 +76,7 @@ class _PureVle(torch.autograd.Function):
         with torch.cuda.device(params.device):
             _lib.timed_call(
                 "feos_dev_pure_vle_bwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(rho), _lib.ptr(failed),
-                _lib.ptr(g) if ctx.which == 0 else None, _lib.ptr(g) if ctx.which == 1 else None, n,
+                _lib.ptr(pos), _lib.ptr(g) if ctx.which == 0 else None, _lib.ptr(g) if ctx.which == 1 else None, n,
                 _lib.ptr(grad_params), _lib.ptr(grad_t), _stream(),
             )
         return grad_params, grad_t, None
@@ -66,21 +86,23 @@ class _PureRhoTp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, params, temperature, pressure):
         n = temperature.shape[0]
-        rho = torch.empty((n,), dtype=torch.float64, device=params.device)
-        val = torch.empty((n,), dtype=torch.float64, device=params.device)
-        failed = torch.empty((n,), dtype=torch.uint8, device=params.device)
-        with torch.cuda.device(params.device):
+        dev = params.device
+        rho = torch.empty((n,), dtype=torch.float64, device=dev)
+        val = torch.empty((n,), dtype=torch.float64, device=dev)
+        failed = torch.empty((n,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
             _lib.timed_call(
                 "feos_dev_pure_rho_tp_fwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(pressure), n,
                 _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None, _stream(),
             )
-        ctx.save_for_backward(params, temperature, pressure, rho, failed)
+            out, pos = compact(failed, val)
+        ctx.save_for_backward(params, temperature, pressure, rho, failed, pos)
         ctx.mark_non_differentiable(rho, failed)
-        return val, rho, failed
+        return out, failed, rho
 
     @staticmethod
-    def backward(ctx, g_val, _g_rho, _g_failed):
-        params, temperature, pressure, rho, failed = ctx.saved_tensors
+    def backward(ctx, g_val, _g_failed, _g_rho):
+        params, temperature, pressure, rho, failed, pos = ctx.saved_tensors
         n = temperature.shape[0]
         g = g_val.contiguous()
         need_p, need_t, need_pr = ctx.needs_input_grad
@@ -90,8 +112,8 @@ class _PureRhoTp(torch.autograd.Function):
         with torch.cuda.device(params.device):
             _lib.timed_call(
                 "feos_dev_pure_rho_tp_bwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(pressure),
-                _lib.ptr(rho), _lib.ptr(failed), _lib.ptr(g), n, _lib.ptr(grad_params), _lib.ptr(grad_t),
-                _lib.ptr(grad_pr), _stream(),
+                _lib.ptr(rho), _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, _lib.ptr(grad_params),
+                _lib.ptr(grad_t), _lib.ptr(grad_pr), _stream(),
             )
         return grad_params, grad_t, grad_pr
 
@@ -121,24 +143,21 @@ class PcSaftPure:
     def vapor_pressure(self, temperature):
         """(failed mask [N], p_sat [n_ok] in Pa) -- pcsaft_pure.py:201-215."""
         t = _prep(temperature, self._dev)
-        val, _, failed = _PureVle.apply(self._params, t, 0)
-        nans = failed.bool()
-        return self._back(nans), self._back(val[~nans])
+        val, failed, _ = _PureVle.apply(self._params, t, 0)
+        return self._back(failed.bool()), self._back(val)
 
     def equilibrium_liquid_density(self, temperature):
         """(failed mask [N], rho_L^sat [n_ok] in kmol/m^3) -- pcsaft_pure.py:217-233."""
         t = _prep(temperature, self._dev)
-        val, _, failed = _PureVle.apply(self._params, t, 1)
-        nans = failed.bool()
-        return self._back(nans), self._back(val[~nans])
+        val, failed, _ = _PureVle.apply(self._params, t, 1)
+        return self._back(failed.bool()), self._back(val)
 
     def liquid_density(self, temperature, pressure):
         """(failed mask [N], rho_L(T, p) [n_ok] in kmol/m^3) -- pcsaft_pure.py:184-199."""
         t = _prep(temperature, self._dev)
         p = _prep(pressure, self._dev)
-        val, _, failed = _PureRhoTp.apply(self._params, t, p)
-        nans = failed.bool()
-        return self._back(nans), self._back(val[~nans])
+        val, failed, _ = _PureRhoTp.apply(self._params, t, p)
+        return self._back(failed.bool()), self._back(val)
 
     # ---- state functions (values only for now; SURVEY section 8(f) rank 1) -----------------------
     def derivatives(self, temperature, density):

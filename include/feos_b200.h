@@ -39,6 +39,15 @@ int64_t feos_b200_launch_count(void);
  * all SMs (bench.py roofline denominator; blocks until measured). */
 int feos_b200_measure_fp64_peak(int iters, double* tflops);
 
+/* Order-preserving removal of the rows of failed states (the compaction of src/pcsaft.rs:94-101,
+ * :127-128 and filter_binary :216-231, and of the mask indexing at pcsaft_pure.py:192-194).
+ *   failed [n]                                in
+ *   pos [n]     row i -> output row, -1 if failed (may be NULL)            out
+ *   n_ok        DEVICE scalar: number of converged states                 out
+ *   in [n,in_cols] -> out [n_ok,out_cols], columns >= in_cols are zero (in may be NULL) */
+int feos_dev_compact(const uint8_t* failed, int64_t n, int32_t* pos, int64_t* n_ok, const double* in,
+                     int in_cols, double* out, int out_cols, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* pure component: PcSaft.vapor_pressure / PcSaft.liquid_density                               */
 /* ------------------------------------------------------------------------------------------ */
@@ -60,10 +69,12 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
 /* Gradient of  sum_i g_vp[i] * vapor_pressure[i] + g_rho[i] * liquid_density[i]  with respect to the
  * parameters and the temperature at the converged densities (implicit-function theorem); replaces
  * torch autograd through pcsaft_pure.py:210-215 / :226-233.  g_vp or g_rho may be NULL (= 0).
+ * `pos` (from feos_dev_compact, may be NULL) maps state i to its row in the COMPACTED g arrays;
+ * with pos == NULL the g arrays are full length.
  *   grad_params [n,8], grad_temperature [n] (may be NULL)   out; rows of failed states are 0 */
 int feos_dev_pure_vle_bwd(const double* params, const double* temperature, const double* rho,
-                          const uint8_t* failed, const double* g_vp, const double* g_rho, int64_t n,
-                          double* grad_params, double* grad_temperature, void* stream);
+                          const uint8_t* failed, const int32_t* pos, const double* g_vp, const double* g_rho,
+                          int64_t n, double* grad_params, double* grad_temperature, void* stream);
 
 /* Liquid density at (T, p).  Replaces PyPcSaft::liquid_density -> liquid_density_
  * (src/pcsaft.rs:29-41, :105-129) fused with pcsaft_pure.py:196-199.
@@ -72,9 +83,10 @@ int feos_dev_pure_rho_tp_fwd(const double* params, const double* temperature, co
                              int64_t n, double* rho, double* liquid_density, uint8_t* failed, int32_t* evals,
                              void* stream);
 
-/* Gradient of sum_i g[i] * liquid_density[i] w.r.t. parameters, T and p (any output may be NULL). */
+/* Gradient of sum_i g[i] * liquid_density[i] w.r.t. parameters, T and p (any output may be NULL);
+ * `pos` as above. */
 int feos_dev_pure_rho_tp_bwd(const double* params, const double* temperature, const double* pressure,
-                             const double* rho, const uint8_t* failed, const double* g, int64_t n,
+                             const double* rho, const uint8_t* failed, const int32_t* pos, const double* g, int64_t n,
                              double* grad_params, double* grad_temperature, double* grad_pressure,
                              void* stream);
 
@@ -92,6 +104,41 @@ int feos_host_pcsaft_vapor_pressure(const double* params, const double* temperat
 /* PcSaft.liquid_density(parameters, temperature, pressure) -> (f64[n_ok], bool[n]) (src/pcsaft.rs:29-41) */
 int feos_host_pcsaft_liquid_density(const double* params, const double* temperature, const double* pressure,
                                     int64_t n, double* rho_out, uint8_t* status, int64_t* n_ok);
+
+/* ------------------------------------------------------------------------------------------ */
+/* binary mixture with k_ij: PcSaft.bubble_point / PcSaft.dew_point                            */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Binary bubble (bubble = 1, `molefracs` = liquid x_1) or dew (bubble = 0, vapour y_1) point at T.
+ * Replaces PyPcSaft::bubble_point / dew_point -> bubble_point_ / dew_point_ (src/pcsaft.rs:44-79,
+ * :150-214) and fuses the Newton-step pressure of PcSaftMix.bubble_point / dew_point
+ * (feos_torch/pcsaft_mix.py:422-468).
+ *   params [n,2,8], kij [n,2] = (k_ij, eps_AiBj; 0 = combining rule), temperature [n], molefracs [n]
+ *   rho [n,4] = (rho_V1, rho_V2, rho_L1, rho_L2) in 1/A^3 (filter_binary order, src/pcsaft.rs:225-228)
+ *   pressure [n] in Pa (may be NULL), failed [n], evals [n] (may be NULL) */
+int feos_dev_mix_point_fwd(const double* params, const double* kij, const double* temperature,
+                           const double* molefracs, int64_t n, int bubble, double* rho, double* pressure,
+                           uint8_t* failed, int32_t* evals, void* stream);
+
+/* Gradient of sum_i g[i] * pressure[i] w.r.t. params [n,2,8], kij [n,2] and T [n] (any may be NULL);
+ * replaces torch autograd through pcsaft_mix.py:435-444 / :459-468.  `pos` as for the pure path. */
+int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
+                           const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble,
+                           double* grad_params, double* grad_kij, double* grad_temperature, void* stream);
+
+/* a, p/kT, mu_i^res/kT [n,2], v_i [n,2] at (T, rho [n,2]): PcSaftMix.derivatives (pcsaft_mix.py:395-420). */
+int feos_dev_mix_state(const double* params, const double* kij, const double* temperature, const double* density,
+                       int64_t n, double* a, double* p, double* mu, double* v, void* stream);
+
+/* PcSaft.bubble_point / dew_point(parameters f64[n,2,8], kij f64[n,2], temperature, molefracs, pressure)
+ * -> (f64[n_ok,4], bool[n]) with host buffers (src/pcsaft.rs:44-79).  `pressure` (the reference's
+ * starting value) is accepted and ignored. */
+int feos_host_pcsaft_bubble_point(const double* params, const double* kij, const double* temperature,
+                                  const double* liquid_molefracs, const double* pressure, int64_t n, double* rho_out,
+                                  uint8_t* status, int64_t* n_ok);
+int feos_host_pcsaft_dew_point(const double* params, const double* kij, const double* temperature,
+                               const double* vapor_molefracs, const double* pressure, int64_t n, double* rho_out,
+                               uint8_t* status, int64_t* n_ok);
 
 #ifdef __cplusplus
 }

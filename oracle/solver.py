@@ -279,7 +279,7 @@ def binary_bubble_dew(helm, max_density_fn, temperature, molefrac1, pressure_pa,
     w = z.clone()  # incipient-phase composition estimate
     # initial estimate of the incipient phase from a zero-pressure-like liquid (ideal vapour)
     if bubble:
-        rl = _density_at_p(helm, T, z, p, 0.8 * rmax(z), rmax(z), True)
+        rl = _density_at_p(helm, T, z, p, rmax(z), rmax(z), True)
         _, g, _, p_l, _ = _mix_props(helm, T, rl[:, None] * z)
         part = z * rl[:, None] * torch.exp(g)  # ideal-vapour partial densities
         p = torch.where(torch.isfinite(part.sum(dim=1)) & (part.sum(dim=1) > 0), part.sum(dim=1), p)
@@ -288,22 +288,22 @@ def binary_bubble_dew(helm, max_density_fn, temperature, molefrac1, pressure_pa,
         # find x with y(x) = y for an ideal vapour over a liquid near zero pressure
         s_t = torch.log(z[:, 0] / z[:, 1])
         s = s_t.clone()
-        for _ in range(30):
+        for _ in range(40):
             x1 = torch.sigmoid(s)
             x = torch.stack([x1, 1.0 - x1], dim=1)
-            rl = _density_at_p(helm, T, x, torch.zeros_like(p), 0.8 * rmax(x), rmax(x), True, n_iter=12)
+            rl = _density_at_p(helm, T, x, torch.zeros_like(p), rmax(x), rmax(x), True, n_iter=12)
             _, g, _, _, _ = _mix_props(helm, T, rl[:, None] * x)
-            s = s_t - (g[:, 0] - g[:, 1])
+            s = 0.5 * s + 0.5 * (s_t - (g[:, 0] - g[:, 1]))  # damped: strongly non-ideal pairs oscillate otherwise
         x1 = torch.sigmoid(s)
         w = torch.stack([x1, 1.0 - x1], dim=1)
-        rl = _density_at_p(helm, T, w, torch.zeros_like(p), 0.8 * rmax(w), rmax(w), True, n_iter=12)
+        rl = _density_at_p(helm, T, w, torch.zeros_like(p), rmax(w), rmax(w), True, n_iter=12)
         _, g, _, _, _ = _mix_props(helm, T, rl[:, None] * w)
         part = w * rl[:, None] * torch.exp(g)
         p = torch.where(torch.isfinite(part.sum(dim=1)) & (part.sum(dim=1) > 0), part.sum(dim=1), p)
 
     x_l = z if bubble else w
     y_v = w if bubble else z
-    rho_l = _density_at_p(helm, T, x_l, p, 0.8 * rmax(x_l), rmax(x_l), True)
+    rho_l = _density_at_p(helm, T, x_l, p, rmax(x_l), rmax(x_l), True)
     rho_v = p.clone()
 
     # successive substitution sweeps (moderate count; Newton polish follows)

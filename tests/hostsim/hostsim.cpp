@@ -101,3 +101,74 @@ void sim_pure_state(const double* params, const double* T, const double* rho, in
   }
 }
 }
+
+// ---------------------------------------------------------------------------------------------
+// binary mixtures
+// ---------------------------------------------------------------------------------------------
+#include "../../feos_torch_b200/csrc/mix_grad.cuh"
+
+extern "C" {
+
+void sim_mix_state(const double* params, const double* kij, const double* T, const double* rho, int64_t n, double* a,
+                   double* p, double* mu, double* v) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16], kk[2] = {kij[2 * i], kij[2 * i + 1]};
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    PcSaftBinary b;
+    pcsaft_binary_init(b, prm, kk, T[i]);
+    MixEval e = b.eval(rho[2 * i], rho[2 * i + 1]);
+    a[i] = e.a; p[i] = e.p; mu[2 * i] = e.mu[0]; mu[2 * i + 1] = e.mu[1]; v[2 * i] = e.v[0]; v[2 * i + 1] = e.v[1];
+  }
+}
+
+void sim_mix_point(const double* params, const double* kij, const double* T, const double* z, int64_t n, int bubble,
+                   int use_robust, double* rho /*[n,4]*/, double* value, uint8_t* status, int32_t* evals) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16], kk[2] = {kij[2 * i], kij[2 * i + 1]};
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    PcSaftBinary b;
+    pcsaft_binary_init(b, prm, kk, T[i]);
+    PointState st, se;
+    MixEval es, ei;
+    int ne = 0;
+    int rc = point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
+    if (rc == kStatusRetry && use_robust) rc = point_robust(b, bubble != 0, z[i], st, es, ei, se, ne);
+    status[i] = (uint8_t)rc;
+    evals[i] = ne;
+    if (rc == kStatusOk) {
+      double r[4], re[4];
+      point_densities(st, bubble != 0, z[i], r);
+      point_densities(se, bubble != 0, z[i], re);
+      for (int k = 0; k < 4; ++k) rho[4 * i + k] = r[k];
+      double spec[2], inc[2];
+      if (bubble) { spec[0] = re[2]; spec[1] = re[3]; inc[0] = re[0]; inc[1] = re[1]; }
+      else { spec[0] = re[0]; spec[1] = re[1]; inc[0] = re[2]; inc[1] = re[3]; }
+      value[i] = point_pressure(es, ei.a, spec, inc) * T[i] * kPaPerRed;
+    } else {
+      for (int k = 0; k < 4; ++k) rho[4 * i + k] = NAN;
+      value[i] = NAN;
+    }
+  }
+}
+
+void sim_mix_point_bwd(const double* params, const double* kij, const double* T, const double* rho, int64_t n,
+                       int bubble, const double* g, double* grad /*[n,19]*/) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16], kk[2] = {kij[2 * i], kij[2 * i + 1]};
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    PcSaftBinary b;
+    pcsaft_binary_init(b, prm, kk, T[i]);
+    const double* r = rho + 4 * i;
+    double spec[2], inc[2];
+    if (bubble) { spec[0] = r[2]; spec[1] = r[3]; inc[0] = r[0]; inc[1] = r[1]; }
+    else { spec[0] = r[0]; spec[1] = r[1]; inc[0] = r[2]; inc[1] = r[3]; }
+    MixEval es = b.eval(spec[0], spec[1]);
+    PointWeights q = point_weights(es, spec, inc);
+    for (int f = 0; f < 21; f += 3) {
+      double g3[3];
+      mix_point_grad_pass<3>(prm, kk, T[i], spec, inc, q, f, g[i], g3);
+      for (int k = 0; k < 3; ++k) if (f + k < 19) grad[19 * i + f + k] = g3[k];
+    }
+  }
+}
+}

@@ -76,3 +76,29 @@ def pure_state(params, T, rho):
     a = np.empty(n); p = np.empty(n); dp = np.empty(n)
     lib().sim_pure_state(_p(params), _p(T), _p(rho), ctypes.c_int64(n), _p(a), _p(p), _p(dp))
     return a, p, dp
+
+
+def mix_state(params, kij, T, rho):
+    params, kij, T, rho = c64(params), c64(kij), c64(T), c64(rho)
+    n = T.shape[0]
+    a = np.empty(n); p = np.empty(n); mu = np.empty((n, 2)); v = np.empty((n, 2))
+    lib().sim_mix_state(_p(params), _p(kij), _p(T), _p(rho), ctypes.c_int64(n), _p(a), _p(p), _p(mu), _p(v))
+    return a, p, mu, v
+
+
+def mix_point(params, kij, T, z, bubble, robust=True):
+    params, kij, T, z = c64(params), c64(kij), c64(T), c64(z)
+    n = T.shape[0]
+    rho = np.empty((n, 4)); val = np.empty(n)
+    status = np.empty(n, dtype=np.uint8); evals = np.empty(n, dtype=np.int32)
+    lib().sim_mix_point(_p(params), _p(kij), _p(T), _p(z), ctypes.c_int64(n), ctypes.c_int(int(bubble)),
+                        ctypes.c_int(int(robust)), _p(rho), _p(val), _p(status), _p(evals))
+    return rho, val, status, evals
+
+
+def mix_point_bwd(params, kij, T, rho, bubble, g):
+    params, kij, T, rho, g = c64(params), c64(kij), c64(T), c64(rho), c64(g)
+    n = T.shape[0]
+    grad = np.zeros((n, 19))
+    lib().sim_mix_point_bwd(_p(params), _p(kij), _p(T), _p(rho), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(g), _p(grad))
+    return grad

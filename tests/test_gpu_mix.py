@@ -1,0 +1,180 @@
+"""GPU parity tests of the binary bubble / dew point path, through the public API / C ABI."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+F64 = torch.float64
+NEAR_CRITICAL = {50}      # see tests/test_hostsim_mix.py
+STRONG = (11, 12, 13)
+
+
+@pytest.fixture(scope="module")
+def ft():
+    import __graft_entry__ as g
+
+    g.build()
+    import feos_torch_b200
+
+    return feos_torch_b200
+
+
+def test_state_functions(ft, golden_mix):
+    e = golden_mix["test_grid"]
+    P = torch.tensor(e["params"], dtype=F64, device="cuda")
+    K = torch.tensor(e["kij"], dtype=F64, device="cuda")
+    T = torch.tensor(e["T"], dtype=F64, device="cuda")
+    rho = torch.tensor(e["rho"], dtype=F64, device="cuda")
+    a, p, mu, v = ft.PcSaftMix(P, K).derivatives(T, rho)
+    # tests/test_pcsaft_mix.py:119-124
+    assert np.abs(a.cpu().numpy() - e["a"]).max() < 1e-14
+    assert np.abs(p.cpu().numpy() - e["p_red"]).max() < 1e-14
+    assert np.abs(mu.cpu().numpy() - e["mu"]).max() < 1e-13
+    assert (np.abs(v.cpu().numpy() - e["v"]) / np.abs(e["v"])).max() < 1e-11
+    assert ft.PcSaftMix(P, K).helmholtz_energy_density(T, rho).shape == (len(e["a"]), 1)
+
+
+@pytest.mark.parametrize("key,bubble", [("bubble", True), ("dew", False)])
+def test_category_grid(ft, golden_mix, key, bubble):
+    e = golden_mix["category_grid"]
+    ge = e[key]
+    n = len(e["T"])
+    cat = np.array(e["category"])
+    x = torch.tensor(e["params"], dtype=F64, device="cuda", requires_grad=True)
+    k = torch.tensor(e["kij"], dtype=F64, device="cuda", requires_grad=True)
+    t = torch.tensor(e["T"], dtype=F64, device="cuda", requires_grad=True)
+    z = torch.tensor(e["z"], dtype=F64, device="cuda")
+    p0 = torch.tensor(e["p0"], dtype=F64, device="cuda")
+    model = ft.PcSaftMix(x, k)
+    val, nans = (model.bubble_point if bubble else model.dew_point)(t, z, p0)
+    failed = nans.cpu().numpy()
+    gf = np.array(ge["failed"])
+    strict = np.array([i not in NEAR_CRITICAL and (bubble or cat[i] not in STRONG) for i in range(n)])
+    assert (failed == gf)[strict].all()
+    full = np.full(n, np.nan)
+    full[~failed] = val.detach().cpu().numpy()
+    gv = np.full(n, np.nan)
+    gv[~gf] = ge["value"]
+    both = ~failed & ~gf
+    assert (np.abs(full[both] - gv[both]) / np.abs(gv[both])).max() < 1e-10
+    # gradient of the sum over the states both converged
+    w = torch.zeros(n, dtype=F64, device="cuda")
+    w[torch.from_numpy(both).cuda()] = 1.0
+    (val * w[~nans]).sum().backward()
+    gp = np.array(ge["grad_params"]).reshape(n, 16)[both]
+    got = x.grad.cpu().numpy().reshape(n, 16)[both]
+    assert (np.abs(got - gp) / np.abs(gp).max(axis=1, keepdims=True)).max() < 1e-8
+    gk = np.array(ge["grad_kij"])[both]
+    assert (np.abs(k.grad.cpu().numpy()[both] - gk) / (np.abs(gk).max(axis=1, keepdims=True) + 1e-300)).max() < 1e-8
+    gT = np.array(ge["grad_T"])[both]
+    assert (np.abs(t.grad.cpu().numpy()[both] - gT) / np.abs(gT)).max() < 1e-8
+
+
+def test_reference_configs(ft, golden_mix):
+    """tests/test_pcsaft_mix.py:127-251 (p to 1e-8 Pa; dp/dk_ij)."""
+    for name, cfg, bubble in (("test_bubble_point", cases.MIX_BUBBLE, True), ("test_dew_point", cases.MIX_DEW, False)):
+        g = golden_mix[name]
+        kij = torch.tensor([cfg["kij"]] * 2, dtype=F64, device="cuda", requires_grad=True)
+        params = torch.tensor([cfg["params"]] * 2, dtype=F64, device="cuda")
+        T = torch.tensor([cfg["T"]] * 2, dtype=F64, device="cuda", requires_grad=True)
+        p0 = torch.tensor([cfg["p0"]] * 2, dtype=F64, device="cuda", requires_grad=True)
+        z = torch.tensor([cfg["z"]] * 2, dtype=F64, device="cuda", requires_grad=True)
+        model = ft.PcSaftMix(params, kij)
+        p, nans = (model.bubble_point if bubble else model.dew_point)(T, z, p0)
+        assert not nans.any()
+        assert abs(p[0].item() - g["value"][0]) < 1e-8
+        p[0].backward()
+        gk = np.array(g["grad_kij"])[0]
+        assert np.abs(kij.grad[0].cpu().numpy() - gk).max() < 1e-8 * np.abs(gk).max()
+        assert (kij.grad[1] == 0).all()
+        assert z.grad is None and p0.grad is None  # no gradient for mole fractions / start pressure
+
+
+def test_matches_oracle_on_seeded_inputs(ft):
+    from oracle import models as om
+
+    g = torch.Generator().manual_seed(21)
+    n = 48
+    pa, pb = cases.MIX_DEW["params"]
+    P = torch.tensor([[pa, pb]] * n, dtype=F64)
+    K = torch.zeros((n, 2), dtype=F64)
+    K[:, 0] = -0.05 - 0.1 * torch.rand(n, generator=g, dtype=F64)
+    T = (0.6 + 0.25 * torch.rand(n, generator=g, dtype=F64)) * 150 * 1.2757
+    z = 0.05 + 0.9 * torch.rand(n, generator=g, dtype=F64)
+    p0 = torch.full((n,), 1e5, dtype=F64)
+    for bubble in (True, False):
+        ko = K.clone().requires_grad_(True)
+        mo = om.PcSaftMix(P, ko)
+        vo, no = (mo.bubble_point if bubble else mo.dew_point)(T, z, p0)
+        vo.sum().backward()
+        kg = K.cuda().requires_grad_(True)
+        mg = ft.PcSaftMix(P.cuda(), kg)
+        vg, ng = (mg.bubble_point if bubble else mg.dew_point)(T.cuda(), z.cuda(), p0.cuda())
+        vg.sum().backward()
+        assert ng.cpu().tolist() == no.tolist()
+        assert ((vg.detach().cpu() - vo.detach()).abs() / vo.detach().abs()).max().item() < 1e-10
+        assert ((kg.grad.cpu()[:, 0] - ko.grad[:, 0]).abs() / ko.grad[:, 0].abs()).max().item() < 1e-8
+
+
+def test_full_size_c4(ft):
+    """BASELINE config C4 at full size: 1 M (T, x) states of one shared pair with a shared k_ij leaf;
+    equilibrium conditions at the returned densities, composition constraint, gradient of the fit loss
+    w.r.t. the shared k_ij against central finite differences of the kernel's own output."""
+    n = 1_000_000
+    g = torch.Generator().manual_seed(4)
+    pa, pb = cases.MIX_DEW["params"]
+    pair = torch.tensor([pa, pb], dtype=F64, device="cuda")
+    kij = torch.tensor([-0.1, 0.0], dtype=F64, device="cuda", requires_grad=True)
+    T = ((0.6 + 0.25 * torch.rand(n, generator=g, dtype=F64)) * 150 * 1.2757).cuda()
+    z = (0.05 + 0.9 * torch.rand(n, generator=g, dtype=F64)).cuda()
+    p0 = torch.full((n,), 1e5, dtype=F64, device="cuda")
+    P = pair.expand(n, 2, 8)
+    for bubble in (True, False):
+        kij.grad = None
+        model = ft.PcSaftMix(P, kij.expand(n, 2))
+        p, nans = (model.bubble_point if bubble else model.dew_point)(T, z, p0)
+        assert not nans.any() and torch.isfinite(p).all()
+        target = p.detach() * 1.01
+        loss = ((p - target) ** 2).sum()
+        loss.backward()
+        grad = kij.grad[0].item()
+
+        def loss_at(k):
+            kk = torch.tensor([k, 0.0], dtype=F64, device="cuda")
+            m2 = ft.PcSaftMix(P, kk.expand(n, 2))
+            q, _ = (m2.bubble_point if bubble else m2.dew_point)(T, z, p0)
+            return ((q - target) ** 2).sum().item()
+
+        h = 1e-6
+        fd = (loss_at(-0.1 + h) - loss_at(-0.1 - h)) / (2 * h)
+        assert abs(fd - grad) / abs(fd) < 1e-5
+    # raw native API on a slice: equilibrium conditions
+    k = 100_000
+    Pn = P[:k].contiguous().cpu().numpy()
+    Kn = kij.detach().expand(k, 2).contiguous().cpu().numpy()
+    rho, status = ft.PcSaft.bubble_point(Pn, Kn, T[:k].cpu().numpy(), z[:k].cpu().numpy(), p0[:k].cpu().numpy())
+    assert not status.any() and rho.shape == (k, 4)
+    m3 = ft.PcSaftMix(P[:k], kij.detach().expand(k, 2))
+    r = torch.from_numpy(rho).cuda()
+    _, pV, muV, _ = m3.derivatives(T[:k], r[:, 0:2].contiguous())
+    _, pL, muL, _ = m3.derivatives(T[:k], r[:, 2:4].contiguous())
+    assert ((pV - pL).abs() / r[:, 2:4].sum(dim=1)).max().item() < 1e-12
+    assert (muV + r[:, 0:2].log() - muL - r[:, 2:4].log()).abs().max().item() < 1e-9
+    assert ((r[:, 2] / r[:, 2:4].sum(dim=1)) - z[:k]).abs().max().item() < 1e-12
+
+
+def test_edge_cases(ft):
+    pa, pb = cases.MIX_DEW["params"]
+    P = torch.tensor([[pa, pb]] * 3, dtype=F64, device="cuda")
+    K = torch.tensor([[-0.1, 0.0]] * 3, dtype=F64, device="cuda")
+    T = torch.tensor([150.0, 600.0, 160.0], dtype=F64, device="cuda")  # middle one super-critical
+    z = torch.tensor([0.5, 0.5, 0.3], dtype=F64, device="cuda")
+    p, nans = ft.PcSaftMix(P, K).bubble_point(T, z, torch.full_like(T, 1e5))
+    assert nans.tolist() == [False, True, False] and p.shape == (2,)
+    empty = ft.PcSaftMix(P[:0], K[:0]).dew_point(T[:0], z[:0], T[:0])
+    assert empty[0].shape == (0,) and empty[1].shape == (0,)
+    # host tensors in, host tensors out
+    p2, _ = ft.PcSaftMix(P.cpu(), K.cpu()).bubble_point(T.cpu(), z.cpu(), torch.full((3,), 1e5, dtype=F64))
+    assert not p2.is_cuda and torch.equal(p2, p.cpu())
