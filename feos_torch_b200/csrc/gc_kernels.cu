@@ -1,0 +1,328 @@
+// sm_100a kernels and C-ABI entry points of the group-contribution PC-SAFT bubble / dew point path
+// (include/feos_b200.h: feos_dev_gc_*, feos_host_gc_bubble_point / _dew_point).
+//
+//   gc_point_fwd_kernel / gc_point_retry_kernel   as the PC-SAFT mixture kernels, with the coefficient
+//                            stage of gc_pcsaft.cuh (pair table + segment table, read through L1/L2);
+//   gc_point_bwd_kernel      coefficient adjoints (forward-mode passes over the <= 70 coefficients), then
+//                            dual passes over the inputs of the coefficient stage only; segment-parameter
+//                            and k_ab gradients are SHARED by all states: they are reduced in shared
+//                            memory per block and added to the global accumulators with one atomic per
+//                            entry and block;
+//   gc_state_kernel          a, p, mu_i, v_i at given (T, rho_1, rho_2)  (GcPcSaftMix.derivatives).
+#include <vector>
+
+#include "../../include/feos_b200.h"
+#include "common.h"
+#include "gc_pcsaft.cuh"
+
+static_assert(sizeof(feos_gc_pair) == sizeof(feos::GcPair), "feos_gc_pair layout");
+static_assert(FEOS_GC_MAX_SEG == feos::kGcMaxSeg && FEOS_GC_MAX_BOND == feos::kGcMaxBond, "feos_gc_pair limits");
+
+namespace feos {
+
+constexpr int kGcBlock = 128;
+
+struct GcArgs {
+  const GcPair* pairs;
+  const double* seg_params;
+  const double* kab;
+  const int32_t* pair_index;
+  const double* phi;
+  const double* temperature;
+};
+
+__device__ __forceinline__ GcSource make_source(const GcArgs& g, int64_t i) {
+  GcSource s;
+  s.pair = g.pairs + g.pair_index[i];
+  s.seg_params = g.seg_params;
+  s.kab = g.kab;
+  if (g.phi) {
+    double2 p = __ldg(reinterpret_cast<const double2*>(g.phi) + i);
+    s.phi_[0] = p.x;
+    s.phi_[1] = p.y;
+  } else {
+    s.phi_[0] = s.phi_[1] = 1.0;
+  }
+  s.T_ = g.temperature[i];
+  return s;
+}
+
+__device__ __forceinline__ void store_gc_point(int64_t i, int rc, bool bubble, double z0, double T, const PointState& st,
+                                               const PointState& se, const MixEval& es, const MixEval& ei,
+                                               double* __restrict__ rho, double* __restrict__ value,
+                                               uint8_t* __restrict__ failed) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double r[4] = {nan, nan, nan, nan};
+  double val = nan;
+  if (rc == kStatusOk) {
+    double re[4];
+    point_densities(st, bubble, z0, r);
+    point_densities(se, bubble, z0, re);
+    double spec[2], inc[2];
+    if (bubble) { spec[0] = re[2]; spec[1] = re[3]; inc[0] = re[0]; inc[1] = re[1]; }
+    else { spec[0] = re[0]; spec[1] = re[1]; inc[0] = re[2]; inc[1] = re[3]; }
+    val = point_pressure(es, ei.a, spec, inc) * T * kPaPerRed;  // gc_pcsaft.py:489-490
+  }
+  double2* o = reinterpret_cast<double2*>(rho + 4 * i);
+  o[0] = make_double2(r[0], r[1]);
+  o[1] = make_double2(r[2], r[3]);
+  if (value) value[i] = val;
+  failed[i] = (rc == kStatusOk) ? 0 : 1;
+}
+
+__global__ void __launch_bounds__(kGcBlock)
+gc_point_fwd_kernel(GcArgs g, const double* __restrict__ molefrac, int64_t n, int bubble, double* __restrict__ rho,
+                    double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
+                    int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  GcSource src = make_source(g, i);
+  GcBinary b;
+  gc_binary_init(b, src);
+  double z0 = molefrac[i];
+  PointState st, se;
+  MixEval es, ei;
+  int ne = 0;
+  int rc = point_fast(b, bubble != 0, z0, st, es, ei, se, ne);
+  if (evals) evals[i] = ne;
+  if (rc == kStatusRetry) {
+    retry_list[atomicAdd(retry_count, 1)] = (int32_t)i;
+    return;
+  }
+  store_gc_point(i, rc, bubble != 0, z0, src.T_, st, se, es, ei, rho, value, failed);
+}
+
+__global__ void __launch_bounds__(64)
+gc_point_retry_kernel(GcArgs g, const double* __restrict__ molefrac, int bubble, double* __restrict__ rho,
+                      double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
+                      const int32_t* __restrict__ retry_list, const int32_t* __restrict__ retry_count) {
+  int count = *retry_count;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    int64_t i = retry_list[k];
+    GcSource src = make_source(g, i);
+    GcBinary b;
+    gc_binary_init(b, src);
+    double z0 = molefrac[i];
+    PointState st, se;
+    MixEval es, ei;
+    int ne = 0;
+    int rc = point_robust(b, bubble != 0, z0, st, es, ei, se, ne);
+    if (evals) evals[i] += ne;
+    store_gc_point(i, rc, bubble != 0, z0, src.T_, st, se, es, ei, rho, value, failed);
+  }
+}
+
+__global__ void __launch_bounds__(kGcBlock)
+gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ rho, const uint8_t* __restrict__ failed,
+                    const int32_t* __restrict__ pos, const double* __restrict__ gout, int64_t n, int bubble,
+                    double* __restrict__ grad_seg, double* __restrict__ grad_kab, double* __restrict__ grad_phi,
+                    double* __restrict__ grad_t) {
+  extern __shared__ double acc[];  // [8 n_seg + n_rec] block-level sums of the shared-parameter gradients
+  const int n_acc = 8 * n_seg + n_rec;
+  for (int k = threadIdx.x; k < n_acc; k += blockDim.x) acc[k] = 0.0;
+  __syncthreads();
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    double gphi[2] = {0.0, 0.0}, gt = 0.0;
+    if (!failed[i]) {
+      GcSource src = make_source(g, i);
+      const GcPair& pr = *src.pair;
+      GcBinary b;
+      gc_binary_init(b, src);
+      const double2* rp = reinterpret_cast<const double2*>(rho + 4 * i);
+      double2 rv = rp[0], rl = rp[1];
+      double spec[2], inc[2];
+      if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
+      else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
+      MixEval es = b.eval(spec[0], spec[1]);
+      PointWeights q = point_weights(es, spec, inc);
+      MixEval ei = b.eval(inc[0], inc[1]);
+      double p_red = point_pressure(es, ei.a, spec, inc);
+      // A. coefficient adjoints
+      double cbar[kGcMaxCoef];
+      int ncoef = visit_coef(b.c, [](double&, int) {});
+#pragma unroll 1
+      for (int f = 0; f < ncoef; f += 3) gc_coef_adjoint_pass<3>(b.c, spec, inc, q, f, ncoef, cbar);
+      // B. inputs of the coefficient stage
+      double gi = gout[pos ? (int64_t)pos[i] : i];
+      double scale = gi * src.T_ * kPaPerRed;
+      int n_dir = 8 * pr.nseg + n_rec + 3;
+#pragma unroll 1
+      for (int f = 0; f < n_dir; f += 3) {
+        double g3[3];
+        gc_input_grad_pass<3>(src, n_rec, f, cbar, g3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          int d = f + k;
+          if (d >= n_dir) break;
+          double v = g3[k] * scale;
+          if (d < 8 * pr.nseg) {
+            if (grad_seg && v != 0.0) atomicAdd(&acc[8 * pr.seg[d >> 3] + (d & 7)], v);
+          } else if (d < 8 * pr.nseg + n_rec) {
+            if (grad_kab && v != 0.0) atomicAdd(&acc[8 * n_seg + (d - 8 * pr.nseg)], v);
+          } else if (d < 8 * pr.nseg + n_rec + 2) {
+            gphi[d - 8 * pr.nseg - n_rec] = v;
+          } else {
+            gt = v + gi * p_red * kPaPerRed;  // explicit factor T of p = p_red T kB/A^3
+          }
+        }
+      }
+    }
+    if (grad_phi) reinterpret_cast<double2*>(grad_phi)[i] = make_double2(gphi[0], gphi[1]);
+    if (grad_t) grad_t[i] = gt;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_acc; k += blockDim.x) {
+    double v = acc[k];
+    if (v != 0.0) {
+      if (k < 8 * n_seg) {
+        if (grad_seg) atomicAdd(grad_seg + k, v);
+      } else if (grad_kab) {
+        atomicAdd(grad_kab + (k - 8 * n_seg), v);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGcBlock)
+gc_state_kernel(GcArgs g, const double* __restrict__ density, int64_t n, double* __restrict__ a, double* __restrict__ p,
+                double* __restrict__ mu, double* __restrict__ v) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  GcSource src = make_source(g, i);
+  GcBinary b;
+  gc_binary_init(b, src);
+  double2 r = reinterpret_cast<const double2*>(density)[i];
+  MixEval e = b.eval(r.x, r.y);
+  if (a) a[i] = e.a;
+  if (p) p[i] = e.p;
+  if (mu) reinterpret_cast<double2*>(mu)[i] = make_double2(e.mu[0], e.mu[1]);
+  if (v) reinterpret_cast<double2*>(v)[i] = make_double2(e.v[0], e.v[1]);
+}
+
+}  // namespace feos
+
+using namespace feos;
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -2; }
+  template <class T>
+  T* as() { return (T*)p; }
+};
+
+int check_tables(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg, int32_t n_rec,
+                 const double* kab, const int32_t* pair_index) {
+  FEOS_ARG(pairs && n_pairs > 0 && seg_params && n_seg > 0 && n_rec >= 0 && pair_index);
+  FEOS_ARG(n_rec == 0 || kab);
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                          const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                          const double* temperature, const double* molefracs, int64_t n, int bubble, double* rho,
+                          double* pressure, uint8_t* failed, int32_t* evals, void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  if (int rc = check_tables(pairs, n_pairs, seg_params, n_seg, n_rec, kab, pair_index)) return rc;
+  FEOS_ARG(temperature && molefracs && rho && failed);
+  cudaStream_t s = (cudaStream_t)stream;
+  GcArgs g{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
+  int32_t* ws = nullptr;
+  FEOS_CUDA(cudaMallocAsync((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s));
+  FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
+  gc_point_fwd_kernel<<<grid_for(n, kGcBlock), kGcBlock, 0, s>>>(g, molefracs, n, bubble, rho, pressure, failed, evals,
+                                                              ws + 1, ws);
+  FEOS_LAUNCH_OK();
+  int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
+  gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, bubble, rho, pressure, failed, evals, ws + 1, ws);
+  FEOS_LAUNCH_OK();
+  FEOS_CUDA(cudaFreeAsync(ws, s));
+  return 0;
+}
+
+int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                          const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                          const double* temperature, const double* rho, const uint8_t* failed, const int32_t* pos,
+                          const double* g, int64_t n, int bubble, double* grad_seg_params, double* grad_kab,
+                          double* grad_phi, double* grad_temperature, void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  if (int rc = check_tables(pairs, n_pairs, seg_params, n_seg, n_rec, kab, pair_index)) return rc;
+  FEOS_ARG(temperature && rho && failed && g);
+  GcArgs a{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
+  size_t shmem = sizeof(double) * (size_t)(8 * n_seg + n_rec);
+  FEOS_ARG(shmem <= 48 * 1024);
+  gc_point_bwd_kernel<<<grid_for(n, kGcBlock), kGcBlock, shmem, (cudaStream_t)stream>>>(
+      a, n_seg, n_rec, rho, failed, pos, g, n, bubble, grad_seg_params, grad_kab, grad_phi, grad_temperature);
+  FEOS_LAUNCH_OK();
+  return 0;
+}
+
+int feos_dev_gc_state(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                      const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                      const double* temperature, const double* density, int64_t n, double* a, double* p, double* mu,
+                      double* v, void* stream) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
+  if (n == 0) return 0;
+  if (int rc = check_tables(pairs, n_pairs, seg_params, n_seg, n_rec, kab, pair_index)) return rc;
+  FEOS_ARG(temperature && density);
+  GcArgs g{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
+  gc_state_kernel<<<grid_for(n, kGcBlock), kGcBlock, 0, (cudaStream_t)stream>>>(g, density, n, a, p, mu, v);
+  FEOS_LAUNCH_OK();
+  return 0;
+}
+
+int feos_host_gc_point(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                       const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                       const double* temperature, const double* molefracs, const double* pressure, int64_t n,
+                       int bubble, double* rho_out, uint8_t* status, int64_t* n_ok) {
+  clear_error();
+  FEOS_ARG(n >= 0 && n < (int64_t)1 << 31 && n_ok);
+  *n_ok = 0;
+  if (n == 0) return 0;
+  if (int rc = check_tables(pairs, n_pairs, seg_params, n_seg, n_rec, kab, pair_index)) return rc;
+  FEOS_ARG(temperature && molefracs && rho_out && status);
+  (void)pressure;
+  DevBuf dpairs, dseg, dkab, didx, dphi, dt, dz, drho, dfail;
+  if (dpairs.alloc(sizeof(GcPair) * n_pairs) || dseg.alloc(64 * (size_t)n_seg) || dkab.alloc(8 * (size_t)n_rec) ||
+      didx.alloc(4 * n) || dphi.alloc(16 * n) || dt.alloc(8 * n) || dz.alloc(8 * n) || drho.alloc(32 * n) || dfail.alloc(n)) {
+    set_error("cudaMalloc failed for %lld states", (long long)n);
+    return -2;
+  }
+  FEOS_CUDA(cudaMemcpyAsync(dpairs.p, pairs, sizeof(GcPair) * n_pairs, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dseg.p, seg_params, 64 * (size_t)n_seg, cudaMemcpyHostToDevice, 0));
+  if (n_rec) FEOS_CUDA(cudaMemcpyAsync(dkab.p, kab, 8 * (size_t)n_rec, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(didx.p, pair_index, 4 * n, cudaMemcpyHostToDevice, 0));
+  if (phi) FEOS_CUDA(cudaMemcpyAsync(dphi.p, phi, 16 * n, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
+  FEOS_CUDA(cudaMemcpyAsync(dz.p, molefracs, 8 * n, cudaMemcpyHostToDevice, 0));
+  int rc = feos_dev_gc_point_fwd(dpairs.as<feos_gc_pair>(), n_pairs, dseg.as<double>(), n_seg, dkab.as<double>(), n_rec,
+                                 didx.as<int32_t>(), phi ? dphi.as<double>() : nullptr, dt.as<double>(), dz.as<double>(),
+                                 n, bubble, drho.as<double>(), nullptr, dfail.as<uint8_t>(), nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<double> rho(4 * (size_t)n);
+  FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 32 * n, cudaMemcpyDeviceToHost, 0));
+  FEOS_CUDA(cudaMemcpyAsync(status, dfail.p, n, cudaMemcpyDeviceToHost, 0));
+  FEOS_CUDA(cudaStreamSynchronize(0));
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (status[i]) continue;
+    for (int c = 0; c < 4; ++c) rho_out[4 * k + c] = rho[4 * i + c];
+    ++k;
+  }
+  *n_ok = k;
+  return 0;
+}
+
+}  // extern "C"

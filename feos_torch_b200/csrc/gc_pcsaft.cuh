@@ -1,0 +1,338 @@
+// Heterosegmented group-contribution PC-SAFT for binary mixtures: coefficient stage.
+//
+// Device-side replacement for the per-state set-up of GcPcSaftMix (/root/reference/feos_torch/
+// gc_pcsaft.py:14-86 constructor tensors, :116-253 Helmholtz energy) and of the native per-state
+// `GcPcSaftEosParameters::from_segments(..).phi(..)` (/root/reference/src/gc_pcsaft.rs:116-123).
+//
+// The reference carries dense [N,2,S] segment-count and [N,2,S,S] bond-count tensors over the whole
+// segment table (S = 23: 8.5 KB per state) and loops over all S^2 segment pairs.  Here the host
+// de-duplicates the molecule pairs of a batch into a small table of `GcPair` records that list only
+// the segment types and bonded type pairs that are present (identical value),
+// and every state refers to its pair by index.  Everything that depends on (segment parameters, k_ab,
+// phi, T) is folded into the same coefficient structure the PC-SAFT binary uses (MixCoef with a bond
+// list and the GC association formulas), so the density-dependent evaluation, the bubble/dew solver and
+// the Newton-step pressure are shared with the PcSaftMix path.
+#pragma once
+#include <stdint.h>
+
+#include "mix_grad.cuh"
+
+namespace feos {
+
+constexpr int kGcMaxSeg = 12;   // distinct segment types of one molecule pair
+constexpr int kGcMaxBond = 16;  // distinct bonded segment-type pairs of one molecule pair
+
+struct GcPair {
+  int32_t nseg, nbond;
+  int32_t seg[kGcMaxSeg];                // index into the global segment table
+  double cnt[2][kGcMaxSeg];              // number of segments of that type per molecule (gc_pcsaft.py:26-30)
+  int32_t ba[kGcMaxBond], bb[kGcMaxBond];  // bonded type pairs, local indices (gc_pcsaft.py:32-52)
+  double bcnt[2][kGcMaxBond];            // number of such bonds per molecule
+  int8_t krec[kGcMaxSeg][kGcMaxSeg];     // index of the binary segment record of (a, b) or -1
+};
+
+using GcCoef = MixCoef<double, kGcMaxBond, true>;
+
+// Plain-double source of the inputs of the coefficient stage.
+struct GcSource {
+  const GcPair* pair;
+  const double* seg_params;  // [S, 8] global table
+  const double* kab;         // [R] values of the binary segment records
+  double phi_[2], T_;
+  FD double seg(int a, int j) const { return seg_params[8 * pair->seg[a] + j]; }
+  FD double kab_of(int a, int b) const {
+    int r = pair->krec[a][b];
+    return r < 0 ? 0.0 : kab[r];
+  }
+  FD double phi(int c) const { return phi_[c]; }
+  FD double T() const { return T_; }
+};
+
+// The same inputs carrying K dual directions [first, first + K) of the flat direction list
+//   8 a + j (segment a, parameter j) | 8 nseg + r (record r) | 8 nseg + R + c (phi_c) | 8 nseg + R + 2 (T)
+template <int K>
+struct GcDualSource {
+  GcSource s;
+  int first, nrec;
+  FD DN<K> make(double v, int dir) const {
+    DN<K> x(v);
+#pragma unroll
+    for (int k = 0; k < K; ++k) x.e[k] = (dir == first + k) ? 1.0 : 0.0;
+    return x;
+  }
+  FD DN<K> seg(int a, int j) const { return make(s.seg(a, j), 8 * a + j); }
+  FD DN<K> kab_of(int a, int b) const {
+    int r = s.pair->krec[a][b];
+    return r < 0 ? DN<K>(0.0) : make(s.kab[r], 8 * s.pair->nseg + r);
+  }
+  FD DN<K> phi(int c) const { return make(s.phi_[c], 8 * s.pair->nseg + nrec + c); }
+  FD DN<K> T() const { return make(s.T_, 8 * s.pair->nseg + nrec + 2); }
+};
+
+template <class P, class Src>
+FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& pr) {
+  P T = src.T();
+  P ti = ad_recip(T);
+  const int ns = pr.nseg;
+  P d[kGcMaxSeg];
+  // per-segment diameter (gc_pcsaft.py:118-120) and zeta coefficients (:122-131)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c.z[k][0] = c.z[k][1] = P(0.0);
+  c.m[0] = c.m[1] = P(0.0);
+  for (int a = 0; a < ns; ++a) {
+    P m = src.seg(a, 0), s = src.seg(a, 1), e = src.seg(a, 2);
+    P da = s * (1.0 - 0.12 * ad_exp(-3.0 * (e * ti)));
+    d[a] = da;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double n = pr.cnt[i][a];
+      if (n == 0.0) continue;
+      P md = (kPi / 6.0 * n) * m;
+      c.m[i] = c.m[i] + n * m;
+      c.z[0][i] = c.z[0][i] + md;
+      md = md * da;
+      c.z[1][i] = c.z[1][i] + md;
+      md = md * da;
+      c.z[2][i] = c.z[2][i] + md;
+      c.z[3][i] = c.z[3][i] + md * da;
+    }
+  }
+  // hard chain over bonded type pairs (:156-165)
+  c.nbond = pr.nbond;
+  for (int b = 0; b < pr.nbond; ++b) {
+    P da = d[pr.ba[b]], db = d[pr.bb[b]];
+    c.cd[b] = da * db / (da + db);
+    c.bn[b][0] = P(pr.bcnt[0][b]);
+    c.bn[b][1] = P(pr.bcnt[1][b]);
+  }
+  // dispersion (:177-194): eps_ab = sqrt(eps_a eps_b phi_i phi_j)/T (1 - k_ab [i != j])
+  {
+    P phi0 = src.phi(0), phi1 = src.phi(1);
+    P pp[3] = {phi0 * phi0, phi0 * phi1, phi1 * phi1};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c.q1[k] = c.q2[k] = P(0.0);
+    for (int a = 0; a < ns; ++a) {
+      P ma = src.seg(a, 0), sa = src.seg(a, 1), ea = src.seg(a, 2);
+      for (int b = 0; b < ns; ++b) {
+        P mb = src.seg(b, 0), sb = src.seg(b, 1), eb = src.seg(b, 2);
+        P sab = 0.5 * (sa + sb);
+        P s3 = sab * sab * sab;
+        P ee = ea * eb;
+        P mm = ma * mb;
+        // ij = 00, 01, 11 (the 10 term equals the 01 term by symmetry of k_ab)
+        const int ci[3] = {0, 0, 1}, cj[3] = {0, 1, 1};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double nn = pr.cnt[ci[k]][a] * pr.cnt[cj[k]][b];
+          if (nn == 0.0) continue;
+          // eps = 0 segments (">C<" of the Sauer table): the term and its derivatives are taken as zero
+          // (the reference's sqrt(0) yields NaN gradients there)
+          if (ad_primal(ee) == 0.0) continue;
+          P eab = ad_sqrt(ee * pp[k]) * ti;
+          if (k == 1) eab = eab * (1.0 - src.kab_of(a, b));
+          P t = (nn * mm) * eab * s3;
+          c.q1[k] = c.q1[k] + t;
+          c.q2[k] = c.q2[k] + t * eab;
+        }
+      }
+    }
+  }
+  // molecule-level dipole parameters (:66-73, :255-262): mu2_term = mu2 / T
+  {
+    bool dipolar = false;
+    P sg[2], ep[2], mu2t[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      P ms3(0.0), me(0.0), mu2(0.0);
+      for (int a = 0; a < ns; ++a) {
+        double n = pr.cnt[i][a];
+        if (n == 0.0) continue;
+        P m = src.seg(a, 0), s = src.seg(a, 1), e = src.seg(a, 2), mu = src.seg(a, 3);
+        ms3 = ms3 + (n * m) * (s * s * s);
+        me = me + (n * m) * e;
+        mu2 = mu2 + n * (mu * mu);
+        if (ad_primal(mu) != 0.0) dipolar = true;
+      }
+      P mi = ad_recip(c.m[i]);
+      sg[i] = ad_cbrt_pos(ms3 * mi);
+      ep[i] = me * mi;
+      mu2t[i] = mu2 * mi * kDipoleScale * ti;
+    }
+    dipole_coef(c, c.m, sg, ep, mu2t, ti, dipolar);
+  }
+  // association: at most one associating segment per molecule (:76-86), categories (:212-251)
+  {
+    P sa[2], ea[2], kap[2], eab[2];
+    int n_assoc = 0, n_self = 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      sa[i] = ea[i] = kap[i] = eab[i] = c.na[i] = c.nb[i] = P(0.0);
+      for (int a = 0; a < ns; ++a) {
+        double n = pr.cnt[i][a];
+        if (n == 0.0) continue;
+        P k = src.seg(a, 4), e = src.seg(a, 5);
+        double sign = (ad_primal(k) * ad_primal(e) > 0.0) ? 1.0 : ((ad_primal(k) * ad_primal(e) < 0.0) ? -1.0 : 0.0);
+        sa[i] = sa[i] + (n * sign) * src.seg(a, 1);
+        ea[i] = ea[i] + (n * sign) * src.seg(a, 2);
+        kap[i] = kap[i] + n * k;
+        eab[i] = eab[i] + n * e;
+        c.na[i] = c.na[i] + n * src.seg(a, 6);
+        c.nb[i] = c.nb[i] + n * src.seg(a, 7);
+      }
+      double ke = ad_primal(kap[i]) * ad_primal(eab[i]);
+      c.sgn[i] = ke > 0.0 ? 1.0 : (ke < 0.0 ? -1.0 : 0.0);
+      n_assoc += (ke != 0.0);
+      n_self += (ad_primal(c.na[i]) * ad_primal(c.nb[i]) != 0.0);
+    }
+    c.cat = kAssocNone;
+    if (n_assoc == 1 && n_self == 1) c.cat = kAssocSelf;
+    if (n_assoc == 2 && n_self == 2) c.cat = kAssocCross;
+    if (n_assoc == 2 && n_self == 1) c.cat = kAssocInduced;
+    if (c.cat == kAssocSelf) {
+      // :309-330 -- sigma, eps, kappa, eps_ab summed over the two molecules (one of them contributes)
+      P s = sa[0] + sa[1], e = ea[0] + ea[1], k = kap[0] + kap[1], eb = eab[0] + eab[1];
+      P dg = s * (1.0 - 0.12 * ad_exp(-3.0 * (e * ti)));
+      c.dlt0[0] = ad_sqrt(s * s) * (s * s) * ad_sqrt(k * k) * (ad_exp(eb * ti) - 1.0);
+      c.dd[0] = dg * dg / (dg + dg);
+    } else if (c.cat != kAssocNone) {
+      P dg[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) dg[i] = sa[i] * (1.0 - 0.12 * ad_exp(-3.0 * (ea[i] * ti)));
+      const int di_[4] = {0, 0, 1, 1}, dj_[4] = {0, 1, 0, 1};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        int i = di_[k], j = dj_[k];
+        P ss = sa[i] * sa[j];
+        c.dlt0[k] = ad_sqrt(ss) * ss * ad_sqrt(kap[i] * kap[j]) * (ad_exp((0.5 * (eab[i] + eab[j])) * ti) - 1.0);
+        c.dd[k] = dg[i] * dg[j] / (dg[i] + dg[j]);
+      }
+    }
+  }
+}
+
+// Visits every scalar coefficient of a MixCoef in a fixed order (the flat coefficient index used by
+// the gradient kernels).  Returns the number of coefficients.
+template <class C, class F>
+FD int visit_coef(C& c, F&& f) {
+  int idx = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f(c.z[k][0], idx++);
+    f(c.z[k][1], idx++);
+  }
+  f(c.m[0], idx++);
+  f(c.m[1], idx++);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) f(c.q1[k], idx++);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) f(c.q2[k], idx++);
+  for (int b = 0; b < c.nbond; ++b) f(c.cd[b], idx++);
+  if (c.dipolar) {
+    f(c.mu2t[0], idx++);
+    f(c.mu2t[1], idx++);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      f(c.pw1[k], idx++);
+      f(c.pw2[k], idx++);
+      f(c.pe[k], idx++);
+      f(c.ps[k], idx++);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      f(c.tw1[k], idx++);
+      f(c.tw2[k], idx++);
+      f(c.ts[k], idx++);
+    }
+  }
+  if (c.cat != kAssocNone) {
+    int n = (c.cat == kAssocSelf) ? 1 : 4;
+    for (int k = 0; k < n; ++k) {
+      f(c.dlt0[k], idx++);
+      f(c.dd[k], idx++);
+    }
+    f(c.na[0], idx++);
+    f(c.na[1], idx++);
+    f(c.nb[0], idx++);
+    f(c.nb[1], idx++);
+  }
+  return idx;
+}
+constexpr int kGcMaxCoef = 8 + 2 + 6 + kGcMaxBond + 26 + 12;
+
+// copy of the primal coefficients carrying K dual directions over the flat coefficient index
+template <int K>
+FD void seed_coef(MixCoef<DN<K>, kGcMaxBond, true>& cd, const GcCoef& c, int first) {
+  cd.nbond = c.nbond;
+  cd.dipolar = c.dipolar;
+  cd.cat = c.cat;
+  cd.sgn[0] = c.sgn[0];
+  cd.sgn[1] = c.sgn[1];
+  for (int b = 0; b < c.nbond; ++b) {
+    cd.bn[b][0] = DN<K>(c.bn[b][0]);
+    cd.bn[b][1] = DN<K>(c.bn[b][1]);
+  }
+  // walk both structures in the same order
+  double vals[kGcMaxCoef];
+  int n = visit_coef(const_cast<GcCoef&>(c), [&](double& x, int i) { vals[i] = x; });
+  (void)n;
+  visit_coef(cd, [&](DN<K>& x, int i) {
+    x = DN<K>(vals[i]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) x.e[k] = (i == first + k) ? 1.0 : 0.0;
+  });
+}
+
+struct GcBinary {
+  GcCoef c;
+  double msig3[2];
+  FD MixEval eval(double r0, double r1) const { return mix_eval<kGcMaxBond, true>(c, r0, r1); }
+  FD double max_density(double x0) const { return kMaxEta / (x0 * msig3[0] + (1.0 - x0) * msig3[1]); }
+};
+
+FD void gc_binary_init(GcBinary& b, const GcSource& src) {
+  const GcPair& pr = *src.pair;
+  gc_coef<double, GcSource>(b.c, src, pr);
+  b.msig3[0] = b.msig3[1] = 0.0;
+  for (int a = 0; a < pr.nseg; ++a) {
+    double s = src.seg(a, 1);
+    double ms3 = kPi / 6.0 * src.seg(a, 0) * s * s * s;
+    b.msig3[0] += pr.cnt[0][a] * ms3;
+    b.msig3[1] += pr.cnt[1][a] * ms3;
+  }
+}
+
+// ---- gradient of the Newton-step bubble/dew pressure -------------------------------------------
+// Step A: adjoints of the reduced pressure with respect to the coefficients, K coefficient directions
+// per pass (same formula as mix_grad.cuh).  cbar[idx] = d p_red / d coef[idx].
+template <int K>
+FD void gc_coef_adjoint_pass(const GcCoef& c, const double (&spec)[2], const double (&inc)[2], const PointWeights& q,
+                             int first, int ncoef, double* cbar) {
+  MixCoef<DN<K>, kGcMaxBond, true> cd;
+  seed_coef<K>(cd, c, first);
+  DN<K> a_inc = mix_helmholtz<DN<K>, DN<K>, kGcMaxBond, true>(cd, DN<K>(inc[0]), DN<K>(inc[1]));
+  D1T<DN<K>> r0(DN<K>(spec[0]), DN<K>(q.dir[0])), r1(DN<K>(spec[1]), DN<K>(q.dir[1]));
+  D1T<DN<K>> A = mix_helmholtz<DN<K>, D1T<DN<K>>, kGcMaxBond, true>(cd, r0, r1);
+  DN<K> N = a_inc * (1.0 / q.rho_inc) - A.re * q.v + A.d1 + q.cst;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (first + k < ncoef) cbar[first + k] = -N.e[k] / q.denom;
+}
+
+// Step B: K input directions [first, first + K): out[k] = sum_idx cbar[idx] d coef[idx] / d direction
+template <int K>
+FD void gc_input_grad_pass(const GcSource& src, int nrec, int first, const double* cbar, double (&out)[K]) {
+  GcDualSource<K> ds;
+  ds.s = src;
+  ds.first = first;
+  ds.nrec = nrec;
+  MixCoef<DN<K>, kGcMaxBond, true> cd;
+  gc_coef<DN<K>, GcDualSource<K>>(cd, ds, *src.pair);
+#pragma unroll
+  for (int k = 0; k < K; ++k) out[k] = 0.0;
+  visit_coef(cd, [&](DN<K>& x, int i) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] += cbar[i] * x.e[k];
+  });
+}
+
+}  // namespace feos

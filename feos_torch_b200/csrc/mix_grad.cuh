@@ -62,9 +62,9 @@ FD void mix_point_grad_pass(const double (&prm)[16], const double (&kij)[2], dou
   mix_seed<K>(prm, kij, T, first, p, k, t);
   MixCoef<DN<K>> c;
   mix_coef<DN<K>>(c, p, k, t, true);
-  DN<K> a_inc = mix_helmholtz<DN<K>, DN<K>>(c, DN<K>(inc[0]), DN<K>(inc[1]));
+  DN<K> a_inc = mix_helmholtz<DN<K>, DN<K>, 2, false>(c, DN<K>(inc[0]), DN<K>(inc[1]));
   D1T<DN<K>> r0(DN<K>(spec[0]), DN<K>(q.dir[0])), r1(DN<K>(spec[1]), DN<K>(q.dir[1]));
-  D1T<DN<K>> A = mix_helmholtz<DN<K>, D1T<DN<K>>>(c, r0, r1);
+  D1T<DN<K>> A = mix_helmholtz<DN<K>, D1T<DN<K>>, 2, false>(c, r0, r1);
   DN<K> N = a_inc * (1.0 / q.rho_inc) - A.re * q.v + A.d1 + q.cst;
   DN<K> val = (N * (-1.0 / q.denom)) * t * kPaPerRed;
 #pragma unroll

@@ -20,11 +20,18 @@ namespace feos {
 
 enum : int { kAssocNone = 0, kAssocSelf = 1, kAssocCross = 2, kAssocInduced = 3 };
 
-template <class P>
+// NB = capacity of the bond-type list of the hard-chain term, GC = group-contribution association
+// formulas.  A homosegmented PC-SAFT binary is the special case NB = 2 with one "bond type" per
+// component: contact distance d_i / 2 and m_i - 1 bonds (pcsaft_mix.py:63-65 == gc_pcsaft.py:156-165).
+template <class P, int NB = 2, bool GC = false>
 struct MixCoef {
-  // hard sphere / hard chain: zeta_k = sum_i z[k][i] rho_i
+  // hard sphere: zeta_k = sum_i z[k][i] rho_i
   P z[4][2];
-  P m[2], mm1[2], d[2];
+  P m[2];  // segments per molecule
+  // hard chain: a_hc = - sum_b (rho_0 bn[b][0] + rho_1 bn[b][1]) ln g(cd[b])
+  int nbond;
+  P cd[NB];     // d_a d_b / (d_a + d_b)
+  P bn[NB][2];  // number of bonds of this type per molecule
   // dispersion: rho1mix = sum q1[ij] rho_i rho_j (ij = 00, 01 (both orders), 11), rho2mix with q2
   P q1[3], q2[3];
   // dipole: phi2 = sum pair terms, phi3 = sum triplet terms
@@ -37,6 +44,7 @@ struct MixCoef {
   P dlt0[4];   // (sigma_i sigma_j)^1.5 sqrt(kappa_i kappa_j) (exp(eps_AiBj / T) - 1), ij = 00, 01, 10, 11
   P dd[4];     // d_i d_j / (d_i + d_j)
   P na[2], nb[2];
+  double sgn[2];  // GC: 1 if the component carries the associating segment (gc_pcsaft.py:317-320)
 };
 
 template <class P>
@@ -49,11 +57,51 @@ FD DN<N> ad_cbrt_pos(const DN<N>& x) {
   return x.chain(c, c / (3.0 * x.re));
 }
 
+// Gross-Vrabec dipole coefficients from molecule-level m, sigma, eps and mu2_term = (reduced mu^2)/T
+// (pcsaft_mix.py:156-208, gc_pcsaft.py:255-307)
+template <class C, class P>
+FD void dipole_coef(C& c, const P (&m)[2], const P (&sig)[2], const P (&eps)[2], const P (&mu2t)[2], const P& ti,
+                    bool dipolar) {
+  c.dipolar = dipolar;
+  if (!dipolar) return;
+  P mc[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    c.mu2t[i] = mu2t[i];
+    mc[i] = ad_clamp_max(m[i], 2.0);
+  }
+  const int pi_[3] = {0, 0, 1}, pj_[3] = {0, 1, 1};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int i = pi_[k], j = pj_[k];
+    P sij = 0.5 * (sig[i] + sig[j]);
+    P mij = ad_sqrt(mc[i] * mc[j]);
+    P mi = ad_recip(mij);
+    c.pw1[k] = (mij - 1.0) * mi;
+    c.pw2[k] = c.pw1[k] * (mij - 2.0) * mi;
+    c.pe[k] = ad_sqrt(eps[i] * eps[j]) * ti;
+    c.ps[k] = ad_recip(sij * sij * sij) * (i == j ? 1.0 : 2.0);
+  }
+  const int ti_[4] = {0, 0, 0, 1}, tj_[4] = {0, 0, 1, 1}, tk_[4] = {0, 1, 1, 1};
+  const double mult[4] = {1.0, 3.0, 3.0, 1.0};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int i = ti_[t], j = tj_[t], k = tk_[t];
+    P sij = 0.5 * (sig[i] + sig[j]), sik = 0.5 * (sig[i] + sig[k]), sjk = 0.5 * (sig[j] + sig[k]);
+    P mijk = ad_cbrt_pos(mc[i] * mc[j] * mc[k]);
+    P mi = ad_recip(mijk);
+    c.tw1[t] = (mijk - 1.0) * mi;
+    c.tw2[t] = c.tw1[t] * (mijk - 2.0) * mi;
+    c.ts[t] = ad_recip(sij * sik * sjk) * mult[t];
+  }
+}
+
 // prm: 16 values = 2 rows of [m, sigma, eps, mu, kappa_ab, eps_ab, na, nb]; kij = (k_ij, eps_AiBj)
 template <class P>
 FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& T, bool grad_mode) {
   P ti = ad_recip(T);
-  P s3[2], eps[2], sig[2];
+  P s3[2], eps[2], sig[2], dseg[2];
+  c.nbond = 2;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     P m = prm[8 * i], s = prm[8 * i + 1], e = prm[8 * i + 2];
@@ -62,8 +110,10 @@ FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& 
     s3[i] = s * s * s;
     P d = s * (1.0 - 0.12 * ad_exp(-3.0 * (e * ti)));  // pcsaft_mix.py:33
     c.m[i] = m;
-    c.mm1[i] = m - 1.0;
-    c.d[i] = d;
+    dseg[i] = d;
+    c.cd[i] = 0.5 * d;
+    c.bn[i][i] = m - 1.0;
+    c.bn[i][1 - i] = P(0.0);
     P md = (kPi / 6.0) * m;
     c.z[0][i] = md;
     md = md * d;
@@ -85,42 +135,16 @@ FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& 
     c.q2[2] = c.q1[2] * e11;
   }
   // dipole (:111-115, :156-208)
-  double mu0 = ad_primal(prm[3]), mu1 = ad_primal(prm[11]);
-  c.dipolar = (mu0 * mu0 > 0.0) || (mu1 * mu1 > 0.0);
-  if (c.dipolar) {
-    P mc[2];
+  {
+    P mu2t[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       P mu = prm[8 * i + 3];
       // mu2 = mu^2 / (m sigma^3 eps) * 1e-19 J/K/kB (:17-22); mu2_term = sigma^3 eps mu2 / T (:163)
       P mu2 = mu * mu / (c.m[i] * s3[i] * eps[i]) * kDipoleScale;
-      c.mu2t[i] = s3[i] * eps[i] * mu2 * ti;
-      mc[i] = ad_clamp_max(c.m[i], 2.0);
+      mu2t[i] = s3[i] * eps[i] * mu2 * ti;
     }
-    const int pi_[3] = {0, 0, 1}, pj_[3] = {0, 1, 1};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      int i = pi_[k], j = pj_[k];
-      P sij = 0.5 * (sig[i] + sig[j]);
-      P mij = ad_sqrt(mc[i] * mc[j]);
-      P mi = ad_recip(mij);
-      c.pw1[k] = (mij - 1.0) * mi;
-      c.pw2[k] = c.pw1[k] * (mij - 2.0) * mi;
-      c.pe[k] = ad_sqrt(eps[i] * eps[j]) * ti;
-      c.ps[k] = ad_recip(sij * sij * sij) * (i == j ? 1.0 : 2.0);
-    }
-    const int ti_[4] = {0, 0, 0, 1}, tj_[4] = {0, 0, 1, 1}, tk_[4] = {0, 1, 1, 1};
-    const double mult[4] = {1.0, 3.0, 3.0, 1.0};
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      int i = ti_[t], j = tj_[t], k = tk_[t];
-      P sij = 0.5 * (sig[i] + sig[j]), sik = 0.5 * (sig[i] + sig[k]), sjk = 0.5 * (sig[j] + sig[k]);
-      P mijk = ad_cbrt_pos(mc[i] * mc[j] * mc[k]);
-      P mi = ad_recip(mijk);
-      c.tw1[t] = (mijk - 1.0) * mi;
-      c.tw2[t] = c.tw1[t] * (mijk - 2.0) * mi;
-      c.ts[t] = ad_recip(sij * sik * sjk) * mult[t];
-    }
+    dipole_coef(c, c.m, sig, eps, mu2t, ti, ad_primal(prm[3]) != 0.0 || ad_primal(prm[11]) != 0.0);
   }
   // association categories (:118-152)
   {
@@ -135,6 +159,7 @@ FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& 
     c.nb[0] = prm[7];
     c.na[1] = prm[14];
     c.nb[1] = prm[15];
+    c.sgn[0] = c.sgn[1] = 0.0;
     (void)grad_mode;
     if (c.cat == kAssocSelf) {
       // :210-239 -- kappa, eps_ab summed over components, sigma and d weighted with na
@@ -143,7 +168,7 @@ FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& 
       P nas = c.na[0] + c.na[1];
       P nai = ad_recip(nas);
       P sg = (c.na[0] * sig[0] + c.na[1] * sig[1]) * nai;
-      P dg = (c.na[0] * c.d[0] + c.na[1] * c.d[1]) * nai;
+      P dg = (c.na[0] * dseg[0] + c.na[1] * dseg[1]) * nai;
       // (sigma sigma)^1.5 sqrt(kappa kappa) = sigma^3 kappa
       c.dlt0[0] = ad_sqrt(sg * sg) * (sg * sg) * ad_sqrt(kap * kap) * (ad_exp(eab * ti) - 1.0);
       c.dd[0] = dg * dg / (dg + dg);
@@ -157,15 +182,15 @@ FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& 
         if (c.cat == kAssocCross && i != j && ad_primal(kij[1]) != 0.0) e = kij[1];
         P ss = sig[i] * sig[j];
         c.dlt0[k] = ad_sqrt(ss) * ss * ad_sqrt(prm[8 * i + 4] * prm[8 * j + 4]) * (ad_exp(e * ti) - 1.0);
-        c.dd[k] = c.d[i] * c.d[j] / (c.d[i] + c.d[j]);
+        c.dd[k] = dseg[i] * dseg[j] / (dseg[i] + dseg[j]);
       }
     }
   }
 }
 
 // Delta^{AiBj} (:500-522): zeta3_m1 (k (2k + 3) + 1) dlt0, k = dd zeta2 zeta3_m1
-template <class P, class R>
-FD R mix_strength(const MixCoef<P>& c, int k, const R& z2om, const R& omi) {
+template <class C, class R>
+FD R mix_strength(const C& c, int k, const R& z2om, const R& omi) {
   R kk = z2om * c.dd[k];
   return (omi * (kk * (2.0 * kk + 3.0) + 1.0)) * c.dlt0[k];
 }
@@ -246,7 +271,7 @@ FD void induced_residual(const R& x, const R& s0, const R& s1, const R (&t)[4], 
   df = na0 * (g0 + x * dg0 - dbb) + na1 * (g1 + x * dg1 - dbb);
 }
 
-template <class R, int NSTEP>
+template <class R, int NSTEP, bool GC>
 FD R induced_assoc(const R (&rho)[2], const R (&dl)[4], const R (&na)[2], const R (&nb)[2]) {
   // d_ij = Delta_ij rho_j (:353-366)
   R d00 = dl[0] * rho[0], d01 = dl[1] * rho[1], d10 = dl[2] * rho[0], d11 = dl[3] * rho[1];
@@ -260,7 +285,7 @@ FD R induced_assoc(const R (&rho)[2], const R (&dl)[4], const R (&na)[2], const 
     double f, df;
     induced_residual<double>(x, s0p, s1p, tp, na0p, na1p, f, df);
     double nx = x - f / df;
-    if (nx < 0.0) nx = 0.2 * x;  // :381-383
+    if (!GC && nx < 0.0) nx = 0.2 * x;  // :381-383 (not in gc_pcsaft.py:414-433)
     bool done = fabs(nx - x) <= 1e-15;
     x = nx;
     if (done) break;
@@ -285,8 +310,49 @@ template <class T> struct AssocSteps<D2T<T>> { static constexpr int value = 2; }
 template <int N> struct AssocSteps<D1T<DN<N>>> { static constexpr int value = 2; };       // mixed second order
 template <> struct AssocSteps<double> { static constexpr int value = 0; };
 
-template <class P, class R>
-FD R mix_helmholtz(const MixCoef<P>& c, const R& rho0, const R& rho1) {
+// GC cross association (gc_pcsaft.py:332-380, nA = nB = 1): f_i = x_i + x_i sum_j x_j d_ij - 1
+template <class R>
+FD void gc_cross_residual(const R& x0, const R& x1, const R (&d)[4], R& f0, R& f1, R& j00, R& j01, R& j10, R& j11) {
+  f0 = x0 + x0 * (x0 * d[0] + x1 * d[1]) - 1.0;
+  f1 = x1 + x1 * (x0 * d[2] + x1 * d[3]) - 1.0;
+  j00 = 1.0 + 2.0 * (x0 * d[0]) + x1 * d[1];
+  j01 = x0 * d[1];
+  j10 = x1 * d[2];
+  j11 = 1.0 + x0 * d[2] + 2.0 * (x1 * d[3]);
+}
+
+template <class R, int NSTEP>
+FD R gc_cross_assoc(const R (&rho)[2], const R (&dl)[4]) {
+  R d[4] = {dl[0] * rho[0], dl[1] * rho[1], dl[2] * rho[0], dl[3] * rho[1]};  // Delta_ij rho_j
+  double dp[4] = {ad_primal(d[0]), ad_primal(d[1]), ad_primal(d[2]), ad_primal(d[3])};
+  double x0 = 0.2, x1 = 0.2;
+  for (int it = 0; it < 50; ++it) {
+    double f0, f1, j00, j01, j10, j11;
+    gc_cross_residual<double>(x0, x1, dp, f0, f1, j00, j01, j10, j11);
+    double det = j00 * j11 - j01 * j10;
+    double n0 = x0 - (j11 * f0 - j01 * f1) / det;
+    double n1 = x1 - (-j10 * f0 + j00 * f1) / det;
+    bool done = fabs(n0 - x0) <= 1e-15 && fabs(n1 - x1) <= 1e-15;
+    x0 = n0;
+    x1 = n1;
+    if (done) break;
+  }
+  R X0(x0), X1(x1);
+#pragma unroll
+  for (int s = 0; s < NSTEP; ++s) {
+    R f0, f1, j00, j01, j10, j11;
+    gc_cross_residual<R>(X0, X1, d, f0, f1, j00, j01, j10, j11);
+    R idet = ad_recip(j00 * j11 - j01 * j10);
+    R n0 = X0 - (j11 * f0 - j01 * f1) * idet;
+    R n1 = X1 - (j00 * f1 - j10 * f0) * idet;
+    X0 = n0;
+    X1 = n1;
+  }
+  return rho[0] * (2.0 * ad_log(X0) - X0 + 1.0) + rho[1] * (2.0 * ad_log(X1) - X1 + 1.0);
+}
+
+template <class P, class R, int NB, bool GC>
+FD R mix_helmholtz(const MixCoef<P, NB, GC>& c, const R& rho0, const R& rho1) {
   R z0 = rho0 * c.z[0][0] + rho1 * c.z[0][1];
   R z1 = rho0 * c.z[1][0] + rho1 * c.z[1][1];
   R z2 = rho0 * c.z[2][0] + rho1 * c.z[2][1];
@@ -299,13 +365,21 @@ FD R mix_helmholtz(const MixCoef<P>& c, const R& rho0, const R& rho1) {
   // hard sphere (:56-60)
   R a = (6.0 / kPi) * ((3.0 * (z1 * z2)) * omi + ((z2 * z2) * omi2) * z23 + ((z2 * z23) * z23 - z0) * ad_log(om));
 
-  // hard chain (:63-65)
+  // hard chain (:63-65; gc_pcsaft.py:156-165): g = 1/(1-z3) + 3 c cd + 2 (c cd)^2 (1 - z3)
   R cz = z2 * omi2;
-  {
-    R cd0 = cz * c.d[0], cd1 = cz * c.d[1];
-    R g0 = omi + 1.5 * cd0 + (0.5 * (cd0 * cd0)) * om;
-    R g1 = omi + 1.5 * cd1 + (0.5 * (cd1 * cd1)) * om;
-    a = a - (rho0 * c.mm1[0]) * ad_log(g0) - (rho1 * c.mm1[1]) * ad_log(g1);
+  if (NB == 2) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      R x = cz * c.cd[b];
+      R g = omi + 3.0 * x + (2.0 * (x * x)) * om;
+      a = a - (rho0 * c.bn[b][0] + rho1 * c.bn[b][1]) * ad_log(g);
+    }
+  } else {
+    for (int b = 0; b < c.nbond; ++b) {
+      R x = cz * c.cd[b];
+      R g = omi + 3.0 * x + (2.0 * (x * x)) * om;
+      a = a - (rho0 * c.bn[b][0] + rho1 * c.bn[b][1]) * ad_log(g);
+    }
   }
 
   // dispersion (:67-106)
@@ -364,26 +438,38 @@ FD R mix_helmholtz(const MixCoef<P>& c, const R& rho0, const R& rho1) {
     R z2om = z2 * omi;
     if (c.cat == kAssocSelf) {
       R delta = mix_strength(c, 0, z2om, omi);
-      R ra = rho0 * c.na[0] + rho1 * c.na[1];
-      R rb = rho0 * c.nb[0] + rho1 * c.nb[1];
-      R dd = (rb - ra) * delta;
-      R aux = 1.0 - dd;
-      R sq = ad_sqrt(aux * aux + 4.0 * (rb * delta));
-      R xa = 2.0 * ad_recip(sq + 1.0 + dd);
-      R xb = 2.0 * ad_recip(sq + 1.0 - dd);
-      a = a + ra * site_term(xa) + rb * site_term(xb);
+      if (GC) {
+        // gc_pcsaft.py:309-330 (nA = nB = 1): X = 2 / (sqrt(1 + 4 Delta rho) + 1)
+        R rs = rho0 * c.sgn[0] + rho1 * c.sgn[1];
+        R xa = 2.0 * ad_recip(ad_sqrt(1.0 + 4.0 * (delta * rs)) + 1.0);
+        a = a + rs * (2.0 * ad_log(xa) - xa + 1.0);
+      } else {
+        R ra = rho0 * c.na[0] + rho1 * c.na[1];
+        R rb = rho0 * c.nb[0] + rho1 * c.nb[1];
+        R dd = (rb - ra) * delta;
+        R aux = 1.0 - dd;
+        R sq = ad_sqrt(aux * aux + 4.0 * (rb * delta));
+        R xa = 2.0 * ad_recip(sq + 1.0 + dd);
+        R xb = 2.0 * ad_recip(sq + 1.0 - dd);
+        a = a + ra * site_term(xa) + rb * site_term(xb);
+      }
     } else {
       R dl[4] = {mix_strength(c, 0, z2om, omi), mix_strength(c, 1, z2om, omi), mix_strength(c, 2, z2om, omi),
                  mix_strength(c, 3, z2om, omi)};
       if (c.cat == kAssocCross) {
-        R ra[2] = {rho0 * c.na[0], rho1 * c.na[1]};
-        R rb[2] = {rho0 * c.nb[0], rho1 * c.nb[1]};
-        a = a + cross_assoc<R, AssocSteps<R>::value>(ra, rb, dl);
+        if (GC) {
+          R rr[2] = {rho0, rho1};
+          a = a + gc_cross_assoc<R, AssocSteps<R>::value>(rr, dl);
+        } else {
+          R ra[2] = {rho0 * c.na[0], rho1 * c.na[1]};
+          R rb[2] = {rho0 * c.nb[0], rho1 * c.nb[1]};
+          a = a + cross_assoc<R, AssocSteps<R>::value>(ra, rb, dl);
+        }
       } else {
         R rr[2] = {rho0, rho1};
         R na[2] = {R(0.0) + c.na[0], R(0.0) + c.na[1]};
         R nb[2] = {R(0.0) + c.nb[0], R(0.0) + c.nb[1]};
-        a = a + induced_assoc<R, AssocSteps<R>::value>(rr, dl, na, nb);
+        a = a + induced_assoc<R, AssocSteps<R>::value, GC>(rr, dl, na, nb);
       }
     }
   }
@@ -398,11 +484,12 @@ struct MixEval {
   double v[2];                     // partial molar volumes (reduced)
 };
 
-FD MixEval mix_eval(const MixCoef<double>& c, double rho0, double rho1) {
+template <int NB, bool GC>
+FD MixEval mix_eval(const MixCoef<double, NB, GC>& c, double rho0, double rho1) {
   H2<double> r0(rho0), r1(rho1);
   r0.g0 = 1.0;
   r1.g1 = 1.0;
-  H2<double> a = mix_helmholtz<double, H2<double>>(c, r0, r1);
+  H2<double> a = mix_helmholtz<double, H2<double>, NB, GC>(c, r0, r1);
   MixEval e;
   e.a = a.re;
   e.mu[0] = a.g0;

@@ -140,6 +140,57 @@ int feos_host_pcsaft_dew_point(const double* params, const double* kij, const do
                                const double* vapor_molefracs, const double* pressure, int64_t n, double* rho_out,
                                uint8_t* status, int64_t* n_ok);
 
+/* ------------------------------------------------------------------------------------------ */
+/* group-contribution PC-SAFT: GcPcSaft(...).bubble_point / dew_point                          */
+/* ------------------------------------------------------------------------------------------ */
+
+/* One de-duplicated molecule pair of a batch: the segment types present in either molecule and the
+ * bonded type pairs, with per-molecule counts.  Replaces the per-state ChemicalRecord pair and the
+ * per-state `GcPcSaftEosParameters::from_segments` of src/gc_pcsaft.rs:25-69, :116-123 (and the dense
+ * [N,2,S] / [N,2,S,S] count tensors of feos_torch/gc_pcsaft.py:26-52). */
+#define FEOS_GC_MAX_SEG 12
+#define FEOS_GC_MAX_BOND 16
+typedef struct feos_gc_pair {
+  int32_t nseg, nbond;
+  int32_t seg[FEOS_GC_MAX_SEG];                    /* rows of the segment table */
+  double cnt[2][FEOS_GC_MAX_SEG];                  /* segments of that type in molecule 0 / 1 */
+  int32_t ba[FEOS_GC_MAX_BOND], bb[FEOS_GC_MAX_BOND]; /* bonded type pairs (local segment indices) */
+  double bcnt[2][FEOS_GC_MAX_BOND];                /* bonds of that type in molecule 0 / 1 */
+  int8_t krec[FEOS_GC_MAX_SEG][FEOS_GC_MAX_SEG];   /* binary segment record of (a, b), -1 = none */
+} feos_gc_pair;
+
+/* Common inputs of the GC entry points:
+ *   pairs [n_pairs], seg_params [n_seg,8] (rows as the PC-SAFT parameter rows), kab [n_rec] values of
+ *   the binary segment records, pair_index [n] (state -> pair), phi [n,2] (may be NULL = 1),
+ *   temperature [n].  Device pointers for feos_dev_*, host pointers for feos_host_*.
+ * Replaces PyGcPcSaft::bubble_point / dew_point -> bubble_point_ / dew_point_ (src/gc_pcsaft.rs:71-99,
+ * :103-171) fused with GcPcSaftMix.bubble_point / dew_point (feos_torch/gc_pcsaft.py:470-512). */
+int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                          const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                          const double* temperature, const double* molefracs, int64_t n, int bubble, double* rho,
+                          double* pressure, uint8_t* failed, int32_t* evals, void* stream);
+
+/* Gradient of sum_i g[i] * pressure[i].  grad_seg_params [n_seg,8] and grad_kab [n_rec] are shared by
+ * all states and are ACCUMULATED into (zero them first); grad_phi [n,2] and grad_temperature [n] are
+ * written.  Any output may be NULL. */
+int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                          const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                          const double* temperature, const double* rho, const uint8_t* failed, const int32_t* pos,
+                          const double* g, int64_t n, int bubble, double* grad_seg_params, double* grad_kab,
+                          double* grad_phi, double* grad_temperature, void* stream);
+
+/* a, p/kT, mu_i, v_i at (T, rho [n,2]): GcPcSaftMix.derivatives (gc_pcsaft.py:443-468). */
+int feos_dev_gc_state(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                      const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                      const double* temperature, const double* density, int64_t n, double* a, double* p, double* mu,
+                      double* v, void* stream);
+
+/* GcPcSaft.bubble_point / dew_point with host buffers -> (f64[n_ok,4], bool[n]) (src/gc_pcsaft.rs:71-99). */
+int feos_host_gc_point(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                       const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                       const double* temperature, const double* molefracs, const double* pressure, int64_t n,
+                       int bubble, double* rho_out, uint8_t* status, int64_t* n_ok);
+
 #ifdef __cplusplus
 }
 #endif

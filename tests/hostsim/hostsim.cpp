@@ -172,3 +172,103 @@ void sim_mix_point_bwd(const double* params, const double* kij, const double* T,
   }
 }
 }
+
+// ---------------------------------------------------------------------------------------------
+// group-contribution PC-SAFT
+// ---------------------------------------------------------------------------------------------
+#include "../../feos_torch_b200/csrc/gc_pcsaft.cuh"
+
+static GcSource gc_source(const GcPair* pairs, const double* seg, const double* kab, const int32_t* idx,
+                          const double* phi, const double* T, int64_t i) {
+  GcSource s;
+  s.pair = pairs + idx[i];
+  s.seg_params = seg;
+  s.kab = kab;
+  s.phi_[0] = phi ? phi[2 * i] : 1.0;
+  s.phi_[1] = phi ? phi[2 * i + 1] : 1.0;
+  s.T_ = T[i];
+  return s;
+}
+
+extern "C" {
+
+int sim_gc_pair_size() { return (int)sizeof(GcPair); }
+
+void sim_gc_state(const GcPair* pairs, const double* seg, const double* kab, const int32_t* idx, const double* phi,
+                  const double* T, const double* rho, int64_t n, double* a, double* p, double* mu, double* v) {
+  for (int64_t i = 0; i < n; ++i) {
+    GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    GcBinary b;
+    gc_binary_init(b, s);
+    MixEval e = b.eval(rho[2 * i], rho[2 * i + 1]);
+    a[i] = e.a; p[i] = e.p; mu[2 * i] = e.mu[0]; mu[2 * i + 1] = e.mu[1]; v[2 * i] = e.v[0]; v[2 * i + 1] = e.v[1];
+  }
+}
+
+void sim_gc_point(const GcPair* pairs, const double* seg, const double* kab, const int32_t* idx, const double* phi,
+                  const double* T, const double* z, int64_t n, int bubble, double* rho, double* value, uint8_t* status,
+                  int32_t* evals) {
+  for (int64_t i = 0; i < n; ++i) {
+    GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    GcBinary b;
+    gc_binary_init(b, s);
+    PointState st, se;
+    MixEval es, ei;
+    int ne = 0;
+    int rc = point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
+    if (rc == kStatusRetry) rc = point_robust(b, bubble != 0, z[i], st, es, ei, se, ne);
+    status[i] = (uint8_t)rc;
+    evals[i] = ne;
+    if (rc == kStatusOk) {
+      double r[4], re[4];
+      point_densities(st, bubble != 0, z[i], r);
+      point_densities(se, bubble != 0, z[i], re);
+      for (int k = 0; k < 4; ++k) rho[4 * i + k] = r[k];
+      double spec[2], inc[2];
+      if (bubble) { spec[0] = re[2]; spec[1] = re[3]; inc[0] = re[0]; inc[1] = re[1]; }
+      else { spec[0] = re[0]; spec[1] = re[1]; inc[0] = re[2]; inc[1] = re[3]; }
+      value[i] = point_pressure(es, ei.a, spec, inc) * T[i] * kPaPerRed;
+    } else {
+      for (int k = 0; k < 4; ++k) rho[4 * i + k] = NAN;
+      value[i] = NAN;
+    }
+  }
+}
+
+// grad_seg [n_seg,8] and grad_kab [n_rec] accumulate over states; grad_phi [n,2], grad_t [n]
+void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const double* kab, int n_rec,
+                      const int32_t* idx, const double* phi, const double* T, const double* rho, int64_t n, int bubble,
+                      const double* g, double* grad_seg, double* grad_kab, double* grad_phi, double* grad_t) {
+  for (int64_t i = 0; i < n; ++i) {
+    GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    const GcPair& pr = *s.pair;
+    GcBinary b;
+    gc_binary_init(b, s);
+    const double* r = rho + 4 * i;
+    double spec[2], inc[2];
+    if (bubble) { spec[0] = r[2]; spec[1] = r[3]; inc[0] = r[0]; inc[1] = r[1]; }
+    else { spec[0] = r[0]; spec[1] = r[1]; inc[0] = r[2]; inc[1] = r[3]; }
+    MixEval es = b.eval(spec[0], spec[1]);
+    PointWeights q = point_weights(es, spec, inc);
+    MixEval ei = b.eval(inc[0], inc[1]);
+    double p_red = point_pressure(es, ei.a, spec, inc);
+    double cbar[kGcMaxCoef];
+    int ncoef = visit_coef(b.c, [](double&, int) {});
+    for (int f = 0; f < ncoef; f += 3) gc_coef_adjoint_pass<3>(b.c, spec, inc, q, f, ncoef, cbar);
+    double scale = g[i] * T[i] * kPaPerRed;
+    int n_dir = 8 * pr.nseg + n_rec + 3;
+    for (int f = 0; f < n_dir; f += 3) {
+      double g3[3];
+      gc_input_grad_pass<3>(s, n_rec, f, cbar, g3);
+      for (int k = 0; k < 3 && f + k < n_dir; ++k) {
+        int d = f + k;
+        double v = g3[k] * scale;
+        if (d < 8 * pr.nseg) grad_seg[8 * pr.seg[d >> 3] + (d & 7)] += v;
+        else if (d < 8 * pr.nseg + n_rec) grad_kab[d - 8 * pr.nseg] += v;
+        else if (d < 8 * pr.nseg + n_rec + 2) grad_phi[2 * i + d - 8 * pr.nseg - n_rec] = v;
+        else grad_t[i] = v + g[i] * p_red * kPaPerRed;
+      }
+    }
+  }
+}
+}

@@ -102,3 +102,39 @@ def mix_point_bwd(params, kij, T, rho, bubble, g):
     grad = np.zeros((n, 19))
     lib().sim_mix_point_bwd(_p(params), _p(kij), _p(T), _p(rho), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(g), _p(grad))
     return grad
+
+
+def _gc_args(pairs, seg, kab, idx, phi, T):
+    pairs = np.ascontiguousarray(pairs)
+    assert lib().sim_gc_pair_size() == pairs.dtype.itemsize, (lib().sim_gc_pair_size(), pairs.dtype.itemsize)
+    return pairs, c64(seg), c64(kab), np.ascontiguousarray(idx, dtype=np.int32), (None if phi is None else c64(phi)), c64(T)
+
+
+def gc_state(pairs, seg, kab, idx, phi, T, rho):
+    pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
+    rho = c64(rho)
+    n = T.shape[0]
+    a = np.empty(n); p = np.empty(n); mu = np.empty((n, 2)); v = np.empty((n, 2))
+    lib().sim_gc_state(_p(pairs), _p(seg), _p(kab), _p(idx), _p(phi), _p(T), _p(rho), ctypes.c_int64(n), _p(a), _p(p), _p(mu), _p(v))
+    return a, p, mu, v
+
+
+def gc_point(pairs, seg, kab, idx, phi, T, z, bubble):
+    pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
+    z = c64(z)
+    n = T.shape[0]
+    rho = np.empty((n, 4)); val = np.empty(n)
+    status = np.empty(n, dtype=np.uint8); evals = np.empty(n, dtype=np.int32)
+    lib().sim_gc_point(_p(pairs), _p(seg), _p(kab), _p(idx), _p(phi), _p(T), _p(z), ctypes.c_int64(n), ctypes.c_int(int(bubble)),
+                       _p(rho), _p(val), _p(status), _p(evals))
+    return rho, val, status, evals
+
+
+def gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g):
+    pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
+    rho, g = c64(rho), c64(g)
+    n = T.shape[0]
+    gs = np.zeros_like(seg); gk = np.zeros_like(kab); gp = np.zeros((n, 2)); gt = np.zeros(n)
+    lib().sim_gc_point_bwd(_p(pairs), _p(seg), ctypes.c_int(seg.shape[0]), _p(kab), ctypes.c_int(kab.shape[0]), _p(idx), _p(phi),
+                           _p(T), _p(rho), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(g), _p(gs), _p(gk), _p(gp), _p(gt))
+    return gs, gk, gp, gt
