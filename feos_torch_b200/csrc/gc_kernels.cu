@@ -140,7 +140,9 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
       double p_red = point_pressure(es, ei.a, spec, inc);
       // A. coefficient adjoints
       double cbar[kGcMaxCoef];
-      int ncoef = visit_coef(b.c, [](double&, int) {});
+      int ncoef = coef_count(b.c);
+      // (the pass functions are __noinline__: fully inlined into this kernel, nvcc 12.9 -O3 produced wrong
+      // coefficient adjoints on sm_100a while -G and the stand-alone functions were correct)
 #pragma unroll 1
       for (int f = 0; f < ncoef; f += 3) gc_coef_adjoint_pass<3>(b.c, spec, inc, q, f, ncoef, cbar);
       // B. inputs of the coefficient stage

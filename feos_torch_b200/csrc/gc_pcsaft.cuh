@@ -210,54 +210,54 @@ FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& p
   }
 }
 
-// Visits every scalar coefficient of a MixCoef in a fixed order (the flat coefficient index used by
-// the gradient kernels).  Returns the number of coefficients.
-template <class C, class F>
-FD int visit_coef(C& c, F&& f) {
-  int idx = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    f(c.z[k][0], idx++);
-    f(c.z[k][1], idx++);
+// The scalar coefficients of a MixCoef in a fixed order (the flat coefficient index used by the
+// gradient kernels).  FEOS_VISIT_COEF(c, X) expands X(field) for every coefficient of `c`.
+#define FEOS_VISIT_COEF(c, X)                                  \
+  {                                                            \
+    for (int k_ = 0; k_ < 4; ++k_) {                           \
+      X((c).z[k_][0]);                                         \
+      X((c).z[k_][1]);                                         \
+    }                                                          \
+    X((c).m[0]);                                               \
+    X((c).m[1]);                                               \
+    for (int k_ = 0; k_ < 3; ++k_) X((c).q1[k_]);              \
+    for (int k_ = 0; k_ < 3; ++k_) X((c).q2[k_]);              \
+    for (int b_ = 0; b_ < (c).nbond; ++b_) X((c).cd[b_]);      \
+    if ((c).dipolar) {                                         \
+      X((c).mu2t[0]);                                          \
+      X((c).mu2t[1]);                                          \
+      for (int k_ = 0; k_ < 3; ++k_) {                         \
+        X((c).pw1[k_]);                                        \
+        X((c).pw2[k_]);                                        \
+        X((c).pe[k_]);                                         \
+        X((c).ps[k_]);                                         \
+      }                                                        \
+      for (int k_ = 0; k_ < 4; ++k_) {                         \
+        X((c).tw1[k_]);                                        \
+        X((c).tw2[k_]);                                        \
+        X((c).ts[k_]);                                         \
+      }                                                        \
+    }                                                          \
+    if ((c).cat != kAssocNone) {                               \
+      int n_ = ((c).cat == kAssocSelf) ? 1 : 4;                \
+      for (int k_ = 0; k_ < n_; ++k_) {                        \
+        X((c).dlt0[k_]);                                       \
+        X((c).dd[k_]);                                         \
+      }                                                        \
+      X((c).na[0]);                                            \
+      X((c).na[1]);                                            \
+      X((c).nb[0]);                                            \
+      X((c).nb[1]);                                            \
+    }                                                          \
   }
-  f(c.m[0], idx++);
-  f(c.m[1], idx++);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) f(c.q1[k], idx++);
-#pragma unroll
-  for (int k = 0; k < 3; ++k) f(c.q2[k], idx++);
-  for (int b = 0; b < c.nbond; ++b) f(c.cd[b], idx++);
-  if (c.dipolar) {
-    f(c.mu2t[0], idx++);
-    f(c.mu2t[1], idx++);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      f(c.pw1[k], idx++);
-      f(c.pw2[k], idx++);
-      f(c.pe[k], idx++);
-      f(c.ps[k], idx++);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      f(c.tw1[k], idx++);
-      f(c.tw2[k], idx++);
-      f(c.ts[k], idx++);
-    }
-  }
-  if (c.cat != kAssocNone) {
-    int n = (c.cat == kAssocSelf) ? 1 : 4;
-    for (int k = 0; k < n; ++k) {
-      f(c.dlt0[k], idx++);
-      f(c.dd[k], idx++);
-    }
-    f(c.na[0], idx++);
-    f(c.na[1], idx++);
-    f(c.nb[0], idx++);
-    f(c.nb[1], idx++);
-  }
-  return idx;
-}
 constexpr int kGcMaxCoef = 8 + 2 + 6 + kGcMaxBond + 26 + 12;
+
+FD int coef_count(const GcCoef& c) {
+  int n = 16 + c.nbond;
+  if (c.dipolar) n += 26;
+  if (c.cat != kAssocNone) n += ((c.cat == kAssocSelf) ? 2 : 8) + 4;
+  return n;
+}
 
 // copy of the primal coefficients carrying K dual directions over the flat coefficient index
 template <int K>
@@ -273,13 +273,20 @@ FD void seed_coef(MixCoef<DN<K>, kGcMaxBond, true>& cd, const GcCoef& c, int fir
   }
   // walk both structures in the same order
   double vals[kGcMaxCoef];
-  int n = visit_coef(const_cast<GcCoef&>(c), [&](double& x, int i) { vals[i] = x; });
-  (void)n;
-  visit_coef(cd, [&](DN<K>& x, int i) {
-    x = DN<K>(vals[i]);
-#pragma unroll
-    for (int k = 0; k < K; ++k) x.e[k] = (i == first + k) ? 1.0 : 0.0;
-  });
+  int idx = 0;
+#define FEOS_X(f) vals[idx++] = f
+  FEOS_VISIT_COEF(c, FEOS_X)
+#undef FEOS_X
+  idx = 0;
+#define FEOS_X(f)                                                  \
+  {                                                                \
+    DN<K> t_(vals[idx]);                                           \
+    for (int k = 0; k < K; ++k) t_.e[k] = (idx == first + k) ? 1.0 : 0.0; \
+    f = t_;                                                        \
+    ++idx;                                                         \
+  }
+  FEOS_VISIT_COEF(cd, FEOS_X)
+#undef FEOS_X
 }
 
 struct GcBinary {
@@ -305,7 +312,7 @@ FD void gc_binary_init(GcBinary& b, const GcSource& src) {
 // Step A: adjoints of the reduced pressure with respect to the coefficients, K coefficient directions
 // per pass (same formula as mix_grad.cuh).  cbar[idx] = d p_red / d coef[idx].
 template <int K>
-FD void gc_coef_adjoint_pass(const GcCoef& c, const double (&spec)[2], const double (&inc)[2], const PointWeights& q,
+FD_NOINLINE void gc_coef_adjoint_pass(const GcCoef& c, const double (&spec)[2], const double (&inc)[2], const PointWeights& q,
                              int first, int ncoef, double* cbar) {
   MixCoef<DN<K>, kGcMaxBond, true> cd;
   seed_coef<K>(cd, c, first);
@@ -320,7 +327,7 @@ FD void gc_coef_adjoint_pass(const GcCoef& c, const double (&spec)[2], const dou
 
 // Step B: K input directions [first, first + K): out[k] = sum_idx cbar[idx] d coef[idx] / d direction
 template <int K>
-FD void gc_input_grad_pass(const GcSource& src, int nrec, int first, const double* cbar, double (&out)[K]) {
+FD_NOINLINE void gc_input_grad_pass(const GcSource& src, int nrec, int first, const double* cbar, double (&out)[K]) {
   GcDualSource<K> ds;
   ds.s = src;
   ds.first = first;
@@ -329,10 +336,14 @@ FD void gc_input_grad_pass(const GcSource& src, int nrec, int first, const doubl
   gc_coef<DN<K>, GcDualSource<K>>(cd, ds, *src.pair);
 #pragma unroll
   for (int k = 0; k < K; ++k) out[k] = 0.0;
-  visit_coef(cd, [&](DN<K>& x, int i) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) out[k] += cbar[i] * x.e[k];
-  });
+  int idx = 0;
+#define FEOS_X(f)                                               \
+  {                                                             \
+    for (int k = 0; k < K; ++k) out[k] += cbar[idx] * f.e[k];   \
+    ++idx;                                                      \
+  }
+  FEOS_VISIT_COEF(cd, FEOS_X)
+#undef FEOS_X
 }
 
 }  // namespace feos

@@ -253,7 +253,7 @@ void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const d
     MixEval ei = b.eval(inc[0], inc[1]);
     double p_red = point_pressure(es, ei.a, spec, inc);
     double cbar[kGcMaxCoef];
-    int ncoef = visit_coef(b.c, [](double&, int) {});
+    int ncoef = coef_count(b.c);
     for (int f = 0; f < ncoef; f += 3) gc_coef_adjoint_pass<3>(b.c, spec, inc, q, f, ncoef, cbar);
     double scale = g[i] * T[i] * kPaPerRed;
     int n_dir = 8 * pr.nseg + n_rec + 3;

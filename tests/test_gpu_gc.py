@@ -77,7 +77,8 @@ def test_category_grid(ft, golden_gc, key, bubble):
         d = torch.zeros_like(ph)
         d[:, 1] = 1e-6
         fd = (total(ph + d, ep) - total(ph - d, ep)) / 2e-6
-        assert ((fd - phi.grad[:, 1]).abs() / fd.abs()).max().item() < 1e-6
+        # (FD noise floor ~1e-8 |p| for states whose pressure hardly depends on phi)
+        assert ((fd - phi.grad[:, 1]).abs() <= 1e-6 * fd.abs() + 1e-8 * total(ph, ep).abs()).all()
         j = ident.index("CH2")
         de = torch.zeros_like(ep)
         de[j] = 1e-5 * ep[j]
