@@ -243,6 +243,7 @@ def main():
         return
 
     kern_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in timings.items()}
+    kern_steps = {k: [round(a.elapsed_time(b), 3) for a, b in v] for k, v in timings.items()}
     step_ms = ms_dev / args.steps
     dom = "feos_dev_pure_vle_fwd"
     flops_per_launch = n * mean_evals * F_D2
@@ -257,7 +258,7 @@ def main():
         "flops_per_launch": flops_per_launch, "mean_evals_per_state": mean_evals, "flops_per_eval": F_D2,
         "kernel_ms": kern_ms[dom], "share_of_step": kern_ms[dom] / step_ms,
         "hbm": {"algorithmic_bytes": io_bytes, "achieved_gbs": io_bytes / (kern_ms[dom] * 1e-3) / 1e9, "peak_gbs": _peaks().get("hbm_gbs")},
-        "kernel_ms_all": kern_ms,
+        "kernel_ms_all": kern_ms, "kernel_ms_per_step": kern_steps,
     }
 
     value = n * world * args.steps / (ms_dev * 1e-3)

@@ -18,6 +18,29 @@ void set_error(const char* fmt, ...) {
 }
 void clear_error() { g_error[0] = 0; }
 void count_launch(int64_t k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+
+// Stream-ordered scratch memory (retry lists, scan tiles).  The default pool gives memory back to the
+// OS at every synchronisation (release threshold 0), which made cudaMallocAsync cost milliseconds in
+// every step after the Python layer's `.item()`; keep the pool's memory instead.
+int scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
+  static thread_local int tuned_device = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+  if (tuned_device != dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    tuned_device = dev;
+  }
+  cudaError_t err = cudaMallocAsync(p, bytes ? bytes : 1, s);
+  if (err != cudaSuccess) {
+    set_error("cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(err));
+    return -2;
+  }
+  return 0;
+}
 }  // namespace feos
 
 // Register-resident DFMA chains on every SM: the FP64 roofline denominator (MEASURED_PEAKS.json holds

@@ -8,6 +8,7 @@ namespace feos {
 void set_error(const char* fmt, ...);
 void clear_error();
 void count_launch(int64_t k = 1);
+int scratch_alloc(void** p, size_t bytes, cudaStream_t s);  // cudaMallocAsync from a pool that keeps its memory
 
 // evaluates a CUDA runtime call; on failure records the text and returns -2 from the caller
 #define FEOS_CUDA(call)                                                                   \

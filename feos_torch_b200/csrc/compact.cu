@@ -129,7 +129,7 @@ extern "C" int feos_dev_compact(const uint8_t* failed, int64_t n, int32_t* pos, 
   FEOS_ARG(!in || (out && in_cols >= 1 && out_cols >= in_cols));
   int tiles = (int)((n + kTile - 1) / kTile);
   int32_t* ws = nullptr;
-  FEOS_CUDA(cudaMallocAsync((void**)&ws, sizeof(int32_t) * (size_t)tiles, s));
+  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)tiles, s)) return rc_;
   compact_count_kernel<<<tiles, 256, 0, s>>>(failed, n, ws);
   FEOS_LAUNCH_OK();
   compact_scan_kernel<<<1, 1024, 0, s>>>(ws, tiles, n_ok);

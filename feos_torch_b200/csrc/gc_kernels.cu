@@ -239,7 +239,7 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   cudaStream_t s = (cudaStream_t)stream;
   GcArgs g{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
   int32_t* ws = nullptr;
-  FEOS_CUDA(cudaMallocAsync((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s));
+  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s)) return rc_;
   FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
   gc_point_fwd_kernel<<<grid_for(n, kGcBlock), kGcBlock, 0, s>>>(g, molefracs, n, bubble, rho, pressure, failed, evals,
                                                               ws + 1, ws);

@@ -233,7 +233,7 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   FEOS_ARG(params && kij && temperature && molefracs && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
   int32_t* ws = nullptr;
-  FEOS_CUDA(cudaMallocAsync((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s));
+  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s)) return rc_;
   FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
   mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, s>>>(params, kij, temperature, molefracs, n, bubble, rho,
                                                                   pressure, failed, evals, ws + 1, ws);

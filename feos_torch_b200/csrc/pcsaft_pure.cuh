@@ -104,6 +104,10 @@ FD void pure_coef(PureCoef<P>& c, const P& m, const P& sigma, const P& eps, cons
 template <class R>
 FD R site_term(const R& x) { return ad_log(x) - 0.5 * x + 0.5; }
 
+template <class P, class R>
+FD R pure_helmholtz_extras(const PureCoef<P>& c, const R& rho, const R& eta, const R& e2, const R& e3, const R& e4,
+                           const R& omi);
+
 // Stage 2: a(rho).  pcsaft_pure.py:110-178.
 template <class P, class R>
 FD R pure_helmholtz(const PureCoef<P>& c, const R& rho) {
@@ -141,6 +145,16 @@ FD R pure_helmholtz(const PureCoef<P>& c, const R& rho) {
   R rho2 = rho * rho;
   a = a + rho2 * (i1 * c.k1 + (c1 * i2) * c.k2);
 
+  if (c.dipolar || c.assoc) a = a + pure_helmholtz_extras<P, R>(c, rho, eta, e2, e3, e4, omi);
+  return a;
+}
+
+// dipole and association contributions (zero for the non-polar, non-associating majority)
+template <class P, class R>
+FD R pure_helmholtz_extras(const PureCoef<P>& c, const R& rho, const R& eta, const R& e2, const R& e3, const R& e4,
+                           const R& omi) {
+  R a(0.0);
+  R rho2 = rho * rho;
   // dipole (:145-160)
   if (c.dipolar) {
     R j1 = ((cAD[0][0] + c.v1 * cAD[0][1] + c.v2 * cAD[0][2]) + c.e * (cBD[0][0] + c.v1 * cBD[0][1] + c.v2 * cBD[0][2])) +
@@ -175,7 +189,7 @@ FD R pure_helmholtz(const PureCoef<P>& c, const R& rho) {
 struct PureEval {
   double a, a1, p, dp;
 };
-FD PureEval pure_eval(const PureCoef<double>& c, double rho) {
+FD PureEval pure_eval_generic(const PureCoef<double>& c, double rho) {
   D2 r(rho, 1.0, 0.0);
   D2 a = pure_helmholtz<double, D2>(c, r);
   PureEval o;
@@ -183,6 +197,74 @@ FD PureEval pure_eval(const PureCoef<double>& c, double rho) {
   o.a1 = a.d1;
   o.p = rho - a.re + rho * a.d1;
   o.dp = 1.0 + rho * a.d2;
+  return o;
+}
+
+// The same quantities with the hard-sphere, hard-chain and dispersion terms differentiated in closed
+// form: they depend on the density only through eta = c_eta rho, so value, first and second derivative
+// follow from scalar recurrences (Horner with derivatives for the I1/I2 series) instead of generic
+// second-order dual arithmetic -- about 2.5x fewer FP64 instructions per evaluation.  With
+//   a = rho f(eta) + rho^2 g(eta),  f = m F_hs - (m-1) F_hc,  g = k1 I1 + k2 C1 I2:
+//   a'  = f + eta f' + rho (2 g + eta g'),   a'' = c_eta (2 f' + eta f'') + 2 g + 4 eta g' + eta^2 g''.
+// Dipole and association terms (when present) still go through the dual-number path.
+FD PureEval pure_eval(const PureCoef<double>& c, double rho) {
+  const double eta = rho * c.c_eta;
+  const double s = 1.0 / (1.0 - eta);  // d s / d eta = s^2
+  const double t = 1.0 / (2.0 - eta);  // d t / d eta = t^2
+  const double s2 = s * s, s3 = s2 * s, s4 = s2 * s2;
+  // hard sphere F_hs = (4 eta - 3 eta^2) s^2 (:118) and hard chain F_hc = ln((1 - eta/2) s^3) (:121-122)
+  const double fhs = (4.0 - 3.0 * eta) * eta * s2, fhs1 = (4.0 - 2.0 * eta) * s3, fhs2 = (10.0 - 4.0 * eta) * s4;
+  const double fhc = log((1.0 - 0.5 * eta) * s3), fhc1 = 3.0 * s - t, fhc2 = 3.0 * s2 - t * t;
+  const double f = c.m * fhs - c.mm1 * fhc, f1 = c.m * fhs1 - c.mm1 * fhc1, f2 = c.m * fhs2 - c.mm1 * fhc2;
+  // dispersion series (:125-133): Horner with first and second derivative
+  double i1 = cA0[6] + c.w1 * cA1[6] + c.w2 * cA2[6], i1d = 0.0, i1dd = 0.0;
+  double i2 = cB0[6] + c.w1 * cB1[6] + c.w2 * cB2[6], i2d = 0.0, i2dd = 0.0;
+#pragma unroll
+  for (int k = 5; k >= 0; --k) {
+    i1dd = i1dd * eta + i1d;
+    i1d = i1d * eta + i1;
+    i1 = i1 * eta + (cA0[k] + c.w1 * cA1[k] + c.w2 * cA2[k]);
+    i2dd = i2dd * eta + i2d;
+    i2d = i2d * eta + i2;
+    i2 = i2 * eta + (cB0[k] + c.w1 * cB1[k] + c.w2 * cB2[k]);
+  }
+  i1dd *= 2.0;
+  i2dd *= 2.0;
+  // C1 = 1 / D, D = 1 + m X + (1 - m) Y (:134-140), X = (8 eta - 2 eta^2) s^4, Y = N s^2 t^2
+  const double x0 = (8.0 - 2.0 * eta) * eta * s4;
+  const double x1 = (8.0 + (20.0 - 4.0 * eta) * eta) * s4 * s;
+  const double x2 = (60.0 + (72.0 - 12.0 * eta) * eta) * s4 * s2;
+  const double n0 = (((-2.0 * eta + 12.0) * eta - 27.0) * eta + 20.0) * eta;
+  const double n1 = ((-8.0 * eta + 36.0) * eta - 54.0) * eta + 20.0;
+  const double n2 = (-24.0 * eta + 72.0) * eta - 54.0;
+  const double w = s2 * t * t, st = s + t;
+  const double y0 = n0 * w;
+  const double y1 = w * (n1 + 2.0 * n0 * st);
+  const double y2 = w * (n2 + 4.0 * n1 * st + n0 * (4.0 * st * st + 2.0 * (s2 + t * t)));
+  const double d0 = 1.0 + c.m * x0 - c.mm1 * y0, d1 = c.m * x1 - c.mm1 * y1, d2 = c.m * x2 - c.mm1 * y2;
+  const double c1 = 1.0 / d0;
+  const double c1d = -d1 * c1 * c1;
+  const double c1dd = (2.0 * d1 * d1 * c1 - d2) * c1 * c1;
+  const double g = c.k1 * i1 + c.k2 * (c1 * i2);
+  const double g1 = c.k1 * i1d + c.k2 * (c1d * i2 + c1 * i2d);
+  const double g2 = c.k1 * i1dd + c.k2 * (c1dd * i2 + 2.0 * c1d * i2d + c1 * i2dd);
+  double a = rho * (f + rho * g);
+  double a1 = f + eta * f1 + rho * (2.0 * g + eta * g1);
+  double a2 = c.c_eta * (2.0 * f1 + eta * f2) + 2.0 * g + eta * (4.0 * g1 + eta * g2);
+  if (c.dipolar || c.assoc) {
+    D2 r(rho, 1.0, 0.0);
+    D2 et = r * c.c_eta;
+    D2 e2 = et * et;
+    D2 x = pure_helmholtz_extras<double, D2>(c, r, et, e2, e2 * et, e2 * e2, ad_recip(1.0 - et));
+    a += x.re;
+    a1 += x.d1;
+    a2 += x.d2;
+  }
+  PureEval o;
+  o.a = a;
+  o.a1 = a1;
+  o.p = rho - a + rho * a1;
+  o.dp = 1.0 + rho * a2;
   return o;
 }
 

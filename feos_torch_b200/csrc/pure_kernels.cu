@@ -8,9 +8,12 @@
 //                            cannot finish are appended to a retry list (atomic counter), so the
 //                            expensive robust path never stalls the 31 neighbours of a warp;
 //   pure_vle_retry_kernel    robust path over the compacted retry list;
-//   pure_vle_bwd_kernel      implicit-function-theorem gradients, 3 passes of 3 dual directions;
+//   pure_vle_bwd_kernel      implicit-function-theorem gradients: closed-form base terms, dual passes only for
+//                            dipole / association (pure_grad.cuh);
 //   pure_rho_tp_*            liquid density at (T, p), forward and gradient;
 //   pure_state_kernel        a, p, dp/drho at given (T, rho).
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/feos_b200.h"
@@ -85,6 +88,77 @@ pure_vle_fwd_kernel(const double* __restrict__ params, const double* __restrict_
   store_vle(i, st, rho_l, u, el, ev, rle, rve, T, rho, vp, rleq, failed);
 }
 
+// Persistent work-queue variant of the fast path: every lane runs the resumable state machine
+// (PureVleMachine) one Helmholtz evaluation per loop trip; lanes whose state has finished (4-11 Newton
+// iterations, depending on T/T_c) take the next state from a global queue instead of idling until the
+// slowest lane of the warp is done.  Refills are batched (>= kRefillMin idle lanes, warp-aggregated
+// atomic) so that the divergent set-up section (parameter load + coefficient stage) is amortised.
+constexpr int kRefillMin = 6;
+
+// one copy of the evaluation code that all lanes of the warp enter together (inlined, the compiler
+// specialises it per solver phase and the lanes diverge: 12.6 of 32 active lanes per instruction)
+__device__ __noinline__ void pure_eval_call(const PureCoef<double>& c, double rho, PureEval& e) { e = pure_eval(c, rho); }
+
+__global__ void __launch_bounds__(kBlock)
+pure_vle_queue_kernel(const double* __restrict__ params, const double* __restrict__ temperature, int n,
+                      double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
+                      uint8_t* __restrict__ failed, int32_t* __restrict__ evals, int32_t* __restrict__ retry_list,
+                      int32_t* __restrict__ retry_count, int32_t* __restrict__ queue_head) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  bool active = false, exhausted = false;
+  int idx = 0, ne = 0;
+  double T = 0.0;
+  PureCoef<double> c;
+  c.dipolar = c.assoc = false;  // idle lanes evaluate too (converged warp): keep them on the short path
+  c.m = c.mm1 = c.c_eta = c.w1 = c.w2 = c.k1 = c.k2 = 1.0;
+  PureVleMachine m;
+  m.start(1e-3);
+  while (true) {
+    unsigned idle = __ballot_sync(full, !active);
+    if (idle) {
+      int nidle = __popc(idle);
+      if (!exhausted && (nidle >= kRefillMin || nidle == 32)) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(queue_head, nidle);
+        base = __shfl_sync(full, base, 0);
+        int mine = base + __popc(idle & ((1u << lane) - 1u));
+        if (!active && mine < n) {
+          idx = mine;
+          PureRow r = load_row(params, idx);
+          T = temperature[idx];
+          double rho_max;
+          make_coef(r, T, c, rho_max);
+          m.start(rho_max);
+          ne = 0;
+          active = true;
+        }
+        if (base + nidle >= n) exhausted = true;
+        idle = __ballot_sync(full, !active);
+      }
+      if (exhausted && idle == full) break;
+    }
+    double rho_eval = m.density();
+    PureEval e;
+    __syncwarp();
+    pure_eval_call(c, rho_eval, e);
+    if (active) {
+      ++ne;
+      int st = m.advance(e);
+      if (st != kRunning) {
+        active = false;
+        if (evals) evals[idx] = ne;
+        if (st == kStatusRetry) {
+          retry_list[atomicAdd(retry_count, 1)] = idx;
+        } else {
+          double u = m.u;
+          store_vle(idx, st, m.rho_l, u, m.el, m.ev, m.rle, m.rve, T, rho, vp, rleq, failed);
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(64)
 pure_vle_retry_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                       double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
@@ -136,16 +210,12 @@ pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict_
     make_coef(r, T, c, rho_max);
     dpl = pure_eval(c, rr.y).dp;
   }
-#pragma unroll 1
-  for (int f = 0; f < 9; f += 3) {
-    double g3[3];
-    pure_vle_grad_pass<3, NEED_RLEQ>(r.v, T, rr.x, rr.y, dpl, f, gv, gr, g3);
+  double out[9];
+  pure_vle_grad<NEED_RLEQ>(r.v, T, rr.x, rr.y, dpl, gv, gr, out);
+  double2* gp = reinterpret_cast<double2*>(grad_params + 8 * i);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (f + k < 8) grad_params[8 * i + f + k] = g3[k];
-      else if (grad_t) grad_t[i] = g3[k];
-    }
-  }
+  for (int k = 0; k < 4; ++k) gp[k] = make_double2(out[2 * k], out[2 * k + 1]);
+  if (grad_t) grad_t[i] = out[8];
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -201,17 +271,14 @@ pure_rho_tp_bwd_kernel(const double* __restrict__ params, const double* __restri
   double gi = g[pos ? (int64_t)pos[i] : i];
   if (grad_p) grad_p[i] = gi / dp / (T * kPaPerRed) * kKmolM3PerRed;
   if (!grad_params && !grad_t) return;
-#pragma unroll 1
-  for (int f = 0; f < 9; f += 3) {
-    double g3[3];
-    pure_rho_tp_grad_pass<3>(r.v, T, x, p_t, dp, f, gi, g3);
+  double out[9];
+  pure_rho_tp_grad(r.v, T, x, p_t, dp, gi, out);
+  if (grad_params) {
+    double2* gp = reinterpret_cast<double2*>(grad_params + 8 * i);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (f + k < 8) {
-        if (grad_params) grad_params[8 * i + f + k] = g3[k];
-      } else if (grad_t) grad_t[i] = g3[k];
-    }
+    for (int k = 0; k < 4; ++k) gp[k] = make_double2(out[2 * k], out[2 * k + 1]);
   }
+  if (grad_t) grad_t[i] = out[8];
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -256,15 +323,36 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
   if (n == 0) return 0;
   FEOS_ARG(params && temperature && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
-  int32_t* ws = nullptr;  // [0] = retry counter, [1..n] = retry list
-  FEOS_CUDA(cudaMallocAsync((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s));
-  FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
-  pure_vle_fwd_kernel<<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, n, rho, vapor_pressure,
-                                                           liquid_density, failed, evals, ws + 1, ws);
+  int32_t* ws = nullptr;  // [0] = retry counter, [1] = queue head, [2..n+1] = retry list
+  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
+  static const int variant = [] {
+    // "queue" = persistent work-queue kernel, default = one thread per state.  Measured on B200 (1 M C2
+    // states, ncu): 1.07 ms vs 1.08 ms -- the queue keeps more lanes busy per evaluation but pays for it
+    // with divergent bookkeeping (profiles/r1_pure_vle_queue_vs_loop.md)
+    const char* e = getenv("FEOS_B200_PURE_VLE_KERNEL");
+    return (e && e[0] == 'q') ? 1 : 0;
+  }();
+  if (variant == 0 || n < 4096) {
+    pure_vle_fwd_kernel<<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, n, rho, vapor_pressure,
+                                                             liquid_density, failed, evals, ws + 2, ws);
+  } else {
+    static int blocks = 0;
+    if (!blocks) {
+      int dev = 0, sms = 0, per_sm = 0;
+      FEOS_CUDA(cudaGetDevice(&dev));
+      FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pure_vle_queue_kernel, kBlock, 0));
+      blocks = sms * (per_sm > 0 ? per_sm : 1);  // persistent grid: every resident slot of every SM
+    }
+    int grid = (int)std::min<int64_t>(blocks, (n + kBlock - 1) / kBlock);
+    pure_vle_queue_kernel<<<grid, kBlock, 0, s>>>(params, temperature, (int)n, rho, vapor_pressure, liquid_density,
+                                                failed, evals, ws + 2, ws, ws + 1);
+  }
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
   pure_vle_retry_kernel<<<retry_grid, 64, 0, s>>>(params, temperature, rho, vapor_pressure, liquid_density, failed,
-                                                 evals, ws + 1, ws);
+                                                 evals, ws + 2, ws);
   FEOS_LAUNCH_OK();
   FEOS_CUDA(cudaFreeAsync(ws, s));
   return 0;

@@ -91,6 +91,94 @@ FD int pure_vle_fast(const PureCoef<double>& c, double rho_max, double& rho_l, d
   return pure_vle_newton(c, rho_l, u, el, ev, rho_l_eval, rho_v_eval, 30, evals);
 }
 
+// The fast path as a resumable state machine: every call of advance() consumes ONE Helmholtz evaluation
+// at density(), so that the lanes of a warp can run states of different progress in lock step and pick
+// up new states from a work queue as they finish (pure_vle_queue_kernel).  Same arithmetic, iteration
+// limits and results as pure_vle_fast().
+constexpr int kRunning = -1;
+struct PureVleMachine {
+  double rho_l, u;                 // current iterate (u = ln rho_v)
+  double prev_l, prev_u, dl, du;   // back-tracking
+  double rle, rve;                 // last evaluation point, one Newton step before (rho_l, u)
+  double rho_v;                    // exp(u) of the pending vapour evaluation
+  PureEval el, ev;
+  int phase, it, halvings;
+  bool have_prev;
+
+  FD void start(double rho_max) {
+    rho_l = rho_max;
+    u = 0.0;
+    phase = 0;
+    it = 0;
+  }
+  FD double density() {
+    if (phase == 2) {
+      rho_v = exp(u);
+      return rho_v;
+    }
+    return rho_l;
+  }
+  FD int advance(const PureEval& e) {
+    if (phase == 0) {  // liquid density iteration towards the ideal-vapour pressure estimate
+      if (!(e.dp > 0.0)) return kStatusRetry;
+      u = log(rho_l) + e.a1 - e.p / rho_l;
+      double delta = (exp(u) - e.p) / e.dp;
+      delta = fmax(delta, -0.3 * rho_l);
+      rho_l += delta;
+      ++it;
+      if (fabs(delta) < 0.02 * rho_l) {
+        if (!(u == u)) return kStatusRetry;
+        phase = 1;
+        it = 0;
+        prev_l = rho_l;
+        prev_u = u;
+        dl = du = 0.0;
+        have_prev = false;
+        halvings = 0;
+      } else if (it >= 24) {
+        return kStatusRetry;
+      }
+      return kRunning;
+    }
+    if (phase == 1) {  // liquid evaluation of a Newton iteration: wait for the vapour one
+      el = e;
+      phase = 2;
+      return kRunning;
+    }
+    ev = e;
+    phase = 1;
+    ++it;
+    bool bad = !(el.dp > 0.0) || !(ev.dp > 0.0) || !(rho_l > rho_v);
+    if (bad) {
+      if (!have_prev || ++halvings > 10) return kStatusRetry;
+      dl *= 0.5;
+      du *= 0.5;
+      rho_l = prev_l + dl;
+      u = prev_u + du;
+      return it >= 30 ? kStatusRetry : kRunning;
+    }
+    halvings = 0;
+    double D = 1.0 - rho_v / rho_l;
+    if (D < 1e-5) return kStatusRetry;
+    double F1 = el.p - ev.p;
+    double F2 = (el.a1 - ev.a1) + (log(rho_l) - u);
+    dl = -(F1 - rho_v * F2) / (el.dp * D);
+    du = (F2 - F1 / rho_l) / (ev.dp * D);
+    if (!(fabs(dl) < 1e300) || !(fabs(du) < 1e300)) return kStatusRetry;
+    dl = clampd(dl, -0.15 * rho_l, 0.15 * rho_l);
+    du = clampd(du, -2.0, 2.0);
+    prev_l = rho_l;
+    prev_u = u;
+    have_prev = true;
+    rle = rho_l;
+    rve = rho_v;
+    rho_l += dl;
+    u += du;
+    if (fabs(dl) <= kVleTol * prev_l && fabs(du) <= kVleTol) return kStatusOk;
+    return it >= 30 ? kStatusRetry : kRunning;
+  }
+};
+
 // Root of p(rho) = p_t inside [lo, hi] on a mechanically stable branch (p monotone increasing).
 FD double pure_bracketed_density(const PureCoef<double>& c, double p_t, double lo, double hi, double rho, int& evals) {
   for (int it = 0; it < 60; ++it) {
@@ -99,85 +187,109 @@ FD double pure_bracketed_density(const PureCoef<double>& c, double p_t, double l
     if (e.p < p_t) lo = rho; else hi = rho;
     double nw = rho - (e.p - p_t) / e.dp;
     if (!(nw > lo) || !(nw < hi) || !(e.dp > 0.0)) nw = 0.5 * (lo + hi);
-    bool done = fabs(nw - rho) <= 1e-13 * rho;
+    bool done = fabs(nw - rho) <= 1e-9 * rho;
     rho = nw;
     if (done) break;
   }
   return rho;
 }
 
+// Root of dp/drho between a (dp > 0) and b (dp <= 0) by the Illinois variant of regula falsi; returns the
+// end point on the mechanically stable side.
+FD double pure_spinodal(const PureCoef<double>& c, double a, double fa, double b, double fb, int& evals) {
+  for (int it = 0; it < 12; ++it) {
+    double x = (a * fb - b * fa) / (fb - fa);
+    if (!(x > fmin(a, b)) || !(x < fmax(a, b))) x = 0.5 * (a + b);
+    double fx = pure_eval(c, x).dp;
+    evals += 1;
+    if (fx > 0.0) {
+      a = x;
+      fa = fx;
+      fb *= 0.5;
+    } else {
+      b = x;
+      fb = fx;
+      fa *= 0.5;
+    }
+    if (fabs(b - a) < 1e-4 * fabs(a) || fa < 1e-6) break;
+  }
+  return a;
+}
+
 FD int pure_vle_robust(const PureCoef<double>& c, double rho_max, double& rho_l, double& u, PureEval& el,
                        PureEval& ev, double& rho_l_eval, double& rho_v_eval, int& evals) {
-  // 1. scan d(p)/d(rho) on a grid
-  const int NG = 40;
+  // 1. coarse scan of dp/drho: brackets of the mechanically unstable range or the location of min dp
+  const int NG = 14;
   const double top = 1.1 * rho_max;
-  double a_lo = 0.0, a_hi = -1.0;  // [stable, unstable] bracket of the vapour spinodal
-  double b_lo = -1.0, b_hi = -1.0;  // [unstable, stable] bracket of the liquid spinodal
-  double min_dp = 1e300, rho_min = 0.0;
-  double last_stable = 0.0;
+  double a_lo = 0.0, fa_lo = 1.0, a_hi = -1.0, fa_hi = 0.0;  // vapour spinodal in [a_lo (stable), a_hi (unstable)]
+  double b_lo = -1.0, fb_lo = 0.0, b_hi = -1.0, fb_hi = 0.0;  // liquid spinodal in [b_lo (unstable), b_hi (stable)]
+  double min_dp = 1e300;
+  int i_min = 1;
+  double prev_rho = 0.0, prev_dp = 1.0;
   for (int i = 1; i <= NG; ++i) {
     double x = (double)i / NG;
-    double rho = top * x * (0.25 + 0.75 * x);  // denser sampling at low density
-    PureEval e = pure_eval(c, rho);
+    double rho = top * x * (0.3 + 0.7 * x);  // denser sampling at low density
+    double dp = pure_eval(c, rho).dp;
     evals += 1;
-    bool unstable = !(e.dp > 0.0);
-    if (e.dp < min_dp) { min_dp = e.dp; rho_min = rho; }
-    if (unstable) {
-      if (a_hi < 0.0) { a_lo = last_stable; a_hi = rho; }
-      b_lo = rho;
-      b_hi = -1.0;
-    } else {
-      if (a_hi < 0.0) last_stable = rho;
-      if (b_lo > 0.0 && b_hi < 0.0) { b_hi = rho; break; }
+    if (dp < min_dp) { min_dp = dp; i_min = i; }
+    if (!(dp > 0.0)) {
+      if (a_hi < 0.0) { a_lo = prev_rho; fa_lo = prev_dp; a_hi = rho; fa_hi = dp; }
+      b_lo = rho; fb_lo = dp; b_hi = -1.0;
+    } else if (b_lo > 0.0 && b_hi < 0.0) {
+      b_hi = rho; fb_hi = dp;
+      break;
     }
+    prev_rho = rho; prev_dp = dp;
   }
   if (a_hi < 0.0) {
-    // no unstable grid point: refine the minimum of dp by golden section inside its grid cell(s)
-    double w = top / NG * 2.0;
-    double lo = fmax(rho_min - w, 1e-3 * rho_min), hi = rho_min + w;
+    // no unstable grid point: golden-section search for the minimum of dp around the smallest sample
+    auto grid = [&](int i) { double x = (double)i / NG; return top * x * (0.3 + 0.7 * x); };
+    double lo = grid(i_min - 1), hi = grid(i_min < NG ? i_min + 1 : NG);
+    if (i_min == 1) lo = 0.05 * grid(1);
     const double gr = 0.6180339887498949;
     double x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo);
     double f1 = pure_eval(c, x1).dp, f2 = pure_eval(c, x2).dp;
     evals += 2;
-    for (int it = 0; it < 24 && f1 > 0.0 && f2 > 0.0; ++it) {
+    for (int it = 0; it < 14 && f1 > 0.0 && f2 > 0.0 && (hi - lo) > 2e-3 * rho_max; ++it) {
       if (f1 < f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); f1 = pure_eval(c, x1).dp; }
       else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); f2 = pure_eval(c, x2).dp; }
       evals += 1;
     }
-    double xu = (f1 < f2) ? x1 : x2;
-    if (!(fmin(f1, f2) <= 0.0)) return kStatusFailed;  // monotonic isotherm: super-critical
-    // bracket outwards from xu with the grid spacing
-    a_hi = xu; b_lo = xu;
-    a_lo = fmax(xu - 2.0 * w, 0.0);
-    b_hi = xu + 2.0 * w;
-    if (!(pure_eval(c, b_hi).dp > 0.0)) return kStatusFailed;
-    if (a_lo > 0.0 && !(pure_eval(c, a_lo).dp > 0.0)) a_lo = 0.0;
+    if (f1 > 0.0 && f2 > 0.0) return kStatusFailed;  // monotonic isotherm: super-critical
+    double xu = (f1 < f2) ? x1 : x2, fu = fmin(f1, f2);
+    // stable neighbours: the enclosing grid points
+    a_hi = xu; fa_hi = fu; b_lo = xu; fb_lo = fu;
+    a_lo = grid(i_min - 1); b_hi = grid(i_min < NG ? i_min + 1 : NG);
+    if (i_min == 1) a_lo = 0.05 * grid(1);
+    fa_lo = pure_eval(c, a_lo).dp;
+    fb_hi = pure_eval(c, b_hi).dp;
     evals += 2;
+    if (!(fa_lo > 0.0) || !(fb_hi > 0.0)) return kStatusFailed;
   }
   if (b_hi < 0.0) return kStatusFailed;  // unstable up to 1.1 rho_max: no liquid branch
-  // 2. bisect both spinodals; keep the stable-side end points
-  for (int it = 0; it < 40; ++it) {
-    double mid = 0.5 * (a_lo + a_hi);
-    if (pure_eval(c, mid).dp > 0.0) a_lo = mid; else a_hi = mid;
-    mid = 0.5 * (b_lo + b_hi);
-    if (pure_eval(c, mid).dp > 0.0) b_hi = mid; else b_lo = mid;
-    evals += 2;
+  if (!(a_lo > 0.0)) {  // first grid point already unstable: a tiny density is always stable
+    a_lo = 1e-3 * a_hi;
+    fa_lo = pure_eval(c, a_lo).dp;
+    evals += 1;
+    if (!(fa_lo > 0.0)) return kStatusFailed;
   }
-  double rho_sv = a_lo, rho_sl = b_hi;
-  if (!(rho_sv > 0.0)) return kStatusFailed;
+  // 2. spinodals (stable-side end points)
+  double rho_sv = pure_spinodal(c, a_lo, fa_lo, a_hi, fa_hi, evals);
+  double rho_sl = pure_spinodal(c, b_hi, fb_hi, b_lo, fb_lo, evals);
   double p_sv = pure_eval(c, rho_sv).p, p_sl = pure_eval(c, rho_sl).p;
   evals += 2;
   if (!(p_sv > 0.0) || !(p_sv > p_sl)) return kStatusFailed;
-  // 3. bracketed Newton in q = ln p on G(p) = mu_L(p) - mu_V(p), dG/dp = 1/rho_L - 1/rho_V < 0
+  // 3. bracketed Newton in q = ln p on G(p) = mu_L(p) - mu_V(p), dG/dp = 1/rho_L - 1/rho_V < 0; coarse:
+  //    the coupled Newton iteration polishes the result
   double q_hi = log(p_sv);
   double q_lo = (p_sl > 0.0) ? log(p_sl) : q_hi - 60.0;
   double q = (p_sl > 0.0) ? log(0.5 * (p_sl + p_sv)) : q_hi - 0.7;
   double rv = 0.5 * rho_sv, rl = 1.05 * rho_sl;
-  // upper end of the liquid bracket: a density whose pressure exceeds p_sv
   double l_top = fmax(1.2 * rho_max, 1.3 * rho_sl);
   for (int k = 0; k < 8 && !(pure_eval(c, l_top).p > p_sv); ++k) { l_top *= 1.15; evals += 1; }
+  evals += 1;
   bool conv = false;
-  for (int it = 0; it < 80; ++it) {
+  for (int it = 0; it < 60; ++it) {
     double p = exp(q);
     rv = pure_bracketed_density(c, p, 0.0, rho_sv, fmin(rv, rho_sv), evals);
     rl = pure_bracketed_density(c, p, rho_sl, l_top, fmax(rl, rho_sl), evals);
@@ -188,7 +300,7 @@ FD int pure_vle_robust(const PureCoef<double>& c, double rho_max, double& rho_l,
     double dq = -G / (p * (1.0 / rl - 1.0 / rv));
     double qn = q + dq;
     if (!(qn > q_lo) || !(qn < q_hi)) qn = 0.5 * (q_lo + q_hi);
-    bool done = fabs(qn - q) < 1e-9;
+    bool done = fabs(qn - q) < 1e-3;
     q = qn;
     if (done) { conv = true; break; }
   }
@@ -196,7 +308,7 @@ FD int pure_vle_robust(const PureCoef<double>& c, double rho_max, double& rho_l,
   if (fabs(rl / rv - 1.0) < 1e-5) return kStatusFailed;
   rho_l = rl;
   u = log(rv);
-  int st = pure_vle_newton(c, rho_l, u, el, ev, rho_l_eval, rho_v_eval, 20, evals);
+  int st = pure_vle_newton(c, rho_l, u, el, ev, rho_l_eval, rho_v_eval, 30, evals);
   return st == kStatusOk ? kStatusOk : kStatusFailed;
 }
 

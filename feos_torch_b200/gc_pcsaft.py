@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .pcsaft_pure import _cuda_device, _prep, _stream, compact
+from .pcsaft_pure import _back, _cuda_device, _prep, _stream, compact
 
 MAX_SEG = 12
 MAX_BOND = 16
@@ -177,7 +177,7 @@ class GcPcSaftMix:
         self.gc_pcsaft = GcPcSaft._from_tables(self)
 
     def _back(self, t):
-        return t.to(self._out_device)
+        return _back(t, self._out_device)
 
     def _point(self, temperature, molefracs, bubble):
         t = _prep(temperature, self._dev)

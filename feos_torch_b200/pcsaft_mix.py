@@ -8,7 +8,7 @@ and ``temperature``; mole fractions and the starting pressure carry none (pcsaft
 import torch
 
 from . import _lib
-from .pcsaft_pure import _cuda_device, _prep, _stream, compact
+from .pcsaft_pure import _back, _cuda_device, _prep, _stream, compact
 
 
 class _MixPoint(torch.autograd.Function):
@@ -84,7 +84,7 @@ class PcSaftMix:
         return self._source[1].detach().cpu().numpy()
 
     def _back(self, t):
-        return t.to(self._out_device)
+        return _back(t, self._out_device)
 
     def _point(self, temperature, molefracs, bubble):
         t = _prep(temperature, self._dev)

@@ -23,8 +23,51 @@ def _cuda_device(t):
     return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
 
+class _HostToDevice(torch.autograd.Function):
+    """Host tensor -> device for the computation; the gradient comes back into PINNED host memory
+    (torch's caching host allocator), so the device->host copy runs at PCIe speed instead of paging
+    in a fresh pageable buffer every step."""
+
+    @staticmethod
+    def forward(ctx, t, dev):
+        return t.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        return _to_host(g), None
+
+
+def _to_host(t):
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out
+
+
+class _DeviceToHost(torch.autograd.Function):
+    """Result -> pinned host memory; the incoming host gradient goes back to the device."""
+
+    @staticmethod
+    def forward(ctx, t):
+        ctx.dev = t.device
+        return _to_host(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dev, non_blocking=True)
+
+
 def _prep(t, dev):
+    if not t.is_cuda and t.requires_grad:
+        return _HostToDevice.apply(t, dev)
     return t.to(device=dev, dtype=torch.float64).contiguous()
+
+
+def _back(t, out_device):
+    """Return a result on the device the caller's tensors live on (the reference's `.to(self.m.device)`)."""
+    if out_device.type == "cpu":
+        return _DeviceToHost.apply(t) if t.dtype == torch.float64 else t.cpu()
+    return t.to(out_device)
 
 
 def compact(failed, values, out_cols=None):
@@ -137,7 +180,7 @@ class PcSaftPure:
         return self._source.detach().cpu().numpy()
 
     def _back(self, t):
-        return t.to(self._out_device)
+        return _back(t, self._out_device)
 
     # ---- properties on the phase-equilibrium hot path ------------------------------------------
     def vapor_pressure(self, temperature):

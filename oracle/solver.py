@@ -293,7 +293,11 @@ def binary_bubble_dew(helm, max_density_fn, temperature, molefrac1, pressure_pa,
             x = torch.stack([x1, 1.0 - x1], dim=1)
             rl = _density_at_p(helm, T, x, torch.zeros_like(p), rmax(x), rmax(x), True, n_iter=12)
             _, g, _, _, _ = _mix_props(helm, T, rl[:, None] * x)
-            s = 0.5 * s + 0.5 * (s_t - (g[:, 0] - g[:, 1]))  # damped: strongly non-ideal pairs oscillate otherwise
+            s_new = 0.5 * s + 0.5 * (s_t - (g[:, 0] - g[:, 1]))  # damped: strongly non-ideal pairs oscillate otherwise
+            done = bool(((s_new - s).abs() < 1e-9).all())
+            s = s_new
+            if done:
+                break
         x1 = torch.sigmoid(s)
         w = torch.stack([x1, 1.0 - x1], dim=1)
         rl = _density_at_p(helm, T, w, torch.zeros_like(p), rmax(w), rmax(w), True, n_iter=12)
@@ -316,13 +320,17 @@ def binary_bubble_dew(helm, max_density_fn, temperature, molefrac1, pressure_pa,
         if bubble:
             new = x_l * torch.exp(lnk)
             s = new.sum(dim=1)
+            change = (new / s[:, None] - y_v).abs().max()
             y_v = new / s[:, None]
             p = p * s.clamp(0.5, 2.0)
         else:
             new = y_v * torch.exp(-lnk)
             s = new.sum(dim=1)
+            change = (new / s[:, None] - x_l).abs().max()
             x_l = new / s[:, None]
             p = p / s.clamp(0.5, 2.0)
+        if bool(change < 1e-7) and bool(((s - 1.0).abs() < 1e-7).all()):
+            break  # the Newton polish below takes it from here
 
     # Newton polish on (mu_1, mu_2, p) equalities
     if bubble:
@@ -362,7 +370,7 @@ def binary_bubble_dew(helm, max_density_fn, temperature, molefrac1, pressure_pa,
             du = du[:, :, 0]
         scale = (1.0 / du.abs().max(dim=1).values.clamp(min=1e-300)).clamp(max=1.0)  # |du| <= 1
         du = du * scale[:, None]
-        conv = good & (du.abs().max(dim=1).values < 1e-13)
+        conv = good & (du.abs().max(dim=1).values < 1e-11)  # the accepted step squares this
         u = torch.where(conv[:, None] | ~good[:, None], u, u + du)
         if bool((conv | ~good).all()):
             break

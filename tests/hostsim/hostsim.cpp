@@ -38,6 +38,33 @@ void sim_pure_vle(const double* params, const double* T, int64_t n, int use_robu
   }
 }
 
+// the resumable state machine of the work-queue kernel, driven sequentially
+void sim_pure_vle_machine(const double* params, const double* T, int64_t n, double* rho, double* vp, double* rleq,
+                          uint8_t* status, int32_t* evals) {
+  for (int64_t i = 0; i < n; ++i) {
+    PureCoef<double> c;
+    double rho_max;
+    load_coef(params + 8 * i, T[i], c, rho_max);
+    PureVleMachine m;
+    m.start(rho_max);
+    int ne = 0, st = kRunning;
+    while (st == kRunning) {
+      PureEval e = pure_eval(c, m.density());
+      ++ne;
+      st = m.advance(e);
+    }
+    status[i] = (uint8_t)st;
+    evals[i] = ne;
+    if (st == kStatusOk) {
+      rho[2 * i] = exp(m.u);
+      rho[2 * i + 1] = m.rho_l;
+      pure_vle_properties(m.el, m.ev, m.rle, m.rve, T[i], vp[i], rleq[i]);
+    } else {
+      rho[2 * i] = rho[2 * i + 1] = vp[i] = rleq[i] = NAN;
+    }
+  }
+}
+
 void sim_pure_vle_bwd(const double* params, const double* T, const double* rho, int64_t n, const double* gv,
                       const double* gr, double* grad /*[n,9]*/) {
   for (int64_t i = 0; i < n; ++i) {
@@ -52,6 +79,36 @@ void sim_pure_vle_bwd(const double* params, const double* T, const double* rho, 
       else pure_vle_grad_pass<3, false>(params + 8 * i, T[i], rv, rl, dpl, f, gv[i], 0.0, g3);
       for (int k = 0; k < 3; ++k) grad[9 * i + f + k] = g3[k];
     }
+  }
+}
+
+// closed-form gradients (the kernels' path); the pass-based functions above are the cross-check
+void sim_pure_vle_bwd_fast(const double* params, const double* T, const double* rho, int64_t n, const double* gv,
+                           const double* gr, double* grad /*[n,9]*/) {
+  for (int64_t i = 0; i < n; ++i) {
+    double rv = rho[2 * i], rl = rho[2 * i + 1];
+    PureCoef<double> c;
+    double rho_max;
+    load_coef(params + 8 * i, T[i], c, rho_max);
+    double dpl = pure_eval(c, rl).dp;
+    double out[9];
+    if (gr) pure_vle_grad<true>(params + 8 * i, T[i], rv, rl, dpl, gv ? gv[i] : 0.0, gr[i], out);
+    else pure_vle_grad<false>(params + 8 * i, T[i], rv, rl, dpl, gv[i], 0.0, out);
+    for (int k = 0; k < 9; ++k) grad[9 * i + k] = out[k];
+  }
+}
+
+void sim_pure_rho_tp_bwd_fast(const double* params, const double* T, const double* P, const double* rho, int64_t n,
+                              const double* g, double* grad /*[n,9]*/) {
+  for (int64_t i = 0; i < n; ++i) {
+    PureCoef<double> c;
+    double rho_max;
+    load_coef(params + 8 * i, T[i], c, rho_max);
+    double p_t = P[i] / (T[i] * kPaPerRed);
+    double dp = pure_eval(c, rho[i]).dp;
+    double out[9];
+    pure_rho_tp_grad(params + 8 * i, T[i], rho[i], p_t, dp, g[i], out);
+    for (int k = 0; k < 9; ++k) grad[9 * i + k] = out[k];
   }
 }
 
@@ -88,6 +145,18 @@ void sim_pure_rho_tp_bwd(const double* params, const double* T, const double* P,
       for (int k = 0; k < 3; ++k) grad[9 * i + f + k] = g3[k];
     }
     grad_p[i] = g[i] / dp / (T[i] * kPaPerRed) * kKmolM3PerRed;
+  }
+}
+
+// generic second-order dual evaluation (the closed-form pure_eval is checked against it)
+void sim_pure_state_generic(const double* params, const double* T, const double* rho, int64_t n, double* a, double* p,
+                            double* dp) {
+  for (int64_t i = 0; i < n; ++i) {
+    PureCoef<double> c;
+    double rho_max;
+    load_coef(params + 8 * i, T[i], c, rho_max);
+    PureEval e = pure_eval_generic(c, rho[i]);
+    a[i] = e.a; p[i] = e.p; dp[i] = e.dp;
   }
 }
 

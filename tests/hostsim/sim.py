@@ -43,13 +43,22 @@ def pure_vle(params, T, robust=True):
     return rho, vp, rleq, status, evals
 
 
-def pure_vle_bwd(params, T, rho, gv=None, gr=None):
+def pure_vle_machine(params, T):
+    params, T = c64(params), c64(T)
+    n = T.shape[0]
+    rho = np.empty((n, 2)); vp = np.empty(n); rleq = np.empty(n)
+    status = np.empty(n, dtype=np.uint8); evals = np.empty(n, dtype=np.int32)
+    lib().sim_pure_vle_machine(_p(params), _p(T), ctypes.c_int64(n), _p(rho), _p(vp), _p(rleq), _p(status), _p(evals))
+    return rho, vp, rleq, status, evals
+
+
+def pure_vle_bwd(params, T, rho, gv=None, gr=None, generic=False):
     params, T, rho = c64(params), c64(T), c64(rho)
     n = T.shape[0]
     grad = np.zeros((n, 9))
     gv = c64(gv) if gv is not None else None
     gr = c64(gr) if gr is not None else None
-    lib().sim_pure_vle_bwd(_p(params), _p(T), _p(rho), ctypes.c_int64(n), _p(gv), _p(gr), _p(grad))
+    (lib().sim_pure_vle_bwd if generic else lib().sim_pure_vle_bwd_fast)(_p(params), _p(T), _p(rho), ctypes.c_int64(n), _p(gv), _p(gr), _p(grad))
     return grad
 
 
@@ -62,19 +71,21 @@ def pure_rho_tp(params, T, P):
     return rho, val, status, evals
 
 
-def pure_rho_tp_bwd(params, T, P, rho, g):
+def pure_rho_tp_bwd(params, T, P, rho, g, generic=False):
     params, T, P, rho, g = c64(params), c64(T), c64(P), c64(rho), c64(g)
     n = T.shape[0]
     grad = np.zeros((n, 9)); gp = np.zeros(n)
     lib().sim_pure_rho_tp_bwd(_p(params), _p(T), _p(P), _p(rho), ctypes.c_int64(n), _p(g), _p(grad), _p(gp))
+    if not generic:
+        lib().sim_pure_rho_tp_bwd_fast(_p(params), _p(T), _p(P), _p(rho), ctypes.c_int64(n), _p(g), _p(grad))
     return grad, gp
 
 
-def pure_state(params, T, rho):
+def pure_state(params, T, rho, generic=False):
     params, T, rho = c64(params), c64(T), c64(rho)
     n = T.shape[0]
     a = np.empty(n); p = np.empty(n); dp = np.empty(n)
-    lib().sim_pure_state(_p(params), _p(T), _p(rho), ctypes.c_int64(n), _p(a), _p(p), _p(dp))
+    (lib().sim_pure_state_generic if generic else lib().sim_pure_state)(_p(params), _p(T), _p(rho), ctypes.c_int64(n), _p(a), _p(p), _p(dp))
     return a, p, dp
 
 

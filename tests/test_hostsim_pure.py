@@ -84,3 +84,74 @@ def test_pure_vle_large_grid_self_consistent():
     gL = aL / rho[ok, 1] + pL / rho[ok, 1] + np.log(rho[ok, 1])
     assert np.abs(gV - gL).max() < 1e-10
     assert ev[ok].mean() < 30
+
+
+def test_state_machine_equals_loop_solver():
+    """The resumable state machine used by the work-queue kernel reproduces the plain loop solver bit
+    for bit (same densities, status and evaluation counts)."""
+    rng = np.random.default_rng(11)
+    n = 5000
+    m, s, e = rng.uniform(1, 4, n), rng.uniform(3, 4, n), rng.uniform(150, 350, n)
+    tc = e * (0.6380 + 0.7070 * m - 0.06418 * m * m)
+    P = np.zeros((n, 8))
+    P[:, 0], P[:, 1], P[:, 2] = m, s, e
+    P[: n // 4, 4], P[: n // 4, 5], P[: n // 4, 6], P[: n // 4, 7] = 0.02, 2000.0, 1.0, 1.0
+    P[n // 4: n // 2, 3] = 1.5
+    T = rng.uniform(0.45, 1.2, n) * tc
+    a = sim.pure_vle(P, T, robust=False)
+    b = sim.pure_vle_machine(P, T)
+    assert (a[3] == b[3]).all() and (a[4] == b[4]).all()
+    ok = a[3] == 0
+    assert ok.sum() > n // 2
+    for x, y in zip(a[:3], b[:3]):
+        assert np.array_equal(x[ok], y[ok])
+
+
+def test_closed_form_eval_equals_dual_number_eval():
+    """pure_eval (closed-form density derivatives of HS/HC/dispersion) against the generic second-order
+    dual evaluation of the same model, over vapour-like to liquid-like densities."""
+    rng = np.random.default_rng(5)
+    n = 20000
+    P = np.zeros((n, 8))
+    P[:, 0], P[:, 1], P[:, 2] = rng.uniform(1, 6, n), rng.uniform(2.5, 4.5, n), rng.uniform(100, 400, n)
+    P[: n // 3, 3] = rng.uniform(0.5, 3.0, n // 3)
+    P[n // 4: n // 2, 4], P[n // 4: n // 2, 5] = 0.03, 2200.0
+    P[n // 4: n // 2, 6], P[n // 4: n // 2, 7] = 1.0, 2.0
+    T = rng.uniform(150, 600, n)
+    eta = 10 ** rng.uniform(-8, np.log10(0.55), n)
+    rho = eta / (np.pi / 6 * P[:, 0] * P[:, 1] ** 3)
+    a0, p0, d0 = sim.pure_state(P, T, rho, generic=True)
+    a1, p1, d1 = sim.pure_state(P, T, rho)
+    # both evaluate O(rho)-sized sums with cancellations: compare on the scale of the largest term
+    scale = rho * (1 + P[:, 0] * 10)
+    assert (np.abs(a1 - a0) / scale).max() < 1e-13
+    assert (np.abs(p1 - p0) / scale).max() < 1e-13
+    assert (np.abs(d1 - d0) / (1 + np.abs(d0))).max() < 1e-11
+
+
+def test_closed_form_gradients_equal_dual_number_passes():
+    """The kernels' closed-form base gradient (+ dual passes for dipole/association only) against the
+    generic three-pass dual evaluation of the whole model."""
+    rng = np.random.default_rng(8)
+    n = 3000
+    m, s, e = rng.uniform(1, 4, n), rng.uniform(3, 4, n), rng.uniform(150, 350, n)
+    tc = e * (0.6380 + 0.7070 * m - 0.06418 * m * m)
+    P = np.zeros((n, 8))
+    P[:, 0], P[:, 1], P[:, 2] = m, s, e
+    P[: n // 4, 4], P[: n // 4, 5], P[: n // 4, 6], P[: n // 4, 7] = 0.02, 2000.0, 1.0, 2.0
+    P[n // 4: n // 2, 3] = 1.5
+    T = rng.uniform(0.5, 0.9, n) * tc
+    rho, vp, rleq, st, ev = sim.pure_vle(P, T)
+    ok = st == 0
+    P, T, rho = P[ok], T[ok], rho[ok]
+    k = len(T)
+    gv, gr = rng.uniform(0.5, 2, k), rng.uniform(0.5, 2, k)
+    for kw in (dict(gv=gv), dict(gv=gv, gr=gr)):
+        a = sim.pure_vle_bwd(P, T, rho, generic=True, **kw)
+        b = sim.pure_vle_bwd(P, T, rho, **kw)
+        assert (np.abs(a - b) / np.abs(a).max(axis=1, keepdims=True)).max() < 1e-11
+    Pr = np.full(k, 5e6)
+    r1, val, st1, _ = sim.pure_rho_tp(P, T, Pr)
+    a, gpa = sim.pure_rho_tp_bwd(P, T, Pr, r1, gv, generic=True)
+    b, gpb = sim.pure_rho_tp_bwd(P, T, Pr, r1, gv)
+    assert (np.abs(a - b) / np.abs(a).max(axis=1, keepdims=True)).max() < 1e-11
