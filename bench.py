@@ -125,12 +125,137 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+class C2:
+    """BASELINE.json configs[1]: PcSaftPure vapor_pressure + liquid_density, fwd + parameter gradients."""
+    name = "C2: PcSaftPure vapor_pressure + liquid_density fwd+bwd, synthetic non-associating (params,T) pairs"
+    dominant = "feos_dev_pure_vle_fwd"
+    kernel = "pure_vle_fwd_kernel(+retry)"
+    flops_per_eval = F_D2
+    io_bytes_per_state = 64 + 8 + 16 + 8 + 1
+    h2d_per_state = 64 + 8 + 8
+    d2h_per_state = 64 + 2 * 8 + 2
+
+    def __init__(self, n, rank, dev):
+        from feos_torch_b200 import PcSaftPure
+
+        self.PcSaftPure, self.n, self.dev = PcSaftPure, n, dev
+        params_h, T_h, p_h = make_workload(n, 1000 + rank, "cpu")
+        self.params_h, self.T_h, self.p_h = params_h.pin_memory(), T_h.pin_memory(), p_h.pin_memory()
+        self.params = self.params_h.to(dev).requires_grad_(True)
+        self.T = self.T_h.to(dev)
+        # workload generation (untimed): p >= 1.05 p_sat for the converged states
+        with torch.no_grad():
+            nans0, vp0 = PcSaftPure(self.params.detach()).vapor_pressure(self.T)
+            psat = torch.zeros(n, dtype=torch.float64, device=dev)
+            psat[~nans0] = vp0
+            self.p = torch.maximum(self.p_h.to(dev), 1.05 * psat)
+            self.p_h.copy_(self.p)
+        self.shared = []
+
+    def step_device(self):
+        self.params.grad = None
+        model = self.PcSaftPure(self.params)
+        nans, vp = model.vapor_pressure(self.T)
+        nans2, rho = model.liquid_density(self.T, self.p)
+        (vp.sum() + rho.sum()).backward()
+        return nans
+
+    def step_e2e(self):
+        x = self.params_h.requires_grad_(True)
+        x.grad = None
+        model = self.PcSaftPure(x)  # host tensors in: H2D inside
+        nans, vp = model.vapor_pressure(self.T_h)
+        nans2, rho = model.liquid_density(self.T_h, self.p_h)
+        loss = vp.sum() + rho.sum()
+        loss.backward()  # gradient lands on the host tensor: D2H inside
+        return float(loss.detach()), x.grad
+
+    def mean_evals(self, _lib):
+        n = self.n
+        evals = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        rho = torch.empty((n, 2), dtype=torch.float64, device=self.dev)
+        failed = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        _lib.call("feos_dev_pure_vle_fwd", _lib.ptr(self.params.detach()), _lib.ptr(self.T), n, _lib.ptr(rho), None, None,
+                  _lib.ptr(failed), _lib.ptr(evals), torch.cuda.current_stream().cuda_stream)
+        return evals.double().mean().item()
+
+
+class C4:
+    """BASELINE.json configs[3]: PcSaftMix bubble + dew point of ONE shared pair with a shared k_ij leaf,
+    fit loss sum (p - p_target)^2, k_ij gradient summed over the GPUs by one NCCL all-reduce."""
+    name = "C4: PcSaftMix binary bubble_point + dew_point fwd+bwd with shared k_ij, fit-loss gradient all-reduced"
+    dominant = "feos_dev_mix_point_fwd"
+    kernel = "mix_point_fwd_kernel(+retry)"
+    flops_per_eval = 3485.0  # binary non-associating hyper-dual evaluation, SURVEY.md section 8(d)
+    io_bytes_per_state = 128 + 16 + 8 + 8 + 32 + 8 + 1
+    h2d_per_state = 8 + 8
+    d2h_per_state = 2
+
+    def __init__(self, n, rank, dev):
+        from feos_torch_b200 import PcSaftMix
+
+        self.PcSaftMix, self.n, self.dev = PcSaftMix, n, dev
+        g = torch.Generator().manual_seed(2000 + rank)
+        pair = torch.tensor([[1, 3.5, 150, 0, 0, 0, 0, 0], [1, 3.5, 200, 0, 0, 0, 0, 0]], dtype=torch.float64)
+        self.pair = pair.to(dev)
+        self.kij = torch.tensor([-0.1, 0.0], dtype=torch.float64, device=dev, requires_grad=True)
+        self.T_h = ((0.6 + 0.25 * torch.rand(n, generator=g, dtype=torch.float64)) * 150 * 1.2757).pin_memory()
+        self.z_h = (0.05 + 0.9 * torch.rand(n, generator=g, dtype=torch.float64)).pin_memory()
+        self.T, self.z = self.T_h.to(dev), self.z_h.to(dev)
+        self.p0 = torch.full((n,), 1e5, dtype=torch.float64, device=dev)
+        with torch.no_grad():
+            m = PcSaftMix(self.pair.expand(n, 2, 8), self.kij.detach().expand(n, 2))
+            self.tb = m.bubble_point(self.T, self.z, self.p0)[0] * 1.01
+            self.td = m.dew_point(self.T, self.z, self.p0)[0] * 1.01
+        self.shared = [self.kij]
+
+    def _loss(self, T, z):
+        n = self.n
+        model = self.PcSaftMix(self.pair.expand(n, 2, 8), self.kij.expand(n, 2))
+        pb, nb = model.bubble_point(T, z, self.p0)
+        pd, nd = model.dew_point(T, z, self.p0)
+        return ((pb - self.tb) ** 2).sum() + ((pd - self.td) ** 2).sum(), nb
+
+    def step_device(self):
+        from feos_torch_b200 import distributed as fd
+
+        self.kij.grad = None
+        loss, nans = self._loss(self.T, self.z)
+        loss.backward()
+        fd.all_reduce_gradients(self.shared)
+        return nans
+
+    def step_e2e(self):
+        from feos_torch_b200 import distributed as fd
+
+        self.kij.grad = None
+        loss, nans = self._loss(self.T_h.to(self.dev, non_blocking=True), self.z_h.to(self.dev, non_blocking=True))
+        loss.backward()
+        fd.all_reduce_gradients(self.shared)
+        return float(loss.detach()), self.kij.grad.cpu()
+
+    def mean_evals(self, _lib):
+        n = self.n
+        evals = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        rho = torch.empty((n, 4), dtype=torch.float64, device=self.dev)
+        failed = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        P = self.pair.expand(n, 2, 8).contiguous()
+        K = self.kij.detach().expand(n, 2).contiguous()
+        _lib.call("feos_dev_mix_point_fwd", _lib.ptr(P), _lib.ptr(K), _lib.ptr(self.T), _lib.ptr(self.z), n, 1, _lib.ptr(rho),
+                  None, _lib.ptr(failed), _lib.ptr(evals), torch.cuda.current_stream().cuda_stream)
+        return evals.double().mean().item()
+
+
+WORKLOADS = {"c2": C2, "c4": C4}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (BASELINE.json metric)")
     ap.add_argument("--n", type=int, default=1_000_000, help="states per GPU per step")
     ap.add_argument("--ref-n", type=int, default=20_000, help="states per step of the reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -152,40 +277,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from feos_torch_b200 import PcSaftPure, _lib
+    from feos_torch_b200 import _lib
 
     _lib.load()
     n = args.n
-    params_h, T_h, p_h = make_workload(n, 1000 + rank, "cpu")
-    params_h, T_h, p_h = params_h.pin_memory(), T_h.pin_memory(), p_h.pin_memory()
-    params = params_h.to(dev).requires_grad_(True)
-    T = T_h.to(dev)
-    # workload generation (untimed): p >= 1.05 p_sat for the converged states
-    with torch.no_grad():
-        nans0, vp0 = PcSaftPure(params.detach()).vapor_pressure(T)
-        psat = torch.zeros(n, dtype=torch.float64, device=dev)
-        psat[~nans0] = vp0
-        p = torch.maximum(p_h.to(dev), 1.05 * psat)
-        p_h.copy_(p)
+    wl = WORKLOADS[args.workload](n, rank, dev)
     flush = torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device=dev)
-
-    def step_device():
-        params.grad = None
-        model = PcSaftPure(params)
-        nans, vp = model.vapor_pressure(T)
-        nans2, rho = model.liquid_density(T, p)
-        (vp.sum() + rho.sum()).backward()
-        return nans, nans2
-
-    def step_e2e():
-        x = params_h.requires_grad_(True)
-        x.grad = None
-        model = PcSaftPure(x)  # host tensors in: H2D inside
-        nans, vp = model.vapor_pressure(T_h)
-        nans2, rho = model.liquid_density(T_h, p_h)
-        loss = vp.sum() + rho.sum()
-        loss.backward()  # gradient lands on the host tensor: D2H inside
-        return float(loss), x.grad
 
     def barrier():
         if world > 1:
@@ -217,64 +314,61 @@ def main():
     clk_file = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
     sampler = clocks_sampler(clk_file, local) if rank == 0 else None
     launches0 = _lib.launch_count()
-    ms_dev = timed(step_device, args.steps, args.warmup, True)
+    ms_dev = timed(wl.step_device, args.steps, args.warmup, True)
     launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
     timings = _lib.TIMINGS
     _lib.TIMINGS = None
-    ms_e2e = timed(step_e2e, args.steps, args.warmup, False)
+    ms_e2e = timed(wl.step_e2e, args.steps, args.warmup, False)
     if sampler is not None:
         sampler.terminate()
         sampler.wait()
 
     # failed-state accounting + evaluation counts for the roofline (untimed)
-    nans, nans2 = step_device()
+    nans = wl.step_device()
     torch.cuda.synchronize()
     failed_frac = nans.double().mean().item()
-    evals = torch.zeros(n, dtype=torch.int32, device=dev)
-    rho_tmp = torch.empty((n, 2), dtype=torch.float64, device=dev)
-    failed_tmp = torch.empty(n, dtype=torch.uint8, device=dev)
-    _lib.call("feos_dev_pure_vle_fwd", _lib.ptr(params.detach()), _lib.ptr(T), n, _lib.ptr(rho_tmp), None, None,
-              _lib.ptr(failed_tmp), _lib.ptr(evals), torch.cuda.current_stream().cuda_stream)
-    mean_evals = evals.double().mean().item()
+    mean_evals = wl.mean_evals(_lib)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    kern_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in timings.items()}
-    kern_steps = {k: [round(a.elapsed_time(b), 3) for a, b in v] for k, v in timings.items()}
+    kern_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in timings.items()}
     step_ms = ms_dev / args.steps
-    dom = "feos_dev_pure_vle_fwd"
-    flops_per_launch = n * mean_evals * F_D2
-    achieved = flops_per_launch / (kern_ms[dom] * 1e-3) / 1e12
+    dom = wl.dominant
+    dom_calls = len(timings[dom]) // args.steps
+    flops_per_launch = n * mean_evals * wl.flops_per_eval
+    dom_ms = kern_ms[dom] / dom_calls
+    achieved = flops_per_launch / (dom_ms * 1e-3) / 1e12
     peak = _lib.measure_fp64_peak()
     spec = 148 * 64 * 2 * 1.965e9 / 1e12
-    io_bytes = n * (64 + 8 + 16 + 8 + 1)
+    io_bytes = n * wl.io_bytes_per_state
     roofline = {
-        "bound": "fp64", "kernel": "pure_vle_fwd_kernel(+retry)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": wl.kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak if peak else None, "traffic": None,
         "peak_source": "DFMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure); spec 148 SM x 64 lanes x 2 x 1.965 GHz = %.1f" % spec,
-        "flops_per_launch": flops_per_launch, "mean_evals_per_state": mean_evals, "flops_per_eval": F_D2,
-        "kernel_ms": kern_ms[dom], "share_of_step": kern_ms[dom] / step_ms,
-        "hbm": {"algorithmic_bytes": io_bytes, "achieved_gbs": io_bytes / (kern_ms[dom] * 1e-3) / 1e9, "peak_gbs": _peaks().get("hbm_gbs")},
-        "kernel_ms_all": kern_ms, "kernel_ms_per_step": kern_steps,
+        "flops_per_launch": flops_per_launch, "mean_evals_per_state": mean_evals, "flops_per_eval": wl.flops_per_eval,
+        "kernel_ms": dom_ms, "share_of_step": kern_ms[dom] / step_ms,
+        "hbm": {"algorithmic_bytes": io_bytes, "achieved_gbs": io_bytes / (dom_ms * 1e-3) / 1e9, "peak_gbs": _peaks().get("hbm_gbs")},
+        "kernel_ms_per_step": kern_ms,
     }
 
     value = n * world * args.steps / (ms_dev * 1e-3)
     e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.workload == "c2":
         cpu = cpu_baseline(args.ref_n)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if args.workload == "c2" else "pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s",
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "C2: PcSaftPure vapor_pressure + liquid_density fwd+bwd, synthetic non-associating (params,T) pairs",
-                   "states_per_gpu_per_step": n, "parallelism": f"batch sharded over {world} GPU(s), no data-path collective",
+        "config": {"workload": wl.name, "states_per_gpu_per_step": n,
+                   "parallelism": f"batch sharded over {world} GPU(s)" + (", one NCCL all-reduce of the shared-leaf gradient per step" if wl.shared else ", no data-path collective"),
                    "l2": "flushed (256 MiB write) between timed iterations", "failed_fraction": failed_frac},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (64 + 8 + 8) * world, "d2h_bytes_per_step": (n * 64 + 2 * n + 8) * world,
-                "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * wl.h2d_per_state * world,
+                "d2h_bytes_per_step": (n * wl.d2h_per_state + 8) * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": parse_clocks(clk_file),
         "roofline": roofline,
