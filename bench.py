@@ -91,7 +91,7 @@ def run_reference(args, rank, world):
     from oracle import models as om
 
     n = args.ref_n
-    threads = torch.get_num_threads()
+    threads = _use_all_host_threads()
     params, T, p = make_workload(n, 1000, "cpu")
 
     def step():
@@ -246,7 +246,83 @@ class C4:
         return evals.double().mean().item()
 
 
-WORKLOADS = {"c2": C2, "c4": C4}
+class C5:
+    """BASELINE.json configs[4]: GcPcSaftMix bubble + dew point, group parameters of the reference's
+    sauer2014_hetero.json (tests/golden/gc.json), 1 M states over the five non-associating molecule pairs of
+    tests/test_gc_pcsaft.py:17-29, shared k_ab leaf with its gradient all-reduced."""
+    name = "C5: GcPcSaftMix bubble_point + dew_point fwd+bwd, sauer2014 groups, 5 unique molecule pairs, shared k_ab"
+    dominant = "feos_dev_gc_point_fwd"
+    kernel = "gc_point_fwd_kernel(+retry)"
+    flops_per_eval = 4687.0  # GC compact hyper-dual evaluation, SURVEY.md section 8(d)
+    io_bytes_per_state = 4 + 16 + 8 + 8 + 32 + 8 + 1
+    h2d_per_state = 8 + 8
+    d2h_per_state = 2
+
+    def __init__(self, n, rank, dev):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import cases
+        from feos_torch_b200 import GcPcSaftMix
+
+        table = json.load(open(os.path.join(ROOT, "tests", "golden", "gc.json")))["segments"]
+        self.ident = list(table.keys())
+        self.par = tuple(torch.tensor([table[i][k] for i in self.ident], dtype=torch.float64, device=dev) for k in range(8))
+        g = torch.Generator().manual_seed(3000 + rank)
+        which = torch.randint(0, 5, (n,), generator=g).tolist()
+        pairs = [(cases.GC_SEGMENTS[i], cases.GC_BONDS[i]) for i in range(5)]
+        self.segs = [pairs[w][0] for w in which]
+        self.bonds = [pairs[w][1] for w in which]
+        self.kab = torch.tensor(0.03, dtype=torch.float64, device=dev, requires_grad=True)
+        self.phi = torch.tensor([cases.GC_PHI], dtype=torch.float64, device=dev).expand(n, 2).contiguous()
+        self.T_h = (150.0 + 100.0 * torch.rand(n, generator=g, dtype=torch.float64)).pin_memory()
+        self.z_h = (0.05 + 0.9 * torch.rand(n, generator=g, dtype=torch.float64)).pin_memory()
+        self.T, self.z = self.T_h.to(dev), self.z_h.to(dev)
+        self.p0 = torch.full((n,), 1e5, dtype=torch.float64, device=dev)
+        self.GcPcSaftMix, self.n, self.dev = GcPcSaftMix, n, dev
+        self.model = self._model()  # the pair table is built once per fit, not per step
+        self.shared = [self.kab]
+
+    def _model(self):
+        return self.GcPcSaftMix(self.ident, self.par, self.segs, self.bonds, [("CH3", "CH=O", self.kab), (">CH", "HCOO", -0.01)], self.phi)
+
+    def _loss(self, T, z):
+        m = self.model
+        m._kab = torch.stack([self.kab, torch.tensor(-0.01, dtype=torch.float64, device=self.dev)])  # fresh graph each step
+        pb, nb = m.bubble_point(T, z, self.p0)
+        pd, nd = m.dew_point(T, z, self.p0)
+        return pb.sum() + pd.sum(), nb
+
+    def step_device(self):
+        from feos_torch_b200 import distributed as fd
+
+        self.kab.grad = None
+        loss, nans = self._loss(self.T, self.z)
+        loss.backward()
+        fd.all_reduce_gradients(self.shared)
+        return nans
+
+    def step_e2e(self):
+        from feos_torch_b200 import distributed as fd
+
+        self.kab.grad = None
+        loss, nans = self._loss(self.T_h.to(self.dev, non_blocking=True), self.z_h.to(self.dev, non_blocking=True))
+        loss.backward()
+        fd.all_reduce_gradients(self.shared)
+        return float(loss.detach()), self.kab.grad.cpu()
+
+    def mean_evals(self, _lib):
+        n = self.n
+        m = self.model
+        evals = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        rho = torch.empty((n, 4), dtype=torch.float64, device=self.dev)
+        failed = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        _lib.call("feos_dev_gc_point_fwd", _lib.ptr(m._pairs), m._n_pairs, _lib.ptr(m._seg.detach()), m._seg.shape[0],
+                  _lib.ptr(m._kab.detach()), m._kab.shape[0], _lib.ptr(m._pair_index), _lib.ptr(m._phi), _lib.ptr(self.T),
+                  _lib.ptr(self.z), n, 1, _lib.ptr(rho), None, _lib.ptr(failed), _lib.ptr(evals),
+                  torch.cuda.current_stream().cuda_stream)
+        return evals.double().mean().item()
+
+
+WORKLOADS = {"c2": C2, "c4": C4, "c5": C5}
 
 
 def main():
@@ -360,7 +436,7 @@ def main():
     if not args.no_cpu_baseline and args.workload == "c2":
         cpu = cpu_baseline(args.ref_n)
     line = {
-        "metric": METRIC if args.workload == "c2" else "pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s",
+        "metric": METRIC if args.workload == "c2" else "%s_binary_bubble_plus_dew_solves_plus_grads_per_s" % ("pcsaft" if args.workload == "c4" else "gc_pcsaft"),
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
@@ -379,6 +455,16 @@ def main():
         dist.destroy_process_group()
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it may run on."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    return torch.get_num_threads()
+
+
 def _peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -390,7 +476,7 @@ def cpu_baseline(n):
     from oracle import models as om
 
     params, T, p = make_workload(n, 1000, "cpu")
-    threads = torch.get_num_threads()
+    threads = _use_all_host_threads()
     t0 = time.perf_counter()
     x = params.clone().requires_grad_(True)
     model = om.PcSaftPure(x)

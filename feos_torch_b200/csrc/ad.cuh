@@ -17,12 +17,12 @@
 
 #ifdef FEOS_HOST_SIM
 #define FD inline
-#define FD_NOINLINE inline
+#define FD_NOINLINE static inline
 #define FEOS_CONSTANT static const
 #else
 #include <cuda_runtime.h>
 #define FD __device__ __forceinline__
-#define FD_NOINLINE __device__ __noinline__
+#define FD_NOINLINE static __device__ __noinline__
 #define FEOS_CONSTANT __constant__
 #endif
 

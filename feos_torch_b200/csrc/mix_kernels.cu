@@ -17,6 +17,17 @@ namespace feos {
 
 constexpr int kMixBlock = 128;
 
+// The (parameters, k_ij, T)-only coefficients of a state (~70 doubles) live in SHARED memory, one slot
+// per thread, so that the registers hold only the hyper-dual working set of the evaluation.  The slot
+// stride is an odd number of 8-byte words: thread t touches word (stride * t + field), conflict-free.
+constexpr int kModelWords = (sizeof(PcSaftBinary) + 7) / 8;
+constexpr int kModelStride = kModelWords | 1;
+constexpr size_t kMixSmem = sizeof(double) * kModelStride * kMixBlock;
+
+__device__ __forceinline__ PcSaftBinary& model_slot(double* smem) {
+  return *reinterpret_cast<PcSaftBinary*>(smem + (size_t)kModelStride * threadIdx.x);
+}
+
 __device__ __forceinline__ void load_mix(const double* __restrict__ params, const double* __restrict__ kij, int64_t i,
                                          double (&prm)[16], double (&kk)[2]) {
   const double2* p = reinterpret_cast<const double2*>(params + 16 * i);
@@ -60,13 +71,16 @@ mix_point_fwd_kernel(const double* __restrict__ params, const double* __restrict
                      const double* __restrict__ temperature, const double* __restrict__ molefrac, int64_t n, int bubble,
                      double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
                      int32_t* __restrict__ evals, int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count) {
+  extern __shared__ double smem[];
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double prm[16], kk[2];
-  load_mix(params, kij, i, prm, kk);
   double T = temperature[i], z0 = molefrac[i];
-  PcSaftBinary b;
-  pcsaft_binary_init(b, prm, kk, T);
+  PcSaftBinary& b = model_slot(smem);
+  {
+    double prm[16], kk[2];
+    load_mix(params, kij, i, prm, kk);
+    pcsaft_binary_init(b, prm, kk, T);
+  }
   PointState st, se;
   MixEval es, ei;
   int ne = 0;
@@ -235,8 +249,12 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   int32_t* ws = nullptr;
   if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s)) return rc_;
   FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
-  mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, s>>>(params, kij, temperature, molefracs, n, bubble, rho,
-                                                                  pressure, failed, evals, ws + 1, ws);
+  static const int smem_ok = [] {
+    return cudaFuncSetAttribute(mix_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem);
+  }();
+  FEOS_ARG(smem_ok == cudaSuccess);
+  mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, kMixSmem, s>>>(params, kij, temperature, molefracs, n, bubble,
+                                                                         rho, pressure, failed, evals, ws + 1, ws);
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
   mix_point_retry_kernel<<<retry_grid, 64, 0, s>>>(params, kij, temperature, molefracs, bubble, rho, pressure, failed,

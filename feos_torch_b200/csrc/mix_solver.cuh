@@ -205,10 +205,18 @@ FD int point_robust(const Model& mdl, bool bubble, double z0, PointState& st, Mi
 }
 
 // PC-SAFT binary with k_ij as a Model
+// One out-of-line copy of the hyper-dual evaluation per kernel: inlined at its three call sites the
+// solver needs 255 registers and still spills ~1.5 KB per thread.
+FD_NOINLINE void pcsaft_binary_eval(const MixCoef<double>& c, double r0, double r1, MixEval& e) { e = mix_eval(c, r0, r1); }
+
 struct PcSaftBinary {
   MixCoef<double> c;
   double msig3[2];  // pi/6 m_i sigma_i^3
-  FD MixEval eval(double r0, double r1) const { return mix_eval(c, r0, r1); }
+  FD MixEval eval(double r0, double r1) const {
+    MixEval e;
+    pcsaft_binary_eval(c, r0, r1, e);
+    return e;
+  }
   FD double max_density(double x0) const { return kMaxEta / (x0 * msig3[0] + (1.0 - x0) * msig3[1]); }
 };
 
