@@ -9,6 +9,7 @@
 //                            memory per block and added to the global accumulators with one atomic per
 //                            entry and block;
 //   gc_state_kernel          a, p, mu_i, v_i at given (T, rho_1, rho_2)  (GcPcSaftMix.derivatives).
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/feos_b200.h"
@@ -21,6 +22,14 @@ static_assert(FEOS_GC_MAX_SEG == feos::kGcMaxSeg && FEOS_GC_MAX_BOND == feos::kG
 namespace feos {
 
 constexpr int kGcBlock = 128;
+// forward kernels: the ~120-double coefficient structure of a state lives in shared memory (one slot
+// per thread, odd stride in 8-byte words: conflict-free), 64 threads per block -> 3 blocks per SM
+constexpr int kGcFwdBlock = 64;
+constexpr int kGcModelStride = ((sizeof(GcBinary) + 7) / 8) | 1;
+constexpr size_t kGcSmem = sizeof(double) * kGcModelStride * kGcFwdBlock;
+__device__ __forceinline__ GcBinary& gc_model_slot(double* smem) {
+  return *reinterpret_cast<GcBinary*>(smem + (size_t)kGcModelStride * threadIdx.x);
+}
 
 struct GcArgs {
   const GcPair* pairs;
@@ -70,14 +79,15 @@ __device__ __forceinline__ void store_gc_point(int64_t i, int rc, bool bubble, d
   failed[i] = (rc == kStatusOk) ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(kGcBlock)
+__global__ void __launch_bounds__(kGcFwdBlock)
 gc_point_fwd_kernel(GcArgs g, const double* __restrict__ molefrac, int64_t n, int bubble, double* __restrict__ rho,
                     double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
                     int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count) {
+  extern __shared__ double smem[];
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   GcSource src = make_source(g, i);
-  GcBinary b;
+  GcBinary& b = gc_model_slot(smem);
   gc_binary_init(b, src);
   double z0 = molefrac[i];
   PointState st, se;
@@ -148,27 +158,45 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
       // B. inputs of the coefficient stage
       double gi = gout[pos ? (int64_t)pos[i] : i];
       double scale = gi * src.T_ * kPaPerRed;
-      int n_dir = 8 * pr.nseg + n_rec + 3;
-#pragma unroll 1
-      for (int f = 0; f < n_dir; f += 3) {
-        double g3[3];
-        gc_input_grad_pass<3>(src, n_rec, f, cbar, g3);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          int d = f + k;
-          if (d >= n_dir) break;
-          double v = g3[k] * scale;
-          if (d < 8 * pr.nseg) {
-            if (grad_seg && v != 0.0) atomicAdd(&acc[8 * pr.seg[d >> 3] + (d & 7)], v);
-          } else if (d < 8 * pr.nseg + n_rec) {
-            if (grad_kab && v != 0.0) atomicAdd(&acc[8 * n_seg + (d - 8 * pr.nseg)], v);
-          } else if (d < 8 * pr.nseg + n_rec + 2) {
-            gphi[d - 8 * pr.nseg - n_rec] = v;
-          } else {
-            gt = v + gi * p_red * kPaPerRed;  // explicit factor T of p = p_red T kB/A^3
+      // base group (z, m, cd, q1, q2): one reverse-mode sweep; gradients in units of p_red
+      double gseg[8 * kGcMaxSeg];
+      for (int k = 0; k < 8 * pr.nseg; ++k) gseg[k] = 0.0;
+      double gp2[2] = {0.0, 0.0}, gtr = 0.0;
+      double gkab[kGcMaxSeg * kGcMaxSeg];
+      for (int a = 0; a < pr.nseg; ++a)
+        for (int c2 = 0; c2 < pr.nseg; ++c2) gkab[kGcMaxSeg * a + c2] = 0.0;
+      gc_base_adjoint(src, b.c, cbar, gseg, gp2, &gtr, gkab);
+      if (grad_kab) {
+        for (int a = 0; a < pr.nseg; ++a)
+          for (int c2 = 0; c2 < pr.nseg; ++c2) {
+            int r = pr.krec[a][c2];
+            double v = gkab[kGcMaxSeg * a + c2] * scale;
+            if (r >= 0 && v != 0.0) atomicAdd(&acc[8 * n_seg + r], v);
           }
+      }
+      // dipole / association groups (only for pairs that have them): dual passes, 4 directions each
+      int dirs[kGcMaxDirs + 4];
+      int n_dir = gc_active_directions(src, b.c, n_rec, dirs);
+      for (int k = 0; k < 4; ++k) dirs[n_dir + k] = -1;
+#pragma unroll 1
+      for (int f = 0; f < n_dir; f += 4) {
+        double g4[4];
+        gc_input_grad_pass<4, false>(src, n_rec, dirs + f, cbar, g4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int d = dirs[f + k];
+          if (d < 0) break;
+          if (d < 8 * pr.nseg) gseg[d] += g4[k];
+          else gtr += g4[k];
         }
       }
+      for (int k = 0; k < 8 * pr.nseg; ++k) {
+        double v = gseg[k] * scale;
+        if (grad_seg && v != 0.0) atomicAdd(&acc[8 * pr.seg[k >> 3] + (k & 7)], v);
+      }
+      gphi[0] = gp2[0] * scale;
+      gphi[1] = gp2[1] * scale;
+      gt = gtr * scale + gi * p_red * kPaPerRed;  // explicit factor T of p = p_red T kB/A^3
     }
     if (grad_phi) reinterpret_cast<double2*>(grad_phi)[i] = make_double2(gphi[0], gphi[1]);
     if (grad_t) grad_t[i] = gt;
@@ -241,8 +269,12 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   int32_t* ws = nullptr;
   if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s)) return rc_;
   FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
-  gc_point_fwd_kernel<<<grid_for(n, kGcBlock), kGcBlock, 0, s>>>(g, molefracs, n, bubble, rho, pressure, failed, evals,
-                                                              ws + 1, ws);
+  static const int smem_ok = [] {
+    return cudaFuncSetAttribute(gc_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem);
+  }();
+  FEOS_ARG(smem_ok == cudaSuccess);
+  gc_point_fwd_kernel<<<grid_for(n, kGcFwdBlock), kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure,
+                                                                           failed, evals, ws + 1, ws);
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
   gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, bubble, rho, pressure, failed, evals, ws + 1, ws);
@@ -264,6 +296,15 @@ int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   GcArgs a{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
   size_t shmem = sizeof(double) * (size_t)(8 * n_seg + n_rec);
   FEOS_ARG(shmem <= 48 * 1024);
+  // experiment knob: pad the dynamic shared memory to cap the number of resident blocks per SM (the
+  // kernel's per-thread local-memory working set is several KB: fewer resident threads thrash L1/L2 less)
+  static const int pad = [] {
+    const char* e = getenv("FEOS_B200_GC_BWD_SMEM_PAD");
+    int v = e ? atoi(e) : 0;
+    if (v > 0) cudaFuncSetAttribute(gc_point_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v + 48 * 1024);
+    return v;
+  }();
+  shmem += (size_t)pad;
   gc_point_bwd_kernel<<<grid_for(n, kGcBlock), kGcBlock, shmem, (cudaStream_t)stream>>>(
       a, n_seg, n_rec, rho, failed, pos, g, n, bubble, grad_seg_params, grad_kab, grad_phi, grad_temperature);
   FEOS_LAUNCH_OK();

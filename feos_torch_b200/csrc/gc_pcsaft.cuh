@@ -53,11 +53,12 @@ struct GcSource {
 template <int K>
 struct GcDualSource {
   GcSource s;
-  int first, nrec;
+  int ids[K];  // flat direction ids carried by this pass (-1 = unused slot)
+  int nrec;
   FD DN<K> make(double v, int dir) const {
     DN<K> x(v);
 #pragma unroll
-    for (int k = 0; k < K; ++k) x.e[k] = (dir == first + k) ? 1.0 : 0.0;
+    for (int k = 0; k < K; ++k) x.e[k] = (dir == ids[k]) ? 1.0 : 0.0;
     return x;
   }
   FD DN<K> seg(int a, int j) const { return make(s.seg(a, j), 8 * a + j); }
@@ -69,7 +70,9 @@ struct GcDualSource {
   FD DN<K> T() const { return make(s.T_, 8 * s.pair->nseg + nrec + 2); }
 };
 
-template <class P, class Src>
+// BASE = false skips the hard-chain contact distances and the O(nseg^2) dispersion pair loop (their
+// gradient is taken by gc_base_adjoint); z, m are always filled (the dipole group needs m).
+template <class P, class Src, bool BASE = true>
 FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& pr) {
   P T = src.T();
   P ti = ad_recip(T);
@@ -106,7 +109,10 @@ FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& p
     c.bn[b][1] = P(pr.bcnt[1][b]);
   }
   // dispersion (:177-194): eps_ab = sqrt(eps_a eps_b phi_i phi_j)/T (1 - k_ab [i != j])
-  {
+  if (!BASE) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c.q1[k] = c.q2[k] = P(0.0);
+  } else {
     P phi0 = src.phi(0), phi1 = src.phi(1);
     P pp[3] = {phi0 * phi0, phi0 * phi1, phi1 * phi1};
 #pragma unroll
@@ -289,10 +295,16 @@ FD void seed_coef(MixCoef<DN<K>, kGcMaxBond, true>& cd, const GcCoef& c, int fir
 #undef FEOS_X
 }
 
+FD_NOINLINE void gc_binary_eval(const GcCoef& c, double r0, double r1, MixEval& e) { e = mix_eval<kGcMaxBond, true>(c, r0, r1); }
+
 struct GcBinary {
   GcCoef c;
   double msig3[2];
-  FD MixEval eval(double r0, double r1) const { return mix_eval<kGcMaxBond, true>(c, r0, r1); }
+  FD MixEval eval(double r0, double r1) const {
+    MixEval e;
+    gc_binary_eval(c, r0, r1, e);
+    return e;
+  }
   FD double max_density(double x0) const { return kMaxEta / (x0 * msig3[0] + (1.0 - x0) * msig3[1]); }
 };
 
@@ -325,22 +337,142 @@ FD_NOINLINE void gc_coef_adjoint_pass(const GcCoef& c, const double (&spec)[2], 
     if (first + k < ncoef) cbar[first + k] = -N.e[k] / q.denom;
 }
 
-// Step B: K input directions [first, first + K): out[k] = sum_idx cbar[idx] d coef[idx] / d direction
-template <int K>
-FD_NOINLINE void gc_input_grad_pass(const GcSource& src, int nrec, int first, const double* cbar, double (&out)[K]) {
+// The input directions that can have a non-zero gradient for this state: m, sigma, eps of every present
+// segment; mu where the pair is dipolar and the segment carries a dipole (d mu^2 = 0 at mu = 0);
+// kappa, eps_ab, na, nb only if the pair associates; the binary segment records present in the pair;
+// phi_0, phi_1, T.  Returns the number of directions written to `dirs`.
+constexpr int kGcMaxDirs = 8 * kGcMaxSeg + kGcMaxSeg * kGcMaxSeg / 2 + 3;
+FD int gc_active_directions(const GcSource& src, const GcCoef& c, int nrec, int* dirs) {
+  const GcPair& pr = *src.pair;
+  int n = 0;
+  if (!c.dipolar && c.cat == kAssocNone) return 0;  // only the base group: gc_base_adjoint does it all
+  for (int a = 0; a < pr.nseg; ++a) {
+    dirs[n++] = 8 * a;
+    dirs[n++] = 8 * a + 1;
+    dirs[n++] = 8 * a + 2;
+    if (c.dipolar && src.seg(a, 3) != 0.0) dirs[n++] = 8 * a + 3;
+    if (c.cat != kAssocNone)
+      for (int j = 4; j < 8; ++j) dirs[n++] = 8 * a + j;
+  }
+  // (phi and the binary segment records enter the dispersion term only -> base adjoint)
+  (void)nrec;
+  dirs[n++] = 8 * pr.nseg + nrec + 2;  // T
+  return n;
+}
+
+// Step B, base group: reverse-mode sweep through the part of the coefficient stage that produces
+// z[k][i], m[i], cd[b], q1[k], q2[k] (flat coefficient indices 0 .. 15 + nbond).  Given the adjoints
+// cbar it ADDS  sum_idx cbar[idx] d coef[idx] / d theta  to
+//   gseg[8 a + j]  (j = 0, 1, 2: m, sigma, eps of local segment a),  gphi[2],  gT,  and
+//   gkab[kGcMaxSeg a + b] for the k_ab of the segment pair (a in molecule 0, b in molecule 1).
+// (__noinline__ like the pass functions: see the compiler note in gc_kernels.cu)
+FD_NOINLINE void gc_base_adjoint(const GcSource& src, const GcCoef& c, const double* cbar, double* gseg, double* gphi,
+                                 double* gT_out, double* gkab) {
+  double gT = 0.0;
+  const GcPair& pr = *src.pair;
+  const int ns = pr.nseg;
+  const double T = src.T(), ti = 1.0 / T;
+  double d[kGcMaxSeg], dbar[kGcMaxSeg], ex[kGcMaxSeg];
+  // z[k][i] = pi/6 sum_a n_ia m_a d_a^k (indices 2k + i), m[i] = sum_a n_ia m_a (8 + i)
+  for (int a = 0; a < ns; ++a) {
+    double m = src.seg(a, 0), s = src.seg(a, 1), e = src.seg(a, 2);
+    ex[a] = exp(-3.0 * e * ti);
+    double da = s * (1.0 - 0.12 * ex[a]);
+    d[a] = da;
+    double mb = 0.0, db = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double n = pr.cnt[i][a];
+      if (n == 0.0) continue;
+      double w = kPi / 6.0 * n;
+      double z0 = cbar[i], z1 = cbar[2 + i], z2 = cbar[4 + i], z3 = cbar[6 + i];
+      mb += w * (z0 + da * (z1 + da * (z2 + da * z3))) + cbar[8 + i] * n;
+      db += w * m * (z1 + da * (2.0 * z2 + 3.0 * da * z3));
+    }
+    gseg[8 * a] += mb;
+    dbar[a] = db;
+  }
+  // cd[b] = d_a d_b / (d_a + d_b) (indices 16 + b)
+  for (int b = 0; b < pr.nbond; ++b) {
+    int ia = pr.ba[b], ib = pr.bb[b];
+    double sum = d[ia] + d[ib], cb = cbar[16 + b] / (sum * sum);
+    if (ia == ib) {
+      dbar[ia] += cbar[16 + b] * 0.5;
+    } else {
+      dbar[ia] += cb * d[ib] * d[ib];
+      dbar[ib] += cb * d[ia] * d[ia];
+    }
+  }
+  // d_a = sigma_a (1 - 0.12 exp(-3 eps_a / T))
+  for (int a = 0; a < ns; ++a) {
+    double s = src.seg(a, 1), e = src.seg(a, 2);
+    gseg[8 * a + 1] += dbar[a] * d[a] / s;
+    double de = dbar[a] * s * 0.36 * ex[a] * ti;
+    gseg[8 * a + 2] += de;
+    gT -= de * e * ti;
+  }
+  // q1[k] = sum_ab nn_k m_a m_b eab s3ab (indices 10 + k), q2[k] = sum ... eab^2 (13 + k)
+  const double phi0 = src.phi(0), phi1 = src.phi(1);
+  const double pp[3] = {phi0 * phi0, phi0 * phi1, phi1 * phi1};
+  double ppb[3] = {0.0, 0.0, 0.0};
+  for (int a = 0; a < ns; ++a) {
+    double ma = src.seg(a, 0), sa = src.seg(a, 1), ea = src.seg(a, 2);
+    for (int b = 0; b < ns; ++b) {
+      double mb = src.seg(b, 0), sb = src.seg(b, 1), eb = src.seg(b, 2);
+      double ee = ea * eb;
+      if (ee == 0.0) continue;
+      double sab = 0.5 * (sa + sb), s3 = sab * sab * sab;
+      const int ci[3] = {0, 0, 1}, cj[3] = {0, 1, 1};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double nn = pr.cnt[ci[k]][a] * pr.cnt[cj[k]][b];
+        if (nn == 0.0) continue;
+        double kab = (k == 1) ? src.kab_of(a, b) : 0.0;
+        double eab = sqrt(ee * pp[k]) * ti * (1.0 - kab);
+        double t = nn * ma * mb * eab * s3;
+        double tb = cbar[10 + k] + cbar[13 + k] * eab;       // adjoint of t
+        double eb_ = (tb + cbar[13 + k] * eab) * t;          // eab * (adjoint of eab)
+        double tt = tb * t;
+        gseg[8 * a] += tt / ma;
+        gseg[8 * b] += tt / mb;
+        double sg = tt * 1.5 / sab;                          // d s3 / d sigma_a = 1.5 s3 / sab
+        gseg[8 * a + 1] += sg;
+        gseg[8 * b + 1] += sg;
+        gseg[8 * a + 2] += 0.5 * eb_ / ea;
+        gseg[8 * b + 2] += 0.5 * eb_ / eb;
+        ppb[k] += 0.5 * eb_ / pp[k];
+        gT -= eb_ * ti;
+        if (k == 1 && pr.krec[a][b] >= 0) gkab[kGcMaxSeg * a + b] += -eb_ / (1.0 - kab);
+      }
+    }
+  }
+  gphi[0] += 2.0 * phi0 * ppb[0] + phi1 * ppb[1];
+  gphi[1] += phi0 * ppb[1] + 2.0 * phi1 * ppb[2];
+  *gT_out += gT;
+  (void)c;
+}
+
+// Step B: K input directions ids[0..K): out[k] = sum_idx cbar[idx] d coef[idx] / d direction ids[k]
+// ALL = true: every coefficient (cross-check of gc_base_adjoint in the CPU tests); ALL = false: only the
+// dipole and association groups (flat index >= 16 + nbond), the base group being handled by the adjoint.
+template <int K, bool ALL>
+FD_NOINLINE void gc_input_grad_pass(const GcSource& src, int nrec, const int* ids, const double* cbar, double (&out)[K]) {
   GcDualSource<K> ds;
   ds.s = src;
-  ds.first = first;
+#pragma unroll
+  for (int k = 0; k < K; ++k) ds.ids[k] = ids[k];
   ds.nrec = nrec;
   MixCoef<DN<K>, kGcMaxBond, true> cd;
-  gc_coef<DN<K>, GcDualSource<K>>(cd, ds, *src.pair);
+  gc_coef<DN<K>, GcDualSource<K>, ALL>(cd, ds, *src.pair);
 #pragma unroll
   for (int k = 0; k < K; ++k) out[k] = 0.0;
   int idx = 0;
-#define FEOS_X(f)                                               \
-  {                                                             \
-    for (int k = 0; k < K; ++k) out[k] += cbar[idx] * f.e[k];   \
-    ++idx;                                                      \
+  const int skip = ALL ? 0 : 16 + cd.nbond;
+#define FEOS_X(f)                                                 \
+  {                                                               \
+    if (idx >= skip)                                              \
+      for (int k = 0; k < K; ++k) out[k] += cbar[idx] * f.e[k];   \
+    ++idx;                                                        \
   }
   FEOS_VISIT_COEF(cd, FEOS_X)
 #undef FEOS_X

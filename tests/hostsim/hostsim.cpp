@@ -307,7 +307,8 @@ void sim_gc_point(const GcPair* pairs, const double* seg, const double* kab, con
 // grad_seg [n_seg,8] and grad_kab [n_rec] accumulate over states; grad_phi [n,2], grad_t [n]
 void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const double* kab, int n_rec,
                       const int32_t* idx, const double* phi, const double* T, const double* rho, int64_t n, int bubble,
-                      const double* g, double* grad_seg, double* grad_kab, double* grad_phi, double* grad_t) {
+                      const double* g, double* grad_seg, double* grad_kab, double* grad_phi, double* grad_t,
+                      int generic_all) {
   for (int64_t i = 0; i < n; ++i) {
     GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
     const GcPair& pr = *s.pair;
@@ -325,19 +326,48 @@ void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const d
     int ncoef = coef_count(b.c);
     for (int f = 0; f < ncoef; f += 3) gc_coef_adjoint_pass<3>(b.c, spec, inc, q, f, ncoef, cbar);
     double scale = g[i] * T[i] * kPaPerRed;
-    int n_dir = 8 * pr.nseg + n_rec + 3;
-    for (int f = 0; f < n_dir; f += 3) {
-      double g3[3];
-      gc_input_grad_pass<3>(s, n_rec, f, cbar, g3);
-      for (int k = 0; k < 3 && f + k < n_dir; ++k) {
-        int d = f + k;
-        double v = g3[k] * scale;
-        if (d < 8 * pr.nseg) grad_seg[8 * pr.seg[d >> 3] + (d & 7)] += v;
-        else if (d < 8 * pr.nseg + n_rec) grad_kab[d - 8 * pr.nseg] += v;
-        else if (d < 8 * pr.nseg + n_rec + 2) grad_phi[2 * i + d - 8 * pr.nseg - n_rec] = v;
-        else grad_t[i] = v + g[i] * p_red * kPaPerRed;
+    double gseg[8 * kGcMaxSeg];
+    for (int k = 0; k < 8 * pr.nseg; ++k) gseg[k] = 0.0;
+    double gp2[2] = {0.0, 0.0}, gtr = 0.0;
+    if (generic_all) {
+      // cross-check path: every coefficient through dual passes over ALL input directions
+      int n_all = 8 * pr.nseg + n_rec + 3;
+      for (int f = 0; f < n_all; f += 4) {
+        int ids[4];
+        for (int k = 0; k < 4; ++k) ids[k] = (f + k < n_all) ? f + k : -1;
+        double g4[4];
+        gc_input_grad_pass<4, true>(s, n_rec, ids, cbar, g4);
+        for (int k = 0; k < 4 && ids[k] >= 0; ++k) {
+          int d = ids[k];
+          if (d < 8 * pr.nseg) gseg[d] += g4[k];
+          else if (d < 8 * pr.nseg + n_rec) grad_kab[d - 8 * pr.nseg] += g4[k] * scale;
+          else if (d < 8 * pr.nseg + n_rec + 2) gp2[d - 8 * pr.nseg - n_rec] += g4[k];
+          else gtr += g4[k];
+        }
+      }
+    } else {
+      double gkab[kGcMaxSeg * kGcMaxSeg] = {0.0};
+      gc_base_adjoint(s, b.c, cbar, gseg, gp2, &gtr, gkab);
+      for (int a = 0; a < pr.nseg; ++a)
+        for (int c2 = 0; c2 < pr.nseg; ++c2)
+          if (pr.krec[a][c2] >= 0) grad_kab[pr.krec[a][c2]] += gkab[kGcMaxSeg * a + c2] * scale;
+      int dirs[kGcMaxDirs + 4];
+      int n_dir = gc_active_directions(s, b.c, n_rec, dirs);
+      for (int k = 0; k < 4; ++k) dirs[n_dir + k] = -1;
+      for (int f = 0; f < n_dir; f += 4) {
+        double g4[4];
+        gc_input_grad_pass<4, false>(s, n_rec, dirs + f, cbar, g4);
+        for (int k = 0; k < 4 && dirs[f + k] >= 0; ++k) {
+          int d = dirs[f + k];
+          if (d < 8 * pr.nseg) gseg[d] += g4[k];
+          else gtr += g4[k];
+        }
       }
     }
+    for (int k = 0; k < 8 * pr.nseg; ++k) grad_seg[8 * pr.seg[k >> 3] + (k & 7)] += gseg[k] * scale;
+    grad_phi[2 * i] = gp2[0] * scale;
+    grad_phi[2 * i + 1] = gp2[1] * scale;
+    grad_t[i] = gtr * scale + g[i] * p_red * kPaPerRed;
   }
 }
 }

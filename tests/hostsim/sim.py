@@ -141,11 +141,12 @@ def gc_point(pairs, seg, kab, idx, phi, T, z, bubble):
     return rho, val, status, evals
 
 
-def gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g):
+def gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g, generic=False):
     pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
     rho, g = c64(rho), c64(g)
     n = T.shape[0]
     gs = np.zeros_like(seg); gk = np.zeros_like(kab); gp = np.zeros((n, 2)); gt = np.zeros(n)
     lib().sim_gc_point_bwd(_p(pairs), _p(seg), ctypes.c_int(seg.shape[0]), _p(kab), ctypes.c_int(kab.shape[0]), _p(idx), _p(phi),
-                           _p(T), _p(rho), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(g), _p(gs), _p(gk), _p(gp), _p(gt))
+                           _p(T), _p(rho), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(g), _p(gs), _p(gk), _p(gp), _p(gt),
+                           ctypes.c_int(int(generic)))
     return gs, gk, gp, gt

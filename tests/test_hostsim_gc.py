@@ -101,3 +101,23 @@ def test_reference_gc_configs(golden_gc):
         gs, gk, gp, gt = sim.gc_point_bwd(pairs, seg, kab, idx, phi, np.array([cfg["T"]]), rho, bubble, np.ones(1))
         assert abs(gk[0] - g["grad_kab"][0]) < 1e-8 * abs(g["grad_kab"][0])
         assert abs(gt[0] - g["grad_T"][0]) < 1e-8 * abs(g["grad_T"][0])
+
+
+def test_base_adjoint_equals_dual_passes(golden_gc):
+    """The reverse-mode sweep over the base coefficient group (+ dual passes restricted to the dipole /
+    association groups) against dual passes over every input direction and every coefficient."""
+    ident, seg = table(golden_gc)
+    e = golden_gc["category_grid"]
+    rows = e["category"]
+    pairs, idx = build_pair_table(ident, [cases.GC_SEGMENTS[i] for i in rows], [cases.GC_BONDS[i] for i in rows], cases.GC_KAB)
+    kab = np.array([k[2] for k in cases.GC_KAB])
+    T, z = np.array(e["T"]), np.array(e["z"])
+    n = len(T)
+    phi = np.array([cases.GC_PHI] * n)
+    g = np.linspace(0.5, 1.5, n)
+    for bubble in (True, False):
+        rho = sim.gc_point(pairs, seg, kab, idx, phi, T, z, bubble)[0]
+        a = sim.gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g, generic=True)
+        b = sim.gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g)
+        for x, y in zip(a, b):
+            assert np.abs(x - y).max() <= 1e-10 * np.abs(x).max()
