@@ -243,14 +243,14 @@ FD void pure_state_grad(const double* prm, double T, double rho, double (&da)[9]
 //   out[0..8] = gv d(vp)/d(theta) + gr d(rho_l_eq)/d(theta)
 template <bool NEED_RLEQ>
 FD void pure_vle_grad(const double* prm, double T, double rho_v, double rho_l, double dp_l, double gv, double gr,
-                      double (&out)[9]) {
+                      bool need_t, double (&out)[9]) {
   double av[9], avp[9], al[9], alp[9];
   pure_state_grad<false>(prm, T, rho_v, av, avp);
   pure_state_grad<NEED_RLEQ>(prm, T, rho_l, al, alp);
   const double dv = 1.0 / rho_v - 1.0 / rho_l;
   // the value of p_m is needed for the explicit factor T of vp = p_m T kB/A^3
   double pm = 0.0;
-  {
+  if (need_t) {
     PureCoef<double> c;
     pure_coef<double>(c, prm[0], prm[1], prm[2], prm[3], prm[4], prm[5], prm[6], prm[7], T, false);
     PureEval ev = pure_eval(c, rho_v), el = pure_eval(c, rho_l);

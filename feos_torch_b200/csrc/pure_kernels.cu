@@ -211,7 +211,7 @@ pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict_
     dpl = pure_eval(c, rr.y).dp;
   }
   double out[9];
-  pure_vle_grad<NEED_RLEQ>(r.v, T, rr.x, rr.y, dpl, gv, gr, out);
+  pure_vle_grad<NEED_RLEQ>(r.v, T, rr.x, rr.y, dpl, gv, gr, grad_t != nullptr, out);
   double2* gp = reinterpret_cast<double2*>(grad_params + 8 * i);
 #pragma unroll
   for (int k = 0; k < 4; ++k) gp[k] = make_double2(out[2 * k], out[2 * k + 1]);

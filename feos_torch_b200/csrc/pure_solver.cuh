@@ -21,6 +21,10 @@
 
 namespace feos {
 
+// liquid density iterations start at packing fraction 0.45: right of the root for all but the coldest
+// states (from the left Newton overshoots once and then descends monotonically as well); measured on
+// the C2 grid: 12.2 instead of 12.9 evaluations per state, same retry fraction
+constexpr double kLiquidStart = 0.9;
 constexpr double kVleTol = 1e-8;  // accepted Newton step; the applied step squares the error
 constexpr int kStatusOk = 0, kStatusFailed = 1, kStatusRetry = 2;
 
@@ -71,7 +75,7 @@ FD int pure_vle_newton(const PureCoef<double>& c, double& rho_l, double& u, Pure
 
 FD int pure_vle_fast(const PureCoef<double>& c, double rho_max, double& rho_l, double& u, PureEval& el,
                      PureEval& ev, double& rho_l_eval, double& rho_v_eval, int& evals) {
-  rho_l = rho_max;
+  rho_l = kLiquidStart * rho_max;
   u = 0.0;
   bool ready = false;
   for (int it = 0; it < 24; ++it) {
@@ -106,7 +110,7 @@ struct PureVleMachine {
   bool have_prev;
 
   FD void start(double rho_max) {
-    rho_l = rho_max;
+    rho_l = kLiquidStart * rho_max;
     u = 0.0;
     phase = 0;
     it = 0;

@@ -311,24 +311,30 @@ def binary_bubble_dew(helm, max_density_fn, temperature, molefrac1, pressure_pa,
     rho_v = p.clone()
 
     # successive substitution sweeps (moderate count; Newton polish follows)
-    for _ in range(25):
+    for _ in range(40):
         rho_l = _density_at_p(helm, T, x_l, p, rho_l, rmax(x_l), True, n_iter=6)
         rho_v = _density_at_p(helm, T, y_v, p, rho_v, rmax(y_v), False, n_iter=6)
         _, g_l, _, _, _ = _mix_props(helm, T, rho_l[:, None] * x_l)
         _, g_v, _, _, _ = _mix_props(helm, T, rho_v[:, None] * y_v)
         lnk = (g_l - torch.log(p / rho_l)[:, None]) - (g_v - torch.log(p / rho_v)[:, None])  # ln phi_L - ln phi_V
+        # damped successive substitution (geometric mean of old and new): plain substitution oscillates
+        # with growing amplitude for strongly non-ideal (cross-associating) pairs
         if bubble:
             new = x_l * torch.exp(lnk)
             s = new.sum(dim=1)
-            change = (new / s[:, None] - y_v).abs().max()
-            y_v = new / s[:, None]
-            p = p * s.clamp(0.5, 2.0)
+            upd = torch.sqrt(y_v * new / s[:, None])
+            upd = upd / upd.sum(dim=1, keepdim=True)
+            change = (upd - y_v).abs().max()
+            y_v = upd
+            p = p * torch.sqrt(s.clamp(0.5, 2.0))
         else:
             new = y_v * torch.exp(-lnk)
             s = new.sum(dim=1)
-            change = (new / s[:, None] - x_l).abs().max()
-            x_l = new / s[:, None]
-            p = p / s.clamp(0.5, 2.0)
+            upd = torch.sqrt(x_l * new / s[:, None])
+            upd = upd / upd.sum(dim=1, keepdim=True)
+            change = (upd - x_l).abs().max()
+            x_l = upd
+            p = p / torch.sqrt(s.clamp(0.5, 2.0))
         if bool(change < 1e-7) and bool(((s - 1.0).abs() < 1e-7).all()):
             break  # the Newton polish below takes it from here
 

@@ -92,8 +92,8 @@ void sim_pure_vle_bwd_fast(const double* params, const double* T, const double* 
     load_coef(params + 8 * i, T[i], c, rho_max);
     double dpl = pure_eval(c, rl).dp;
     double out[9];
-    if (gr) pure_vle_grad<true>(params + 8 * i, T[i], rv, rl, dpl, gv ? gv[i] : 0.0, gr[i], out);
-    else pure_vle_grad<false>(params + 8 * i, T[i], rv, rl, dpl, gv[i], 0.0, out);
+    if (gr) pure_vle_grad<true>(params + 8 * i, T[i], rv, rl, dpl, gv ? gv[i] : 0.0, gr[i], true, out);
+    else pure_vle_grad<false>(params + 8 * i, T[i], rv, rl, dpl, gv[i], 0.0, true, out);
     for (int k = 0; k < 9; ++k) grad[9 * i + k] = out[k];
   }
 }
