@@ -56,7 +56,7 @@ FD PointWeights point_weights(const MixEval& es, const double (&spec)[2], const 
 
 // out[k] = g * d(p_bubble/dew [Pa]) / d(direction first + k)
 template <int K>
-FD void mix_point_grad_pass(const double (&prm)[16], const double (&kij)[2], double T, const double (&spec)[2],
+FD_NOINLINE void mix_point_grad_pass(const double (&prm)[16], const double (&kij)[2], double T, const double (&spec)[2],
                             const double (&inc)[2], const PointWeights& q, int first, double g, double (&out)[K]) {
   DN<K> p[16], k[2], t;
   mix_seed<K>(prm, kij, T, first, p, k, t);

@@ -63,7 +63,7 @@ __device__ __forceinline__ void store_vle(int64_t i, int st, double rho_l, doubl
   failed[i] = (st == kStatusOk) ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 pure_vle_fwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature, int64_t n,
                     double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
                     uint8_t* __restrict__ failed, int32_t* __restrict__ evals, int32_t* __restrict__ retry_list,
@@ -93,13 +93,13 @@ pure_vle_fwd_kernel(const double* __restrict__ params, const double* __restrict_
 // iterations, depending on T/T_c) take the next state from a global queue instead of idling until the
 // slowest lane of the warp is done.  Refills are batched (>= kRefillMin idle lanes, warp-aggregated
 // atomic) so that the divergent set-up section (parameter load + coefficient stage) is amortised.
-constexpr int kRefillMin = 6;
+constexpr int kRefillMin = 8;
 
 // one copy of the evaluation code that all lanes of the warp enter together (inlined, the compiler
 // specialises it per solver phase and the lanes diverge: 12.6 of 32 active lanes per instruction)
 __device__ __noinline__ void pure_eval_call(const PureCoef<double>& c, double rho, PureEval& e) { e = pure_eval(c, rho); }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 5)
 pure_vle_queue_kernel(const double* __restrict__ params, const double* __restrict__ temperature, int n,
                       double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
                       uint8_t* __restrict__ failed, int32_t* __restrict__ evals, int32_t* __restrict__ retry_list,
@@ -107,6 +107,7 @@ pure_vle_queue_kernel(const double* __restrict__ params, const double* __restric
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   bool active = false, exhausted = false;
+  int done = kRunning;  // status of a finished state whose results are still to be written
   int idx = 0, ne = 0;
   double T = 0.0;
   PureCoef<double> c;
@@ -118,42 +119,71 @@ pure_vle_queue_kernel(const double* __restrict__ params, const double* __restric
     unsigned idle = __ballot_sync(full, !active);
     if (idle) {
       int nidle = __popc(idle);
-      if (!exhausted && (nidle >= kRefillMin || nidle == 32)) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(queue_head, nidle);
-        base = __shfl_sync(full, base, 0);
-        int mine = base + __popc(idle & ((1u << lane) - 1u));
-        if (!active && mine < n) {
-          idx = mine;
-          PureRow r = load_row(params, idx);
-          T = temperature[idx];
-          double rho_max;
-          make_coef(r, T, c, rho_max);
-          m.start(rho_max);
-          ne = 0;
-          active = true;
+      // Divergent section, entered when enough lanes wait: write the results of finished states and hand
+      // out new ones.  Batching it amortises the set-up and store code over >= kRefillMin lanes.
+      if ((!exhausted && nidle >= kRefillMin) || nidle == 32) {
+        if (done != kRunning) {
+          if (evals) evals[idx] = ne;
+          if (done == kStatusRetry) {
+            retry_list[atomicAdd(retry_count, 1)] = idx;
+          } else {
+            double u = m.u;
+            store_vle(idx, done, m.rho_l, u, m.el, m.ev, m.rle, m.rve, T, rho, vp, rleq, failed);
+          }
+          done = kRunning;
         }
-        if (base + nidle >= n) exhausted = true;
-        idle = __ballot_sync(full, !active);
+        if (!exhausted) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(queue_head, nidle);
+          base = __shfl_sync(full, base, 0);
+          int mine = base + __popc(idle & ((1u << lane) - 1u));
+          if (!active && mine < n) {
+            idx = mine;
+            PureRow r = load_row(params, idx);
+            T = temperature[idx];
+            double rho_max;
+            make_coef(r, T, c, rho_max);
+            m.start(rho_max);
+            ne = 0;
+            active = true;
+          }
+          if (base + nidle >= n) exhausted = true;
+          idle = __ballot_sync(full, !active);
+        }
       }
-      if (exhausted && idle == full) break;
+      if (exhausted && idle == full) {
+        // flush what finished since the last refill (reached with every lane idle)
+        if (done != kRunning) {
+          if (evals) evals[idx] = ne;
+          if (done == kStatusRetry) {
+            retry_list[atomicAdd(retry_count, 1)] = idx;
+          } else {
+            double u = m.u;
+            store_vle(idx, done, m.rho_l, u, m.el, m.ev, m.rle, m.rve, T, rho, vp, rleq, failed);
+          }
+        }
+        break;
+      }
     }
+    // converged: evaluation, log(rho_l) and exp(u) are issued by all 32 lanes; only the cheap
+    // bookkeeping halves in between diverge by solver phase
     double rho_eval = m.density();
     PureEval e;
     __syncwarp();
     pure_eval_call(c, rho_eval, e);
+    double L = log(m.rho_l);
+    int st = kRunning;
     if (active) {
       ++ne;
-      int st = m.advance(e);
+      st = m.advance1(e, L);
+    }
+    __syncwarp();
+    double X = exp(m.u);
+    if (active) {
+      if (st == kRunning) st = m.advance2(X);
       if (st != kRunning) {
         active = false;
-        if (evals) evals[idx] = ne;
-        if (st == kStatusRetry) {
-          retry_list[atomicAdd(retry_count, 1)] = idx;
-        } else {
-          double u = m.u;
-          store_vle(idx, st, m.rho_l, u, m.el, m.ev, m.rle, m.rve, T, rho, vp, rleq, failed);
-        }
+        done = st;
       }
     }
   }
@@ -182,7 +212,7 @@ pure_vle_retry_kernel(const double* __restrict__ params, const double* __restric
 }
 
 template <bool NEED_RLEQ>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 3)
 pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                     const double* __restrict__ rho, const uint8_t* __restrict__ failed,
                     const int32_t* __restrict__ pos, const double* __restrict__ g_vp,
@@ -218,7 +248,7 @@ pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict_
   if (grad_t) grad_t[i] = out[8];
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 4)
 pure_rho_tp_fwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                        const double* __restrict__ pressure, int64_t n, double* __restrict__ rho,
                        double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals) {
@@ -242,7 +272,7 @@ pure_rho_tp_fwd_kernel(const double* __restrict__ params, const double* __restri
   if (evals) evals[i] = ne;
 }
 
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 3)
 pure_rho_tp_bwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                        const double* __restrict__ pressure, const double* __restrict__ rho,
                        const uint8_t* __restrict__ failed, const int32_t* __restrict__ pos,
@@ -327,13 +357,13 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
   if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
   FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
   static const int variant = [] {
-    // "queue" = persistent work-queue kernel, default = one thread per state.  Measured on B200 (1 M C2
-    // states, ncu): 1.07 ms vs 1.08 ms -- the queue keeps more lanes busy per evaluation but pays for it
-    // with divergent bookkeeping (profiles/r1_pure_vle_queue_vs_loop.md)
+    // default = persistent work-queue kernel; "loop" = one thread per state.  Measured on B200 (1 M C2
+    // states, ncu): queue 0.566 ms with 22.4 of 32 lanes active per instruction, loop 0.572 ms with 16.9
+    // (profiles/README.md)
     const char* e = getenv("FEOS_B200_PURE_VLE_KERNEL");
-    return (e && e[0] == 'q') ? 1 : 0;
+    return (e && e[0] == 'l') ? 0 : 1;
   }();
-  if (variant == 0 || n < 4096) {
+  if (variant == 0 || n < 65536) {
     pure_vle_fwd_kernel<<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, n, rho, vapor_pressure,
                                                              liquid_density, failed, evals, ws + 2, ws);
   } else {

@@ -100,6 +100,9 @@ FD int pure_vle_fast(const PureCoef<double>& c, double rho_max, double& rho_l, d
 // up new states from a work queue as they finish (pure_vle_queue_kernel).  Same arithmetic, iteration
 // limits and results as pure_vle_fast().
 constexpr int kRunning = -1;
+// Every trip costs one evaluation at density(), one log and one exp, issued by ALL lanes of the warp
+// between the two (cheap, divergent) bookkeeping halves:
+//   e = eval(density());  st = advance1(e, log(rho_l));  if (st == kRunning) st = advance2(exp(u));
 struct PureVleMachine {
   double rho_l, u;                 // current iterate (u = ln rho_v)
   double prev_l, prev_u, dl, du;   // back-tracking
@@ -112,45 +115,25 @@ struct PureVleMachine {
   FD void start(double rho_max) {
     rho_l = kLiquidStart * rho_max;
     u = 0.0;
+    rho_v = 1.0;
     phase = 0;
     it = 0;
   }
-  FD double density() {
-    if (phase == 2) {
-      rho_v = exp(u);
-      return rho_v;
-    }
-    return rho_l;
-  }
-  FD int advance(const PureEval& e) {
+  FD double density() const { return phase == 2 ? rho_v : rho_l; }
+
+  // first half: consumes the evaluation and L = log(rho_l) (of the density before any update)
+  FD int advance1(const PureEval& e, double L) {
     if (phase == 0) {  // liquid density iteration towards the ideal-vapour pressure estimate
       if (!(e.dp > 0.0)) return kStatusRetry;
-      u = log(rho_l) + e.a1 - e.p / rho_l;
-      double delta = (exp(u) - e.p) / e.dp;
-      delta = fmax(delta, -0.3 * rho_l);
-      rho_l += delta;
-      ++it;
-      if (fabs(delta) < 0.02 * rho_l) {
-        if (!(u == u)) return kStatusRetry;
-        phase = 1;
-        it = 0;
-        prev_l = rho_l;
-        prev_u = u;
-        dl = du = 0.0;
-        have_prev = false;
-        halvings = 0;
-      } else if (it >= 24) {
-        return kStatusRetry;
-      }
+      el = e;
+      u = L + e.a1 - e.p / rho_l;
       return kRunning;
     }
     if (phase == 1) {  // liquid evaluation of a Newton iteration: wait for the vapour one
       el = e;
-      phase = 2;
       return kRunning;
     }
     ev = e;
-    phase = 1;
     ++it;
     bool bad = !(el.dp > 0.0) || !(ev.dp > 0.0) || !(rho_l > rho_v);
     if (bad) {
@@ -165,7 +148,7 @@ struct PureVleMachine {
     double D = 1.0 - rho_v / rho_l;
     if (D < 1e-5) return kStatusRetry;
     double F1 = el.p - ev.p;
-    double F2 = (el.a1 - ev.a1) + (log(rho_l) - u);
+    double F2 = (el.a1 - ev.a1) + (L - u);
     dl = -(F1 - rho_v * F2) / (el.dp * D);
     du = (F2 - F1 / rho_l) / (ev.dp * D);
     if (!(fabs(dl) < 1e300) || !(fabs(du) < 1e300)) return kStatusRetry;
@@ -180,6 +163,37 @@ struct PureVleMachine {
     u += du;
     if (fabs(dl) <= kVleTol * prev_l && fabs(du) <= kVleTol) return kStatusOk;
     return it >= 30 ? kStatusRetry : kRunning;
+  }
+
+  // second half: X = exp(u)
+  FD int advance2(double X) {
+    if (phase == 0) {
+      double delta = (X - el.p) / el.dp;
+      delta = fmax(delta, -0.3 * rho_l);
+      rho_l += delta;
+      ++it;
+      if (fabs(delta) < 0.02 * rho_l) {
+        if (!(u == u)) return kStatusRetry;
+        phase = 1;
+        it = 0;
+        rho_v = X;
+        prev_l = rho_l;
+        prev_u = u;
+        dl = du = 0.0;
+        have_prev = false;
+        halvings = 0;
+      } else if (it >= 24) {
+        return kStatusRetry;
+      }
+      return kRunning;
+    }
+    if (phase == 1) {
+      phase = 2;
+      return kRunning;
+    }
+    rho_v = X;
+    phase = 1;
+    return kRunning;
   }
 };
 

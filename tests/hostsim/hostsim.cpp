@@ -51,7 +51,8 @@ void sim_pure_vle_machine(const double* params, const double* T, int64_t n, doub
     while (st == kRunning) {
       PureEval e = pure_eval(c, m.density());
       ++ne;
-      st = m.advance(e);
+      st = m.advance1(e, log(m.rho_l));
+      if (st == kRunning) st = m.advance2(exp(m.u));
     }
     status[i] = (uint8_t)st;
     evals[i] = ne;
