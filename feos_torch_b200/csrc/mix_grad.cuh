@@ -16,24 +16,25 @@ namespace feos {
 
 constexpr int kMixDirs = 19;
 
+// ids[d] = direction carried by dual slot d: 0..15 parameters, 16/17 kij, 18 T, -1 unused
 template <int K>
-FD void mix_seed(const double (&prm)[16], const double (&kij)[2], double T, int first, DN<K> (&p)[16], DN<K> (&k)[2],
-                 DN<K>& t) {
+FD void mix_seed(const double (&prm)[16], const double (&kij)[2], double T, const int* ids, DN<K> (&p)[16],
+                 DN<K> (&k)[2], DN<K>& t) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     p[i] = DN<K>(prm[i]);
 #pragma unroll
-    for (int d = 0; d < K; ++d) p[i].e[d] = (i == first + d) ? 1.0 : 0.0;
+    for (int d = 0; d < K; ++d) p[i].e[d] = (i == ids[d]) ? 1.0 : 0.0;
   }
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     k[i] = DN<K>(kij[i]);
 #pragma unroll
-    for (int d = 0; d < K; ++d) k[i].e[d] = (16 + i == first + d) ? 1.0 : 0.0;
+    for (int d = 0; d < K; ++d) k[i].e[d] = (16 + i == ids[d]) ? 1.0 : 0.0;
   }
   t = DN<K>(T);
 #pragma unroll
-  for (int d = 0; d < K; ++d) t.e[d] = (18 == first + d) ? 1.0 : 0.0;
+  for (int d = 0; d < K; ++d) t.e[d] = (18 == ids[d]) ? 1.0 : 0.0;
 }
 
 // weights of the Newton-step formula from the primal evaluation of the specified phase
@@ -54,12 +55,12 @@ FD PointWeights point_weights(const MixEval& es, const double (&spec)[2], const 
   return q;
 }
 
-// out[k] = g * d(p_bubble/dew [Pa]) / d(direction first + k)
+// out[k] = g * d(p_bubble/dew [Pa]) / d(direction ids[k])
 template <int K>
 FD_NOINLINE void mix_point_grad_pass(const double (&prm)[16], const double (&kij)[2], double T, const double (&spec)[2],
-                            const double (&inc)[2], const PointWeights& q, int first, double g, double (&out)[K]) {
+                            const double (&inc)[2], const PointWeights& q, const int* ids, double g, double (&out)[K]) {
   DN<K> p[16], k[2], t;
-  mix_seed<K>(prm, kij, T, first, p, k, t);
+  mix_seed<K>(prm, kij, T, ids, p, k, t);
   MixCoef<DN<K>> c;
   mix_coef<DN<K>>(c, p, k, t, true);
   DN<K> a_inc = mix_helmholtz<DN<K>, DN<K>, 2, false>(c, DN<K>(inc[0]), DN<K>(inc[1]));

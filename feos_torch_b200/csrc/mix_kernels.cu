@@ -150,20 +150,28 @@ mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict
     q = point_weights(es, spec, inc);
   }
   double gi = g[pos ? (int64_t)pos[i] : i];
+  // only the directions whose gradient is requested (a k_ij fit needs 1 pass instead of 7)
+  int dirs[24];
+  int nd = 0;
+  if (grad_params)
+    for (int d = 0; d < 16; ++d) dirs[nd++] = d;
+  if (grad_kij) {
+    dirs[nd++] = 16;
+    dirs[nd++] = 17;
+  }
+  if (grad_t) dirs[nd++] = 18;
+  for (int d = 0; d < 3; ++d) dirs[nd + d] = -1;
 #pragma unroll 1
-  for (int f = 0; f < 21; f += 3) {
+  for (int f = 0; f < nd; f += 3) {
     double g3[3];
-    mix_point_grad_pass<3>(prm, kk, T, spec, inc, q, f, gi, g3);
+    mix_point_grad_pass<3>(prm, kk, T, spec, inc, q, dirs + f, gi, g3);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      int d = f + k;
-      if (d < 16) {
-        if (grad_params) grad_params[16 * i + d] = g3[k];
-      } else if (d < 18) {
-        if (grad_kij) grad_kij[2 * i + (d - 16)] = g3[k];
-      } else if (d == 18) {
-        if (grad_t) grad_t[i] = g3[k];
-      }
+      int d = dirs[f + k];
+      if (d < 0) break;
+      if (d < 16) grad_params[16 * i + d] = g3[k];
+      else if (d < 18) grad_kij[2 * i + (d - 16)] = g3[k];
+      else grad_t[i] = g3[k];
     }
   }
 }

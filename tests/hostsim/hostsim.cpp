@@ -236,7 +236,8 @@ void sim_mix_point_bwd(const double* params, const double* kij, const double* T,
     PointWeights q = point_weights(es, spec, inc);
     for (int f = 0; f < 21; f += 3) {
       double g3[3];
-      mix_point_grad_pass<3>(prm, kk, T[i], spec, inc, q, f, g[i], g3);
+      int ids[3] = {f < 19 ? f : -1, f + 1 < 19 ? f + 1 : -1, f + 2 < 19 ? f + 2 : -1};
+      mix_point_grad_pass<3>(prm, kk, T[i], spec, inc, q, ids, g[i], g3);
       for (int k = 0; k < 3; ++k) if (f + k < 19) grad[19 * i + f + k] = g3[k];
     }
   }
