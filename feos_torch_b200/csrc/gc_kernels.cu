@@ -153,8 +153,17 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
       int ncoef = coef_count(b.c);
       // (the pass functions are __noinline__: fully inlined into this kernel, nvcc 12.9 -O3 produced wrong
       // coefficient adjoints on sm_100a while -G and the stand-alone functions were correct)
+      {
+        GcDualCoef cd;
+        double* seed[kGcMaxCoef];
+        gc_dual_coef(cd, b.c, seed);
 #pragma unroll 1
-      for (int f = 0; f < ncoef; f += 3) gc_coef_adjoint_pass<3>(b.c, spec, inc, q, f, ncoef, cbar);
+        for (int f = 0; f < ncoef; ++f) {
+          *seed[f] = 1.0;
+          cbar[f] = gc_coef_adjoint(cd, spec, inc, q);
+          *seed[f] = 0.0;
+        }
+      }
       // B. inputs of the coefficient stage
       double gi = gout[pos ? (int64_t)pos[i] : i];
       double scale = gi * src.T_ * kPaPerRed;

@@ -321,8 +321,50 @@ FD void gc_binary_init(GcBinary& b, const GcSource& src) {
 }
 
 // ---- gradient of the Newton-step bubble/dew pressure -------------------------------------------
-// Step A: adjoints of the reduced pressure with respect to the coefficients, K coefficient directions
-// per pass (same formula as mix_grad.cuh).  cbar[idx] = d p_red / d coef[idx].
+// Step A: adjoints of the reduced pressure with respect to the coefficients (same formula as
+// mix_grad.cuh), ONE coefficient direction per pass so that D1T<DN<1>> (4 doubles per value) stays in
+// registers.  The dual copy of the coefficients is built once per state (gc_dual_coef); a pass only flips
+// the seed of its coefficient through the pointer table `seed`.  cbar[idx] = d p_red / d coef[idx].
+using GcDualCoef = MixCoef<DN<1>, kGcMaxBond, true>;
+
+FD int gc_dual_coef(GcDualCoef& cd, const GcCoef& c, double** seed) {
+  cd.nbond = c.nbond;
+  cd.dipolar = c.dipolar;
+  cd.cat = c.cat;
+  cd.sgn[0] = c.sgn[0];
+  cd.sgn[1] = c.sgn[1];
+  for (int b = 0; b < c.nbond; ++b) {
+    cd.bn[b][0] = DN<1>(c.bn[b][0]);
+    cd.bn[b][1] = DN<1>(c.bn[b][1]);
+  }
+  double vals[kGcMaxCoef];
+  int idx = 0;
+#define FEOS_X(f) vals[idx++] = f
+  FEOS_VISIT_COEF(c, FEOS_X)
+#undef FEOS_X
+  idx = 0;
+#define FEOS_X(f)            \
+  {                          \
+    f = DN<1>(vals[idx]);    \
+    seed[idx] = &f.e[0];     \
+    ++idx;                   \
+  }
+  FEOS_VISIT_COEF(cd, FEOS_X)
+#undef FEOS_X
+  return idx;
+}
+
+FD_NOINLINE double gc_coef_adjoint(const GcDualCoef& cd, const double (&spec)[2], const double (&inc)[2],
+                                   const PointWeights& q) {
+  typedef DN<1> P;
+  P a_inc = mix_helmholtz<P, P, kGcMaxBond, true>(cd, P(inc[0]), P(inc[1]));
+  D1T<P> r0(P(spec[0]), P(q.dir[0])), r1(P(spec[1]), P(q.dir[1]));
+  D1T<P> A = mix_helmholtz<P, D1T<P>, kGcMaxBond, true>(cd, r0, r1);
+  P N = a_inc * (1.0 / q.rho_inc) - A.re * q.v + A.d1 + q.cst;
+  return -N.e[0] / q.denom;
+}
+
+// K coefficient directions per pass with a freshly seeded copy (kept as the cross-check of the above)
 template <int K>
 FD_NOINLINE void gc_coef_adjoint_pass(const GcCoef& c, const double (&spec)[2], const double (&inc)[2], const PointWeights& q,
                              int first, int ncoef, double* cbar) {

@@ -326,7 +326,18 @@ void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const d
     double p_red = point_pressure(es, ei.a, spec, inc);
     double cbar[kGcMaxCoef];
     int ncoef = coef_count(b.c);
-    for (int f = 0; f < ncoef; f += 3) gc_coef_adjoint_pass<3>(b.c, spec, inc, q, f, ncoef, cbar);
+    if (generic_all) {
+      for (int f = 0; f < ncoef; f += 3) gc_coef_adjoint_pass<3>(b.c, spec, inc, q, f, ncoef, cbar);
+    } else {
+      GcDualCoef cd;
+      double* seed[kGcMaxCoef];
+      gc_dual_coef(cd, b.c, seed);
+      for (int f = 0; f < ncoef; ++f) {
+        *seed[f] = 1.0;
+        cbar[f] = gc_coef_adjoint(cd, spec, inc, q);
+        *seed[f] = 0.0;
+      }
+    }
     double scale = g[i] * T[i] * kPaPerRed;
     double gseg[8 * kGcMaxSeg];
     for (int k = 0; k < 8 * pr.nseg; ++k) gseg[k] = 0.0;
