@@ -137,7 +137,22 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
     if (!failed[i]) {
       GcSource src = make_source(g, i);
       const GcPair& pr = *src.pair;
-      GcBinary b;
+      // every per-thread array whose address is handed to the (deliberately out-of-line) pass functions lives
+      // in ONE stack object: as separate locals nvcc 12.9 -O3 overlapped them on sm_100a (see gc_pcsaft.cuh)
+      struct Scratch {
+        GcBinary b;
+        double cbar[kGcMaxCoef];
+        double gseg[8 * kGcMaxSeg];
+        double gkab[kGcMaxSeg * kGcMaxSeg];
+        int dirs[kGcMaxDirs + 4];
+        GcDualCoef cd;
+        double* seed[kGcMaxCoef];
+      } w;
+      GcBinary& b = w.b;
+      double* cbar = w.cbar;
+      double* gseg = w.gseg;
+      double* gkab = w.gkab;
+      int* dirs = w.dirs;
       gc_binary_init(b, src);
       const double2* rp = reinterpret_cast<const double2*>(rho + 4 * i);
       double2 rv = rp[0], rl = rp[1];
@@ -146,32 +161,16 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
       else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
       MixEval es = b.eval(spec[0], spec[1]);
       PointWeights q = point_weights(es, spec, inc);
-      MixEval ei = b.eval(inc[0], inc[1]);
-      double p_red = point_pressure(es, ei.a, spec, inc);
-      // A. coefficient adjoints
-      double cbar[kGcMaxCoef];
-      int ncoef = coef_count(b.c);
-      // (the pass functions are __noinline__: fully inlined into this kernel, nvcc 12.9 -O3 produced wrong
-      // coefficient adjoints on sm_100a while -G and the stand-alone functions were correct)
-      {
-        GcDualCoef cd;
-        double* seed[kGcMaxCoef];
-        gc_dual_coef(cd, b.c, seed);
-#pragma unroll 1
-        for (int f = 0; f < ncoef; ++f) {
-          *seed[f] = 1.0;
-          cbar[f] = gc_coef_adjoint(cd, spec, inc, q);
-          *seed[f] = 0.0;
-        }
-      }
+      double p_red = point_pressure(es, gc_binary_value(b.c, inc[0], inc[1]), spec, inc);
+      // A. coefficient adjoints: closed form for the base group, dual passes (dipole / association part of
+      // the model only) for pairs that have those terms
+      gc_coef_adjoints(b.c, spec, inc, q, w.cd, w.seed, cbar);
       // B. inputs of the coefficient stage
       double gi = gout[pos ? (int64_t)pos[i] : i];
       double scale = gi * src.T_ * kPaPerRed;
       // base group (z, m, cd, q1, q2): one reverse-mode sweep; gradients in units of p_red
-      double gseg[8 * kGcMaxSeg];
       for (int k = 0; k < 8 * pr.nseg; ++k) gseg[k] = 0.0;
       double gp2[2] = {0.0, 0.0}, gtr = 0.0;
-      double gkab[kGcMaxSeg * kGcMaxSeg];
       for (int a = 0; a < pr.nseg; ++a)
         for (int c2 = 0; c2 < pr.nseg; ++c2) gkab[kGcMaxSeg * a + c2] = 0.0;
       gc_base_adjoint(src, b.c, cbar, gseg, gp2, &gtr, gkab);
@@ -184,7 +183,6 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
           }
       }
       // dipole / association groups (only for pairs that have them): dual passes, 4 directions each
-      int dirs[kGcMaxDirs + 4];
       int n_dir = gc_active_directions(src, b.c, n_rec, dirs);
       for (int k = 0; k < 4; ++k) dirs[n_dir + k] = -1;
 #pragma unroll 1

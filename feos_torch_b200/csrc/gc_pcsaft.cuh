@@ -364,6 +364,48 @@ FD_NOINLINE double gc_coef_adjoint(const GcDualCoef& cd, const double (&spec)[2]
   return -N.e[0] / q.denom;
 }
 
+// The same for the dipole + association part of the Helmholtz energy only (PARTS = 2): used for the
+// coefficients of those groups and for the zeta_2 / zeta_3 coefficients they also depend on.
+FD_NOINLINE double gc_coef_adjoint_extra(const GcDualCoef& cd, const double (&spec)[2], const double (&inc)[2],
+                                         const PointWeights& q) {
+  typedef DN<1> P;
+  P a_inc = mix_helmholtz<P, P, kGcMaxBond, true, 2>(cd, P(inc[0]), P(inc[1]));
+  D1T<P> r0(P(spec[0]), P(q.dir[0])), r1(P(spec[1]), P(q.dir[1]));
+  D1T<P> A = mix_helmholtz<P, D1T<P>, kGcMaxBond, true, 2>(cd, r0, r1);
+  P N = a_inc * (1.0 / q.rho_inc) - A.re * q.v + A.d1;
+  return -N.e[0] / q.denom;
+}
+
+// Step A as the kernels run it: the base group (hard sphere, hard chain, dispersion: flat indices
+// 0 .. 15 + nbond) in closed form (mix_base_coef_adjoint, mix_grad.cuh); only pairs with dipoles or
+// association pay forward-mode passes, restricted to that part of the model (PARTS = 2), for the
+// coefficients of those groups and for z[2][i], z[3][i] (flat indices 4 .. 7), to which they ADD.
+// `cd` / `seed` are caller-provided storage for the dual coefficient copy.  Compiler note (nvcc 12.9,
+// sm_100a, -O3): ptxas merges the frames of the out-of-line pass functions into the kernel's frame and
+// overlapped `cd` with the caller's `cbar` when they were separate locals (the base adjoints read back as
+// coefficient values).  The kernels therefore keep every array whose address is passed to a pass function
+// in ONE scratch struct, which cannot be split.
+FD void gc_coef_adjoints(const GcCoef& c, const double (&spec)[2], const double (&inc)[2], const PointWeights& q,
+                         GcDualCoef& cd, double** seed, double* cbar) {
+  mix_base_coef_adjoint<kGcMaxBond, true>(c, spec, inc, q, cbar);
+  if (!c.dipolar && c.cat == kAssocNone) return;
+  const int ncoef = gc_dual_coef(cd, c, seed);
+  const int first = 16 + c.nbond;
+#pragma unroll 1
+  for (int f = 4; f < ncoef; ++f) {
+    if (f == 8) f = first;
+    *seed[f] = 1.0;
+    double v = gc_coef_adjoint_extra(cd, spec, inc, q);
+    *seed[f] = 0.0;
+    if (f < 8) cbar[f] += v;
+    else cbar[f] = v;
+  }
+}
+
+FD_NOINLINE double gc_binary_value(const GcCoef& c, double r0, double r1) {
+  return mix_helmholtz<double, double, kGcMaxBond, true>(c, r0, r1);
+}
+
 // K coefficient directions per pass with a freshly seeded copy (kept as the cross-check of the above)
 template <int K>
 FD_NOINLINE void gc_coef_adjoint_pass(const GcCoef& c, const double (&spec)[2], const double (&inc)[2], const PointWeights& q,

@@ -55,6 +55,171 @@ FD PointWeights point_weights(const MixEval& es, const double (&spec)[2], const 
   return q;
 }
 
+// ---- closed-form coefficient adjoints of the base group (hard sphere + hard chain + dispersion) ----
+// a_base depends on the coefficients only through
+//   zeta_k = sum_i z[k][i] rho_i,  mbar = sum_i m[i] rho_i / rho,  Q1 = sum q1 rho rho,  Q2,  cd[b],
+// so  d a / d coef  is 4 + 1 + 2 partial derivatives times the (known) densities plus one partial per bond
+// type.  BasePhase<R> holds those partials at one density point in the number type R of the densities:
+// R = double for the incipient phase, R = D1T<double> (density + direction) for the specified phase, whose
+// .d1 part is then the directional density derivative of the coefficient gradient.  The bubble / dew
+// pressure adjoint of a coefficient combines the two phases (point_comb).  Replaces 16 + nbond forward-mode
+// passes over the whole Helmholtz energy (one per coefficient).
+// Everything is scalar state in registers (no locally indexed arrays): the per-bond terms are consumed
+// as they are produced.
+template <class R>
+struct BasePhase {
+  R rho0, rho1;
+  R z0, z1, z2, z3, om, omi, omi2, omi3, cz, dcz3;
+  R a0, a1, a2, a3;  // d a / d zeta_k
+  R mb;              // d a / d mbar / rho
+  R q1, q2;          // d a / d Q1, d a / d Q2
+};
+
+template <class R>
+FD void horner7(const double (&k)[7], const R& x, R& v, R& dv) {
+  v = R(k[6]);
+  dv = R(0.0);
+#pragma unroll
+  for (int n = 5; n >= 0; --n) {
+    dv = dv * x + v;
+    v = v * x + k[n];
+  }
+}
+
+// hard-sphere partials; sets up the packing-fraction helpers the other terms use
+template <class R, class C>
+FD void base_phase_begin(BasePhase<R>& s, const C& c, const R& rho0, const R& rho1) {
+  s.rho0 = rho0;
+  s.rho1 = rho1;
+  s.z0 = rho0 * c.z[0][0] + rho1 * c.z[0][1];
+  s.z1 = rho0 * c.z[1][0] + rho1 * c.z[1][1];
+  s.z2 = rho0 * c.z[2][0] + rho1 * c.z[2][1];
+  s.z3 = rho0 * c.z[3][0] + rho1 * c.z[3][1];
+  s.om = 1.0 - s.z3;
+  s.omi = ad_recip(s.om);
+  s.omi2 = s.omi * s.omi;
+  s.omi3 = s.omi2 * s.omi;
+  R iz3 = ad_recip(s.z3);
+  R L = ad_log(s.om);
+  // a_hs = 6/pi [3 z1 z2 / om + z2^3 / (z3 om^2) + (z2^3 / z3^2 - z0) ln om]
+  R z2sq = s.z2 * s.z2;
+  R t = (z2sq * s.z2) * (iz3 * iz3);  // z2^3 / z3^2
+  s.a0 = (-6.0 / kPi) * L;
+  s.a1 = (18.0 / kPi) * (s.z2 * s.omi);
+  s.a2 = (18.0 / kPi) * (s.z1 * s.omi + (z2sq * iz3) * s.omi2 + (z2sq * (iz3 * iz3)) * L);
+  s.a3 = (6.0 / kPi) * ((3.0 * (s.z1 * s.z2)) * s.omi2 + (t * s.z3) * (2.0 * s.omi3 - iz3 * s.omi2) - (2.0 * (t * iz3)) * L -
+                        (t - s.z0) * s.omi);
+  s.cz = s.z2 * s.omi2;
+  s.dcz3 = 2.0 * (s.z2 * s.omi3);  // d cz / d zeta3
+}
+
+// hard chain, one bond type: a = - B ln g,  g = 1/om + 3 x + 2 x^2 om,  x = z2 cd / om^2.
+// Returns d a / d cd and adds the zeta_2 / zeta_3 partials.
+template <class R>
+FD R base_phase_bond(BasePhase<R>& s, double cd, double bn0, double bn1) {
+  R x = s.cz * cd;
+  R x2 = x * x;
+  R gg = s.omi + 3.0 * x + (2.0 * x2) * s.om;
+  R gx = 3.0 + 4.0 * (x * s.om);
+  R w = (s.rho0 * bn0 + s.rho1 * bn1) * ad_recip(gg);  // B / g
+  R wgx = w * gx;
+  s.a2 = s.a2 - wgx * (s.omi2 * cd);
+  s.a3 = s.a3 - w * (s.omi2 + gx * (s.dcz3 * cd) - 2.0 * x2);
+  return -(wgx * s.cz);
+}
+
+// dispersion: a = -pi [2 Q1 I1(eta, mbar) + Q2 C1(eta, mbar) I2(eta, mbar) mbar]
+template <class R, class C>
+FD void base_phase_end(BasePhase<R>& s, const C& c) {
+  const R& z3 = s.z3;
+  R rti = ad_recip(s.rho0 + s.rho1);
+  R mbar = (s.rho0 * c.m[0] + s.rho1 * c.m[1]) * rti;
+  R r00 = s.rho0 * s.rho0, r01 = s.rho0 * s.rho1, r11 = s.rho1 * s.rho1;
+  R Q1 = r00 * c.q1[0] + (2.0 * r01) * c.q1[1] + r11 * c.q1[2];
+  R Q2 = r00 * c.q2[0] + (2.0 * r01) * c.q2[1] + r11 * c.q2[2];
+  R mi = ad_recip(mbar);
+  R w1 = 1.0 - mi;
+  R w2 = w1 * (1.0 - 2.0 * mi);
+  R dw1 = mi * mi;
+  R dw2 = dw1 * (3.0 - 4.0 * mi);
+  R s0, s1, s2, d0, d1, d2;
+  horner7(cA0, z3, s0, d0);
+  horner7(cA1, z3, s1, d1);
+  horner7(cA2, z3, s2, d2);
+  R i1 = s0 + w1 * s1 + w2 * s2;
+  R i1e = d0 + w1 * d1 + w2 * d2;
+  R i1m = dw1 * s1 + dw2 * s2;
+  horner7(cB0, z3, s0, d0);
+  horner7(cB1, z3, s1, d1);
+  horner7(cB2, z3, s2, d2);
+  R i2 = s0 + w1 * s1 + w2 * s2;
+  R i2e = d0 + w1 * d1 + w2 * d2;
+  R i2m = dw1 * s1 + dw2 * s2;
+  R e2 = z3 * z3, e3 = e2 * z3;
+  R tmi = ad_recip(2.0 - z3);
+  R omi4 = s.omi2 * s.omi2;
+  R xn = 8.0 * z3 - 2.0 * e2;
+  R X = xn * omi4;
+  R dX = (8.0 - 4.0 * z3) * omi4 + (4.0 * xn) * (omi4 * s.omi);
+  R yn = 20.0 * z3 - 27.0 * e2 + 12.0 * e3 - 2.0 * (e2 * e2);
+  R ow = s.omi2 * (tmi * tmi);
+  R Y = yn * ow;
+  R dY = (20.0 - 54.0 * z3 + 36.0 * e2 - 8.0 * e3) * ow + (2.0 * yn) * (ow * (s.omi + tmi));
+  R c1 = ad_recip(1.0 + mbar * X + (1.0 - mbar) * Y);
+  R c1sq = c1 * c1;
+  R c1e = -(c1sq * (mbar * dX + (1.0 - mbar) * dY));
+  R c1m = -(c1sq * (X - Y));
+  s.q1 = (-2.0 * kPi) * i1;
+  s.q2 = (-kPi) * ((c1 * i2) * mbar);
+  s.a3 = s.a3 + (-kPi) * (2.0 * (Q1 * i1e) + (Q2 * mbar) * (c1e * i2 + c1 * i2e));
+  s.mb = ((-kPi) * (2.0 * (Q1 * i1m) + Q2 * ((c1m * i2 + c1 * i2m) * mbar + c1 * i2))) * rti;
+}
+
+FD double point_comb(double gi, const D1& gs, const PointWeights& q) {
+  // - d N / d coef / denom with N = a_inc / rho_inc - v a_spec + D_dir a_spec + cst
+  return -(gi / q.rho_inc - gs.re * q.v + gs.d1) / q.denom;
+}
+
+// cbar[idx] = d p_red / d coef[idx] for the base coefficients in the flat order of FEOS_VISIT_COEF:
+// z[k][i] -> 2 k + i, m[i] -> 8 + i, q1[k] -> 10 + k, q2[k] -> 13 + k, cd[b] -> 16 + b.
+template <int NB, bool GC>
+FD_NOINLINE void mix_base_coef_adjoint(const MixCoef<double, NB, GC>& c, const double (&spec)[2], const double (&inc)[2],
+                                       const PointWeights& q, double* cbar) {
+  BasePhase<double> pi;
+  BasePhase<D1> ps;
+  const double i0 = inc[0], i1 = inc[1];
+  const D1 s0(spec[0], q.dir[0]), s1(spec[1], q.dir[1]);
+  base_phase_begin(pi, c, i0, i1);
+  base_phase_begin(ps, c, s0, s1);
+  const int nb = (NB == 2) ? 2 : c.nbond;
+#pragma unroll 1
+  for (int b = 0; b < nb; ++b) {
+    double cd = c.cd[b], bn0 = c.bn[b][0], bn1 = c.bn[b][1];
+    double gi = base_phase_bond(pi, cd, bn0, bn1);
+    D1 gs = base_phase_bond(ps, cd, bn0, bn1);
+    cbar[16 + b] = point_comb(gi, gs, q);
+  }
+  base_phase_end(pi, c);
+  base_phase_end(ps, c);
+  cbar[0] = point_comb(pi.a0 * i0, ps.a0 * s0, q);
+  cbar[1] = point_comb(pi.a0 * i1, ps.a0 * s1, q);
+  cbar[2] = point_comb(pi.a1 * i0, ps.a1 * s0, q);
+  cbar[3] = point_comb(pi.a1 * i1, ps.a1 * s1, q);
+  cbar[4] = point_comb(pi.a2 * i0, ps.a2 * s0, q);
+  cbar[5] = point_comb(pi.a2 * i1, ps.a2 * s1, q);
+  cbar[6] = point_comb(pi.a3 * i0, ps.a3 * s0, q);
+  cbar[7] = point_comb(pi.a3 * i1, ps.a3 * s1, q);
+  cbar[8] = point_comb(pi.mb * i0, ps.mb * s0, q);
+  cbar[9] = point_comb(pi.mb * i1, ps.mb * s1, q);
+  const D1 r00 = s0 * s0, r01 = 2.0 * (s0 * s1), r11 = s1 * s1;
+  cbar[10] = point_comb(pi.q1 * (i0 * i0), ps.q1 * r00, q);
+  cbar[11] = point_comb(pi.q1 * (2.0 * i0 * i1), ps.q1 * r01, q);
+  cbar[12] = point_comb(pi.q1 * (i1 * i1), ps.q1 * r11, q);
+  cbar[13] = point_comb(pi.q2 * (i0 * i0), ps.q2 * r00, q);
+  cbar[14] = point_comb(pi.q2 * (2.0 * i0 * i1), ps.q2 * r01, q);
+  cbar[15] = point_comb(pi.q2 * (i1 * i1), ps.q2 * r11, q);
+}
+
 // out[k] = g * d(p_bubble/dew [Pa]) / d(direction ids[k])
 template <int K>
 FD_NOINLINE void mix_point_grad_pass(const double (&prm)[16], const double (&kij)[2], double T, const double (&spec)[2],

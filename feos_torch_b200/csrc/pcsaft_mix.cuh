@@ -351,7 +351,10 @@ FD R gc_cross_assoc(const R (&rho)[2], const R (&dl)[4]) {
   return rho[0] * (2.0 * ad_log(X0) - X0 + 1.0) + rho[1] * (2.0 * ad_log(X1) - X1 + 1.0);
 }
 
-template <class P, class R, int NB, bool GC>
+// PARTS: bit 0 = hard sphere + hard chain + dispersion (the "base" group), bit 1 = dipole + association.
+// The gradient kernels evaluate the two groups separately (closed-form coefficient adjoints for the base
+// group, dual passes for the rest).
+template <class P, class R, int NB, bool GC, int PARTS = 3>
 FD R mix_helmholtz(const MixCoef<P, NB, GC>& c, const R& rho0, const R& rho1) {
   R z0 = rho0 * c.z[0][0] + rho1 * c.z[0][1];
   R z1 = rho0 * c.z[1][0] + rho1 * c.z[1][1];
@@ -362,8 +365,11 @@ FD R mix_helmholtz(const MixCoef<P, NB, GC>& c, const R& rho0, const R& rho1) {
   R omi2 = omi * omi;
   R z23 = z2 * ad_recip(z3);
 
+  R a(0.0);
+  R e2 = z3 * z3, e3 = e2 * z3, e4 = e2 * e2;
+  if (PARTS & 1) {
   // hard sphere (:56-60)
-  R a = (6.0 / kPi) * ((3.0 * (z1 * z2)) * omi + ((z2 * z2) * omi2) * z23 + ((z2 * z23) * z23 - z0) * ad_log(om));
+  a = (6.0 / kPi) * ((3.0 * (z1 * z2)) * omi + ((z2 * z2) * omi2) * z23 + ((z2 * z23) * z23 - z0) * ad_log(om));
 
   // hard chain (:63-65; gc_pcsaft.py:156-165): g = 1/(1-z3) + 3 c cd + 2 (c cd)^2 (1 - z3)
   R cz = z2 * omi2;
@@ -388,7 +394,7 @@ FD R mix_helmholtz(const MixCoef<P, NB, GC>& c, const R& rho0, const R& rho1) {
   R r00 = rho0 * rho0, r01 = rho0 * rho1, r11 = rho1 * rho1;
   R rho1mix = r00 * c.q1[0] + (2.0 * r01) * c.q1[1] + r11 * c.q1[2];
   R rho2mix = r00 * c.q2[0] + (2.0 * r01) * c.q2[1] + r11 * c.q2[2];
-  R e2 = z3 * z3, e3 = e2 * z3, e4 = e2 * e2, e5 = e2 * e3, e6 = e3 * e3;
+  R e5 = e2 * e3, e6 = e3 * e3;
   {
     R mi = ad_recip(mbar);
     R w1 = (mbar - 1.0) * mi;
@@ -406,9 +412,10 @@ FD R mix_helmholtz(const MixCoef<P, NB, GC>& c, const R& rho0, const R& rho1) {
                     (1.0 - mbar) * ((20.0 * z3 - 27.0 * e2 + 12.0 * e3 - 2.0 * e4) * (omi2 * (tmi * tmi))));
     a = a + (-kPi) * (2.0 * (rho1mix * i1) + (rho2mix * c1) * (i2 * mbar));
   }
+  }  // PARTS & 1
 
   // dipoles (:156-208)
-  if (c.dipolar) {
+  if ((PARTS & 2) && c.dipolar) {
     R t0 = rho0 * c.mu2t[0], t1 = rho1 * c.mu2t[1];
     R tt[3] = {t0 * t0, t0 * t1, t1 * t1};
     R phi2(0.0), phi3(0.0);
@@ -434,7 +441,7 @@ FD R mix_helmholtz(const MixCoef<P, NB, GC>& c, const R& rho0, const R& rho1) {
   }
 
   // association (:118-152)
-  if (c.cat != kAssocNone) {
+  if ((PARTS & 2) && c.cat != kAssocNone) {
     R z2om = z2 * omi;
     if (c.cat == kAssocSelf) {
       R delta = mix_strength(c, 0, z2om, omi);

@@ -3,6 +3,8 @@
 // exercised in the GPU-less build container.  Not part of the product; nothing in feos_torch_b200
 // loads it.
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "../../feos_torch_b200/csrc/pure_solver.cuh"
 #include "../../feos_torch_b200/csrc/pure_grad.cuh"
 
@@ -322,8 +324,7 @@ void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const d
     else { spec[0] = r[0]; spec[1] = r[1]; inc[0] = r[2]; inc[1] = r[3]; }
     MixEval es = b.eval(spec[0], spec[1]);
     PointWeights q = point_weights(es, spec, inc);
-    MixEval ei = b.eval(inc[0], inc[1]);
-    double p_red = point_pressure(es, ei.a, spec, inc);
+    double p_red = point_pressure(es, gc_binary_value(b.c, inc[0], inc[1]), spec, inc);
     double cbar[kGcMaxCoef];
     int ncoef = coef_count(b.c);
     if (generic_all) {
@@ -331,11 +332,16 @@ void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const d
     } else {
       GcDualCoef cd;
       double* seed[kGcMaxCoef];
-      gc_dual_coef(cd, b.c, seed);
-      for (int f = 0; f < ncoef; ++f) {
-        *seed[f] = 1.0;
-        cbar[f] = gc_coef_adjoint(cd, spec, inc, q);
-        *seed[f] = 0.0;
+      gc_coef_adjoints(b.c, spec, inc, q, cd, seed, cbar);
+      if (getenv("FEOS_SIM_CHECK_COEF")) {
+        // debugging aid: the closed-form / restricted adjoints against one full dual pass per coefficient
+        gc_dual_coef(cd, b.c, seed);
+        for (int f = 0; f < ncoef; ++f) {
+          *seed[f] = 1.0;
+          double ref = gc_coef_adjoint(cd, spec, inc, q);
+          *seed[f] = 0.0;
+          if (fabs(ref - cbar[f]) > 1e-9 * (fabs(ref) + 1e-300)) printf("state %lld coef %d: %.15g vs %.15g\n", (long long)i, f, cbar[f], ref);
+        }
       }
     }
     double scale = g[i] * T[i] * kPaPerRed;
