@@ -174,6 +174,7 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
       for (int a = 0; a < pr.nseg; ++a)
         for (int c2 = 0; c2 < pr.nseg; ++c2) gkab[kGcMaxSeg * a + c2] = 0.0;
       gc_base_adjoint(src, b.c, cbar, gseg, gp2, &gtr, gkab);
+      if (b.c.dipolar) gc_dipole_adjoint(src, b.c, cbar + 16 + b.c.nbond, gseg, &gtr);
       if (grad_kab) {
         for (int a = 0; a < pr.nseg; ++a)
           for (int c2 = 0; c2 < pr.nseg; ++c2) {
@@ -182,7 +183,7 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
             if (r >= 0 && v != 0.0) atomicAdd(&acc[8 * n_seg + r], v);
           }
       }
-      // dipole / association groups (only for pairs that have them): dual passes, 4 directions each
+      // association group (only for pairs that associate): dual passes, 4 directions each
       int n_dir = gc_active_directions(src, b.c, n_rec, dirs);
       for (int k = 0; k < 4; ++k) dirs[n_dir + k] = -1;
 #pragma unroll 1

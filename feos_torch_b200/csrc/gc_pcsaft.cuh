@@ -70,8 +70,9 @@ struct GcDualSource {
   FD DN<K> T() const { return make(s.T_, 8 * s.pair->nseg + nrec + 2); }
 };
 
-// BASE = false skips the hard-chain contact distances and the O(nseg^2) dispersion pair loop (their
-// gradient is taken by gc_base_adjoint); z, m are always filled (the dipole group needs m).
+// BASE = false computes the association group only (the gradients of the hard-sphere / hard-chain /
+// dispersion and dipole groups are taken by the reverse sweeps gc_base_adjoint / gc_dipole_adjoint); the
+// structure flags (nbond, dipolar, cat) are always set so that the flat coefficient order is the same.
 template <class P, class Src, bool BASE = true>
 FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& pr) {
   P T = src.T();
@@ -164,7 +165,8 @@ FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& p
       ep[i] = me * mi;
       mu2t[i] = mu2 * mi * kDipoleScale * ti;
     }
-    dipole_coef(c, c.m, sg, ep, mu2t, ti, dipolar);
+    if (BASE) dipole_coef(c, c.m, sg, ep, mu2t, ti, dipolar);
+    else c.dipolar = dipolar;
   }
   // association: at most one associating segment per molecule (:76-86), categories (:212-251)
   {
@@ -364,33 +366,37 @@ FD_NOINLINE double gc_coef_adjoint(const GcDualCoef& cd, const double (&spec)[2]
   return -N.e[0] / q.denom;
 }
 
-// The same for the dipole + association part of the Helmholtz energy only (PARTS = 2): used for the
-// coefficients of those groups and for the zeta_2 / zeta_3 coefficients they also depend on.
+// The same for the association part of the Helmholtz energy only (PARTS = 4): used for the coefficients
+// of that group and for the zeta_2 / zeta_3 coefficients it also depends on.
 FD_NOINLINE double gc_coef_adjoint_extra(const GcDualCoef& cd, const double (&spec)[2], const double (&inc)[2],
                                          const PointWeights& q) {
   typedef DN<1> P;
-  P a_inc = mix_helmholtz<P, P, kGcMaxBond, true, 2>(cd, P(inc[0]), P(inc[1]));
+  P a_inc = mix_helmholtz<P, P, kGcMaxBond, true, 4>(cd, P(inc[0]), P(inc[1]));
   D1T<P> r0(P(spec[0]), P(q.dir[0])), r1(P(spec[1]), P(q.dir[1]));
-  D1T<P> A = mix_helmholtz<P, D1T<P>, kGcMaxBond, true, 2>(cd, r0, r1);
+  D1T<P> A = mix_helmholtz<P, D1T<P>, kGcMaxBond, true, 4>(cd, r0, r1);
   P N = a_inc * (1.0 / q.rho_inc) - A.re * q.v + A.d1;
   return -N.e[0] / q.denom;
 }
 
 // Step A as the kernels run it: the base group (hard sphere, hard chain, dispersion: flat indices
-// 0 .. 15 + nbond) in closed form (mix_base_coef_adjoint, mix_grad.cuh); only pairs with dipoles or
-// association pay forward-mode passes, restricted to that part of the model (PARTS = 2), for the
-// coefficients of those groups and for z[2][i], z[3][i] (flat indices 4 .. 7), to which they ADD.
-// `cd` / `seed` are caller-provided storage for the dual coefficient copy.  Compiler note (nvcc 12.9,
-// sm_100a, -O3): ptxas merges the frames of the out-of-line pass functions into the kernel's frame and
+// 0 .. 15 + nbond) and the dipole group (26 coefficients) in closed form (mix_base_coef_adjoint,
+// mix_dipole_coef_adjoint, mix_grad.cuh); only associating pairs pay forward-mode passes, restricted to the
+// association term (PARTS = 4), for its coefficients and for z[2][i], z[3][i] (flat indices 4 .. 7), to which
+// they ADD.  `cd` / `seed` are caller-provided storage for the dual coefficient copy.  Compiler note (nvcc
+// 12.9, sm_100a, -O3): ptxas merges the frames of the out-of-line pass functions into the kernel's frame and
 // overlapped `cd` with the caller's `cbar` when they were separate locals (the base adjoints read back as
 // coefficient values).  The kernels therefore keep every array whose address is passed to a pass function
 // in ONE scratch struct, which cannot be split.
 FD void gc_coef_adjoints(const GcCoef& c, const double (&spec)[2], const double (&inc)[2], const PointWeights& q,
                          GcDualCoef& cd, double** seed, double* cbar) {
   mix_base_coef_adjoint<kGcMaxBond, true>(c, spec, inc, q, cbar);
-  if (!c.dipolar && c.cat == kAssocNone) return;
+  int first = 16 + c.nbond;
+  if (c.dipolar) {
+    mix_dipole_coef_adjoint<kGcMaxBond, true>(c, spec, inc, q, cbar, first);
+    first += 26;
+  }
+  if (c.cat == kAssocNone) return;
   const int ncoef = gc_dual_coef(cd, c, seed);
-  const int first = 16 + c.nbond;
 #pragma unroll 1
   for (int f = 4; f < ncoef; ++f) {
     if (f == 8) f = first;
@@ -421,25 +427,21 @@ FD_NOINLINE void gc_coef_adjoint_pass(const GcCoef& c, const double (&spec)[2], 
     if (first + k < ncoef) cbar[first + k] = -N.e[k] / q.denom;
 }
 
-// The input directions that can have a non-zero gradient for this state: m, sigma, eps of every present
-// segment; mu where the pair is dipolar and the segment carries a dipole (d mu^2 = 0 at mu = 0);
-// kappa, eps_ab, na, nb only if the pair associates; the binary segment records present in the pair;
-// phi_0, phi_1, T.  Returns the number of directions written to `dirs`.
-constexpr int kGcMaxDirs = 8 * kGcMaxSeg + kGcMaxSeg * kGcMaxSeg / 2 + 3;
+// The input directions of the ASSOCIATION group that can have a non-zero gradient for this state (every other
+// group is handled by a reverse sweep): sigma, eps of the associating segments; kappa, eps_ab, na, nb of every
+// present segment (they are summed over the molecule, gc_pcsaft.py:76-86); T.
+constexpr int kGcMaxDirs = 6 * kGcMaxSeg + 1;
 FD int gc_active_directions(const GcSource& src, const GcCoef& c, int nrec, int* dirs) {
   const GcPair& pr = *src.pair;
   int n = 0;
-  if (!c.dipolar && c.cat == kAssocNone) return 0;  // only the base group: gc_base_adjoint does it all
+  if (c.cat == kAssocNone) return 0;
   for (int a = 0; a < pr.nseg; ++a) {
-    dirs[n++] = 8 * a;
-    dirs[n++] = 8 * a + 1;
-    dirs[n++] = 8 * a + 2;
-    if (c.dipolar && src.seg(a, 3) != 0.0) dirs[n++] = 8 * a + 3;
-    if (c.cat != kAssocNone)
-      for (int j = 4; j < 8; ++j) dirs[n++] = 8 * a + j;
+    if (src.seg(a, 4) * src.seg(a, 5) != 0.0) {
+      dirs[n++] = 8 * a + 1;
+      dirs[n++] = 8 * a + 2;
+    }
+    for (int j = 4; j < 8; ++j) dirs[n++] = 8 * a + j;
   }
-  // (phi and the binary segment records enter the dispersion term only -> base adjoint)
-  (void)nrec;
   dirs[n++] = 8 * pr.nseg + nrec + 2;  // T
   return n;
 }
@@ -536,9 +538,95 @@ FD_NOINLINE void gc_base_adjoint(const GcSource& src, const GcCoef& c, const dou
   (void)c;
 }
 
+// Step B, dipole group: reverse-mode sweep through the molecule-level dipole parameters (gc_coef, :146-168)
+// and dipole_coef (pcsaft_mix.cuh).  cb = adjoints of the 26 dipole coefficients in the flat order
+// (mu2t[2]; pw1, pw2, pe, ps per pair; tw1, tw2, ts per triplet); ADDS to gseg (m, sigma, eps, mu) and gT.
+FD_NOINLINE void gc_dipole_adjoint(const GcSource& src, const GcCoef& c, const double* cb, double* gseg, double* gT_out) {
+  const GcPair& pr = *src.pair;
+  const int ns = pr.nseg;
+  const double T = src.T(), ti = 1.0 / T;
+  double m[2], ms3[2], me[2], mu2[2], sg[2], ep[2], mc[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    m[i] = c.m[i];
+    ms3[i] = me[i] = mu2[i] = 0.0;
+    for (int a = 0; a < ns; ++a) {
+      double n = pr.cnt[i][a];
+      if (n == 0.0) continue;
+      double ma = src.seg(a, 0), s = src.seg(a, 1), e = src.seg(a, 2), mu = src.seg(a, 3);
+      ms3[i] += n * ma * s * s * s;
+      me[i] += n * ma * e;
+      mu2[i] += n * mu * mu;
+    }
+    sg[i] = cbrt(ms3[i] / m[i]);
+    ep[i] = me[i] / m[i];
+    mc[i] = m[i] <= 2.0 ? m[i] : 2.0;
+  }
+  double mcb[2] = {0.0, 0.0}, sgb[2] = {0.0, 0.0}, epb[2] = {0.0, 0.0}, gT = 0.0;
+  const int pi_[3] = {0, 0, 1}, pj_[3] = {0, 1, 1};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = pi_[k], j = pj_[k];
+    const double* o = cb + 2 + 4 * k;  // pw1, pw2, pe, ps
+    double x = sqrt(mc[i] * mc[j]), xi = 1.0 / x;
+    double xb = (o[0] + o[1] * (3.0 - 4.0 * xi)) * xi * xi;
+    mcb[i] += xb * x / (2.0 * mc[i]);
+    mcb[j] += xb * x / (2.0 * mc[j]);
+    double pe = c.pe[k];
+    epb[i] += o[2] * pe / (2.0 * ep[i]);
+    epb[j] += o[2] * pe / (2.0 * ep[j]);
+    gT -= o[2] * pe * ti;
+    double sij = 0.5 * (sg[i] + sg[j]);
+    double sb = -1.5 * o[3] * c.ps[k] / sij;  // (d ps / d sij) / 2
+    sgb[i] += sb;
+    sgb[j] += sb;
+  }
+  const int ti_[4] = {0, 0, 0, 1}, tj_[4] = {0, 0, 1, 1}, tk_[4] = {0, 1, 1, 1};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int i = ti_[t], j = tj_[t], k = tk_[t];
+    const double* o = cb + 14 + 3 * t;  // tw1, tw2, ts
+    double y = cbrt(mc[i] * mc[j] * mc[k]), yi = 1.0 / y;
+    double yb = (o[0] + o[1] * (3.0 - 4.0 * yi)) * yi * yi * y / 3.0;
+    mcb[i] += yb / mc[i];
+    mcb[j] += yb / mc[j];
+    mcb[k] += yb / mc[k];
+    double tb = -0.5 * o[2] * c.ts[t];
+    double sij = 0.5 * (sg[i] + sg[j]), sik = 0.5 * (sg[i] + sg[k]), sjk = 0.5 * (sg[j] + sg[k]);
+    sgb[i] += tb / sij + tb / sik;
+    sgb[j] += tb / sij + tb / sjk;
+    sgb[k] += tb / sik + tb / sjk;
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    double mi = 1.0 / m[i];
+    double mu2t = c.mu2t[i];
+    double mu2b = cb[i] * mi * kDipoleScale * ti;  // adjoint of sum n mu^2
+    gT -= cb[i] * mu2t * ti;
+    double mb = -cb[i] * mu2t * mi;
+    if (m[i] <= 2.0) mb += mcb[i];
+    double u = ms3[i] * mi;
+    double ub = sgb[i] * sg[i] / (3.0 * u);  // sg = u^(1/3)
+    double ms3b = ub * mi;
+    mb -= ub * u * mi;
+    double meb = epb[i] * mi;
+    mb -= epb[i] * ep[i] * mi;
+    for (int a = 0; a < ns; ++a) {
+      double n = pr.cnt[i][a];
+      if (n == 0.0) continue;
+      double ma = src.seg(a, 0), s = src.seg(a, 1), e = src.seg(a, 2), mu = src.seg(a, 3);
+      gseg[8 * a] += n * (mb + ms3b * s * s * s + meb * e);
+      gseg[8 * a + 1] += ms3b * n * ma * 3.0 * s * s;
+      gseg[8 * a + 2] += meb * n * ma;
+      gseg[8 * a + 3] += mu2b * n * 2.0 * mu;
+    }
+  }
+  *gT_out += gT;
+}
+
 // Step B: K input directions ids[0..K): out[k] = sum_idx cbar[idx] d coef[idx] / d direction ids[k]
-// ALL = true: every coefficient (cross-check of gc_base_adjoint in the CPU tests); ALL = false: only the
-// dipole and association groups (flat index >= 16 + nbond), the base group being handled by the adjoint.
+// ALL = true: every coefficient (cross-check of the reverse sweeps in the CPU tests); ALL = false: only the
+// association group (flat index >= 16 + nbond [+ 26 if dipolar]), the others being handled by the sweeps.
 template <int K, bool ALL>
 FD_NOINLINE void gc_input_grad_pass(const GcSource& src, int nrec, const int* ids, const double* cbar, double (&out)[K]) {
   GcDualSource<K> ds;
@@ -551,7 +639,7 @@ FD_NOINLINE void gc_input_grad_pass(const GcSource& src, int nrec, const int* id
 #pragma unroll
   for (int k = 0; k < K; ++k) out[k] = 0.0;
   int idx = 0;
-  const int skip = ALL ? 0 : 16 + cd.nbond;
+  const int skip = ALL ? 0 : 16 + cd.nbond + (cd.dipolar ? 26 : 0);
 #define FEOS_X(f)                                                 \
   {                                                               \
     if (idx >= skip)                                              \

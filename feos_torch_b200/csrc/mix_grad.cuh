@@ -220,6 +220,139 @@ FD_NOINLINE void mix_base_coef_adjoint(const MixCoef<double, NB, GC>& c, const d
   cbar[15] = point_comb(pi.q2 * (i1 * i1), ps.q2 * r11, q);
 }
 
+// ---- closed-form coefficient adjoints of the Gross-Vrabec dipole term -------------------------------
+//   a_dip = phi2^2 / (phi2 - phi3),
+//   phi2 = -pi sum_k tt_k J2_k ps_k,            J2_k = PA0 + pw1_k PA1 + pw2_k PA2 + pe_k (PB0 + pw1_k PB1 + pw2_k PB2)
+//   phi3 = -4/3 pi^2 sum_t ttt_t J3_t ts_t,     J3_t = PC0 + tw1_t PC1 + tw2_t PC2
+// with tt = (t0^2, t0 t1, t1^2), ttt = (t0^3, t0^2 t1, t1^2 t0, t1^3), t_i = rho_i mu2t_i and the
+// polynomials PA_j, PB_j, PC_j in eta = zeta_3.  Every one of the 26 coefficients enters linearly or
+// through these few products, so the gradient costs about as much as the term itself.
+template <class R>
+struct DipolePhase {
+  R pa[3], pb[3], pc[3], dpa[3], dpb[3], dpc[3];  // polynomials in eta and their eta-derivatives
+  R t0, t1, tt[3], ttt[4];
+  R j2[3], j3[4];
+  R w2, w3;  // d a / d phi2 * (-pi),  d a / d phi3 * (-4/3 pi^2)
+  R deta;    // d a_dip / d eta
+};
+
+template <class R, class C>
+FD void dipole_phase(DipolePhase<R>& d, const C& c, const R& rho0, const R& rho1, const R& eta) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    // Horner with derivative; orders 4 (AD), 2 (BD), 3 (CD)
+    R v(cAD[4][j]), dv(0.0);
+#pragma unroll
+    for (int n = 3; n >= 0; --n) {
+      dv = dv * eta + v;
+      v = v * eta + cAD[n][j];
+    }
+    d.pa[j] = v;
+    d.dpa[j] = dv;
+    v = R(cBD[2][j]);
+    dv = R(0.0);
+#pragma unroll
+    for (int n = 1; n >= 0; --n) {
+      dv = dv * eta + v;
+      v = v * eta + cBD[n][j];
+    }
+    d.pb[j] = v;
+    d.dpb[j] = dv;
+    v = R(cCD[3][j]);
+    dv = R(0.0);
+#pragma unroll
+    for (int n = 2; n >= 0; --n) {
+      dv = dv * eta + v;
+      v = v * eta + cCD[n][j];
+    }
+    d.pc[j] = v;
+    d.dpc[j] = dv;
+  }
+  d.t0 = rho0 * c.mu2t[0];
+  d.t1 = rho1 * c.mu2t[1];
+  d.tt[0] = d.t0 * d.t0;
+  d.tt[1] = d.t0 * d.t1;
+  d.tt[2] = d.t1 * d.t1;
+  d.ttt[0] = d.tt[0] * d.t0;
+  d.ttt[1] = d.tt[0] * d.t1;
+  d.ttt[2] = d.tt[2] * d.t0;
+  d.ttt[3] = d.tt[2] * d.t1;
+  R phi2(0.0), phi3(0.0), e2(0.0), e3(0.0);  // e2, e3: d phi / d eta (before the constant factors)
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    d.j2[k] = (d.pa[0] + d.pa[1] * c.pw1[k] + d.pa[2] * c.pw2[k]) + (d.pb[0] + d.pb[1] * c.pw1[k] + d.pb[2] * c.pw2[k]) * c.pe[k];
+    R dj = (d.dpa[0] + d.dpa[1] * c.pw1[k] + d.dpa[2] * c.pw2[k]) + (d.dpb[0] + d.dpb[1] * c.pw1[k] + d.dpb[2] * c.pw2[k]) * c.pe[k];
+    R w = d.tt[k] * c.ps[k];
+    phi2 = phi2 + w * d.j2[k];
+    e2 = e2 + w * dj;
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    d.j3[t] = d.pc[0] + d.pc[1] * c.tw1[t] + d.pc[2] * c.tw2[t];
+    R dj = d.dpc[0] + d.dpc[1] * c.tw1[t] + d.dpc[2] * c.tw2[t];
+    R w = d.ttt[t] * c.ts[t];
+    phi3 = phi3 + w * d.j3[t];
+    e3 = e3 + w * dj;
+  }
+  phi2 = phi2 * (-kPi);
+  phi3 = phi3 * (-4.0 / 3.0 * kPi * kPi);
+  R idf = ad_recip(phi2 - phi3);
+  R r = phi2 * idf;
+  d.w2 = (r * (phi2 - 2.0 * phi3) * idf) * (-kPi);
+  d.w3 = (r * r) * (-4.0 / 3.0 * kPi * kPi);
+  d.deta = d.w2 * e2 + d.w3 * e3;
+}
+
+// cbar[first .. first + 25] = d p_red / d (dipole coefficients) in the order of FEOS_VISIT_COEF (mu2t[2]; pw1, pw2,
+// pe, ps per pair; tw1, tw2, ts per triplet); ADDS the dipole term's share to the z[3][i] adjoints cbar[6], cbar[7].
+template <int NB, bool GC>
+FD_NOINLINE void mix_dipole_coef_adjoint(const MixCoef<double, NB, GC>& c, const double (&spec)[2], const double (&inc)[2],
+                                         const PointWeights& q, double* cbar, int first) {
+  const double i0 = inc[0], i1 = inc[1];
+  const D1 s0(spec[0], q.dir[0]), s1(spec[1], q.dir[1]);
+  DipolePhase<double> di;
+  DipolePhase<D1> ds;
+  dipole_phase(di, c, i0, i1, i0 * c.z[3][0] + i1 * c.z[3][1]);
+  dipole_phase(ds, c, s0, s1, s0 * c.z[3][0] + s1 * c.z[3][1]);
+  cbar[6] += point_comb(di.deta * i0, ds.deta * s0, q);
+  cbar[7] += point_comb(di.deta * i1, ds.deta * s1, q);
+  // mu2t_i through t_i = rho_i mu2t_i
+  {
+    double a2 = (2.0 * di.t0) * (c.ps[0] * di.j2[0]) + di.t1 * (c.ps[1] * di.j2[1]);
+    double a3 = (3.0 * di.tt[0]) * (c.ts[0] * di.j3[0]) + (2.0 * di.tt[1]) * (c.ts[1] * di.j3[1]) + di.tt[2] * (c.ts[2] * di.j3[2]);
+    D1 b2 = (2.0 * ds.t0) * (ds.j2[0] * c.ps[0]) + ds.t1 * (ds.j2[1] * c.ps[1]);
+    D1 b3 = (3.0 * ds.tt[0]) * (ds.j3[0] * c.ts[0]) + (2.0 * ds.tt[1]) * (ds.j3[1] * c.ts[1]) + ds.tt[2] * (ds.j3[2] * c.ts[2]);
+    cbar[first] = point_comb((di.w2 * a2 + di.w3 * a3) * i0, (ds.w2 * b2 + ds.w3 * b3) * s0, q);
+    a2 = di.t0 * (c.ps[1] * di.j2[1]) + (2.0 * di.t1) * (c.ps[2] * di.j2[2]);
+    a3 = di.tt[0] * (c.ts[1] * di.j3[1]) + (2.0 * di.tt[1]) * (c.ts[2] * di.j3[2]) + (3.0 * di.tt[2]) * (c.ts[3] * di.j3[3]);
+    b2 = ds.t0 * (ds.j2[1] * c.ps[1]) + (2.0 * ds.t1) * (ds.j2[2] * c.ps[2]);
+    b3 = ds.tt[0] * (ds.j3[1] * c.ts[1]) + (2.0 * ds.tt[1]) * (ds.j3[2] * c.ts[2]) + (3.0 * ds.tt[2]) * (ds.j3[3] * c.ts[3]);
+    cbar[first + 1] = point_comb((di.w2 * a2 + di.w3 * a3) * i1, (ds.w2 * b2 + ds.w3 * b3) * s1, q);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double wi = di.w2 * di.tt[k];
+    D1 ws = ds.w2 * ds.tt[k];
+    double wpi = wi * c.ps[k];
+    D1 wps = ws * c.ps[k];
+    double* o = cbar + first + 2 + 4 * k;
+    o[0] = point_comb(wpi * (di.pa[1] + di.pb[1] * c.pe[k]), wps * (ds.pa[1] + ds.pb[1] * c.pe[k]), q);
+    o[1] = point_comb(wpi * (di.pa[2] + di.pb[2] * c.pe[k]), wps * (ds.pa[2] + ds.pb[2] * c.pe[k]), q);
+    o[2] = point_comb(wpi * (di.pb[0] + di.pb[1] * c.pw1[k] + di.pb[2] * c.pw2[k]),
+                      wps * (ds.pb[0] + ds.pb[1] * c.pw1[k] + ds.pb[2] * c.pw2[k]), q);
+    o[3] = point_comb(wi * di.j2[k], ws * ds.j2[k], q);
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    double wi = di.w3 * di.ttt[t];
+    D1 ws = ds.w3 * ds.ttt[t];
+    double* o = cbar + first + 14 + 3 * t;
+    o[0] = point_comb((wi * c.ts[t]) * di.pc[1], (ws * c.ts[t]) * ds.pc[1], q);
+    o[1] = point_comb((wi * c.ts[t]) * di.pc[2], (ws * c.ts[t]) * ds.pc[2], q);
+    o[2] = point_comb(wi * di.j3[t], ws * ds.j3[t], q);
+  }
+}
+
 // out[k] = g * d(p_bubble/dew [Pa]) / d(direction ids[k])
 template <int K>
 FD_NOINLINE void mix_point_grad_pass(const double (&prm)[16], const double (&kij)[2], double T, const double (&spec)[2],

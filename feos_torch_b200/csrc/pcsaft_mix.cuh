@@ -351,10 +351,10 @@ FD R gc_cross_assoc(const R (&rho)[2], const R (&dl)[4]) {
   return rho[0] * (2.0 * ad_log(X0) - X0 + 1.0) + rho[1] * (2.0 * ad_log(X1) - X1 + 1.0);
 }
 
-// PARTS: bit 0 = hard sphere + hard chain + dispersion (the "base" group), bit 1 = dipole + association.
-// The gradient kernels evaluate the two groups separately (closed-form coefficient adjoints for the base
-// group, dual passes for the rest).
-template <class P, class R, int NB, bool GC, int PARTS = 3>
+// PARTS: bit 0 = hard sphere + hard chain + dispersion (the "base" group), bit 1 = dipole term, bit 2 =
+// association.  The gradient kernels evaluate the groups separately (closed-form coefficient adjoints for
+// the base and dipole groups, dual passes for association).
+template <class P, class R, int NB, bool GC, int PARTS = 7>
 FD R mix_helmholtz(const MixCoef<P, NB, GC>& c, const R& rho0, const R& rho1) {
   R z0 = rho0 * c.z[0][0] + rho1 * c.z[0][1];
   R z1 = rho0 * c.z[1][0] + rho1 * c.z[1][1];
@@ -441,7 +441,7 @@ FD R mix_helmholtz(const MixCoef<P, NB, GC>& c, const R& rho0, const R& rho1) {
   }
 
   // association (:118-152)
-  if ((PARTS & 2) && c.cat != kAssocNone) {
+  if ((PARTS & 4) && c.cat != kAssocNone) {
     R z2om = z2 * omi;
     if (c.cat == kAssocSelf) {
       R delta = mix_strength(c, 0, z2om, omi);

@@ -367,6 +367,7 @@ void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const d
     } else {
       double gkab[kGcMaxSeg * kGcMaxSeg] = {0.0};
       gc_base_adjoint(s, b.c, cbar, gseg, gp2, &gtr, gkab);
+      if (b.c.dipolar) gc_dipole_adjoint(s, b.c, cbar + 16 + b.c.nbond, gseg, &gtr);
       for (int a = 0; a < pr.nseg; ++a)
         for (int c2 = 0; c2 < pr.nseg; ++c2)
           if (pr.krec[a][c2] >= 0) grad_kab[pr.krec[a][c2]] += gkab[kGcMaxSeg * a + c2] * scale;
