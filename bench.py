@@ -129,11 +129,16 @@ class C2:
     """BASELINE.json configs[1]: PcSaftPure vapor_pressure + liquid_density, fwd + parameter gradients."""
     name = "C2: PcSaftPure vapor_pressure + liquid_density fwd+bwd, synthetic non-associating (params,T) pairs"
     dominant = "feos_dev_pure_vle_fwd"
-    kernel = "pure_vle_fwd_kernel(+retry)"
+    kernel = "pure_vle_queue_kernel(+retry)"
     flops_per_eval = F_D2
     io_bytes_per_state = 64 + 8 + 16 + 8 + 1
+    # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the dominant kernel at 1 M
+    # states, per state (profiles/README.md)
+    traffic_per_state = 80.5
+    traffic_source = "profiles/r1_final_pure_vle_queue_raw.csv"
     h2d_per_state = 64 + 8 + 8
     d2h_per_state = 64 + 2 * 8 + 2
+    default_n = 1_000_000
 
     def __init__(self, n, rank, dev):
         from feos_torch_b200 import PcSaftPure
@@ -180,6 +185,75 @@ class C2:
         return evals.double().mean().item()
 
 
+def critical_temperature(PcSaftPure, params, t_lo, t_hi, iters=22):
+    """Per-state T_c estimate by bisection on the converged/failed mask of the VLE kernel (workload
+    generation only, untimed): the largest T in [t_lo, t_hi] with a vapour-liquid equilibrium."""
+    model = PcSaftPure(params)
+    lo, hi = t_lo.clone(), t_hi.clone()
+    for _ in range(iters):
+        mid = 0.5 * (lo + hi)
+        failed, _ = model.vapor_pressure(mid)
+        lo = torch.where(failed, lo, mid)
+        hi = torch.where(failed, mid, hi)
+    return lo
+
+
+class C3:
+    """BASELINE.json configs[2]: PcSaftPure equilibrium_liquid_density with 2B-associating parameters
+    (kappa_AB ~ logU[0.003, 0.1], eps_AB/k ~ U[1500, 3000] K, nA = nB = 1), T = tau T_c(theta), tau ~ U[0.55, 0.95]
+    with the per-state T_c from `critical_temperature`."""
+    name = "C3: PcSaftPure equilibrium_liquid_density fwd+bwd, synthetic 2B-associating (params,T) pairs"
+    dominant = "feos_dev_pure_vle_fwd"
+    kernel = "pure_vle_queue_kernel(+retry)"
+    flops_per_eval = F_D2
+    io_bytes_per_state = 64 + 8 + 16 + 8 + 1
+    traffic_per_state = None
+    traffic_source = None
+    h2d_per_state = 64 + 8
+    d2h_per_state = 64 + 8 + 1
+    default_n = 10_000_000
+
+    def __init__(self, n, rank, dev):
+        from feos_torch_b200 import PcSaftPure
+
+        self.PcSaftPure, self.n, self.dev = PcSaftPure, n, dev
+        g = torch.Generator().manual_seed(4000 + rank)
+        r = lambda: torch.rand(n, generator=g, dtype=torch.float64)
+        params = torch.zeros((n, 8), dtype=torch.float64)
+        params[:, 0], params[:, 1], params[:, 2] = 1.0 + 3.0 * r(), 3.0 + r(), 150.0 + 200.0 * r()
+        params[:, 4] = torch.exp(math.log(0.003) + r() * math.log(0.1 / 0.003))
+        params[:, 5] = 1500.0 + 1500.0 * r()
+        params[:, 6] = 1.0
+        params[:, 7] = 1.0
+        tau = 0.55 + 0.40 * r()
+        self.params_h = params.pin_memory()
+        self.params = self.params_h.to(dev).requires_grad_(True)
+        with torch.no_grad():
+            m, eps = self.params[:, 0].detach(), self.params[:, 2].detach()
+            tc0 = eps * (0.6380 + 0.7070 * m - 0.06418 * m * m)  # non-associating T_c: a lower bound
+            tc = critical_temperature(PcSaftPure, self.params.detach(), 0.9 * tc0, 6.0 * tc0)
+            self.T = (tau.to(dev) * tc).contiguous()
+        self.T_h = self.T.cpu().pin_memory()
+        self.shared = []
+
+    def step_device(self):
+        self.params.grad = None
+        nans, rho = self.PcSaftPure(self.params).equilibrium_liquid_density(self.T)
+        rho.sum().backward()
+        return nans
+
+    def step_e2e(self):
+        x = self.params_h.requires_grad_(True)
+        x.grad = None
+        nans, rho = self.PcSaftPure(x).equilibrium_liquid_density(self.T_h)
+        loss = rho.sum()
+        loss.backward()
+        return float(loss.detach()), x.grad
+
+    def mean_evals(self, _lib):
+        return C2.mean_evals(self, _lib)
+
+
 class C4:
     """BASELINE.json configs[3]: PcSaftMix bubble + dew point of ONE shared pair with a shared k_ij leaf,
     fit loss sum (p - p_target)^2, k_ij gradient summed over the GPUs by one NCCL all-reduce."""
@@ -188,8 +262,11 @@ class C4:
     kernel = "mix_point_fwd_kernel(+retry)"
     flops_per_eval = 3485.0  # binary non-associating hyper-dual evaluation, SURVEY.md section 8(d)
     io_bytes_per_state = 128 + 16 + 8 + 8 + 32 + 8 + 1
+    traffic_per_state = 196.0
+    traffic_source = "profiles/r1_final_mix_point_fwd_raw.csv"
     h2d_per_state = 8 + 8
     d2h_per_state = 2
+    default_n = 1_000_000
 
     def __init__(self, n, rank, dev):
         from feos_torch_b200 import PcSaftMix
@@ -255,8 +332,11 @@ class C5:
     kernel = "gc_point_fwd_kernel(+retry)"
     flops_per_eval = 4687.0  # GC compact hyper-dual evaluation, SURVEY.md section 8(d)
     io_bytes_per_state = 4 + 16 + 8 + 8 + 32 + 8 + 1
+    traffic_per_state = 51.0
+    traffic_source = "profiles/r1_final_gc_point_fwd_raw.csv"
     h2d_per_state = 8 + 8
     d2h_per_state = 2
+    default_n = 1_000_000
 
     def __init__(self, n, rank, dev):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -322,7 +402,7 @@ class C5:
         return evals.double().mean().item()
 
 
-WORKLOADS = {"c2": C2, "c4": C4, "c5": C5}
+WORKLOADS = {"c2": C2, "c3": C3, "c4": C4, "c5": C5}
 
 
 def main():
@@ -332,7 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (BASELINE.json metric)")
-    ap.add_argument("--n", type=int, default=1_000_000, help="states per GPU per step")
+    ap.add_argument("--n", type=int, default=0, help="states per GPU per step (default: the workload's BASELINE size)")
     ap.add_argument("--ref-n", type=int, default=20_000, help="states per step of the reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -356,7 +436,7 @@ def main():
     from feos_torch_b200 import _lib
 
     _lib.load()
-    n = args.n
+    n = args.n or WORKLOADS[args.workload].default_n
     wl = WORKLOADS[args.workload](n, rank, dev)
     flush = torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device=dev)
 
@@ -422,7 +502,8 @@ def main():
     io_bytes = n * wl.io_bytes_per_state
     roofline = {
         "bound": "fp64", "kernel": wl.kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak else None, "traffic": None,
+        "frac": achieved / peak if peak else None,
+        "traffic": wl.traffic_per_state * n if wl.traffic_per_state else None, "traffic_source": wl.traffic_source,
         "peak_source": "DFMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure); spec 148 SM x 64 lanes x 2 x 1.965 GHz = %.1f" % spec,
         "flops_per_launch": flops_per_launch, "mean_evals_per_state": mean_evals, "flops_per_eval": wl.flops_per_eval,
         "kernel_ms": dom_ms, "share_of_step": kern_ms[dom] / step_ms,
@@ -436,7 +517,9 @@ def main():
     if not args.no_cpu_baseline and args.workload == "c2":
         cpu = cpu_baseline(args.ref_n)
     line = {
-        "metric": METRIC if args.workload == "c2" else "%s_binary_bubble_plus_dew_solves_plus_grads_per_s" % ("pcsaft" if args.workload == "c4" else "gc_pcsaft"),
+        "metric": {"c2": METRIC, "c3": "pcsaft_equilibrium_liquid_density_solves_plus_grads_per_s",
+                   "c4": "pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s",
+                   "c5": "gc_pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s"}[args.workload],
         "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",

@@ -109,3 +109,8 @@ def ptr(t):
     if hasattr(t, "data_ptr"):
         return ctypes.c_void_p(t.data_ptr())
     return ctypes.c_void_p(t.ctypes.data)
+
+
+def ptr_at(t, byte_offset):
+    """``ptr(t)`` advanced by ``byte_offset`` bytes (row-chunked launches)."""
+    return ctypes.c_void_p(t.data_ptr() + byte_offset)

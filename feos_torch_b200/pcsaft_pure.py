@@ -23,22 +23,98 @@ def _cuda_device(t):
     return t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device())
 
 
+# ---- host tensors in / out: chunked, stream-pipelined transfers --------------------------------
+# A [N, 8] parameter tensor on the host is 64 B per state each way (parameters in, gradients out): at
+# PCIe speed that is as long as the solves themselves.  Large pinned inputs are therefore copied in row
+# chunks on a copy stream with one event per chunk; the forward kernels are launched per chunk behind
+# its event, and the backward kernels record one event per chunk so that the gradient's device->host
+# copy of chunk k runs while chunk k + 1 is being computed.
+_CHUNK_MIN = 1 << 18  # rows; below 2 chunks of this size a single copy is used
+_COPY_STREAMS = {}
+
+
+class _Chunks:
+    """Row ranges of a device tensor and the events after which each range is valid."""
+    __slots__ = ("bounds", "events", "version")
+
+    def __init__(self, bounds, events, version):
+        self.bounds, self.events, self.version = bounds, events, version
+
+
+def _chunk_bounds(n):
+    k = max(1, min(16, n // _CHUNK_MIN))
+    step = (-(-n // k) + 127) // 128 * 128
+    return [(a, min(a + step, n)) for a in range(0, n, step)]
+
+
+def _copy_stream(dev, kind):
+    key = (dev.index, kind)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
+def _chunks_of(t):
+    """The pending-chunk record of a tensor, if it is still the tensor the record was made for."""
+    ch = getattr(t, "_feos_chunks", None)
+    if ch is not None and ch.version != t._version:  # modified in place since (e.g. gradient accumulation)
+        return None
+    return ch
+
+
+def _wait_chunks(t):
+    """Make the current stream wait for every pending chunk of ``t`` (consumers that read it whole)."""
+    ch = _chunks_of(t)
+    if ch is not None:
+        cur = torch.cuda.current_stream(t.device)
+        for ev in ch.events:
+            cur.wait_event(ev)
+    return t
+
+
 class _HostToDevice(torch.autograd.Function):
     """Host tensor -> device for the computation; the gradient comes back into PINNED host memory
     (torch's caching host allocator), so the device->host copy runs at PCIe speed instead of paging
     in a fresh pageable buffer every step."""
+    last_chunks = None
 
     @staticmethod
-    def forward(ctx, t, dev):
+    def forward(ctx, t, dev, chunked):
+        n = t.shape[0] if t.dim() else 0
+        if chunked and n >= 2 * _CHUNK_MIN and t.dtype == torch.float64 and t.is_contiguous() and t.is_pinned():
+            out = torch.empty(t.shape, dtype=torch.float64, device=dev)
+            cur = torch.cuda.current_stream(dev)
+            cs = _copy_stream(dev, "h2d")
+            cs.wait_stream(cur)  # the allocation may recycle memory still in use on the current stream
+            bounds, events = _chunk_bounds(n), []
+            with torch.cuda.stream(cs):
+                for a, b in bounds:
+                    out[a:b].copy_(t[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cs)
+                    events.append(ev)
+            out.record_stream(cs)
+            _HostToDevice.last_chunks = _Chunks(bounds, events, out._version)
+            return out
+        _HostToDevice.last_chunks = None
         return t.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
 
     @staticmethod
     def backward(ctx, g):
-        return _to_host(g), None
+        return _to_host(g, _chunks_of(g)), None, None
 
 
-def _to_host(t):
+def _to_host(t, chunks=None):
     out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    if chunks is not None:
+        ds = _copy_stream(t.device, "d2h")
+        with torch.cuda.stream(ds):
+            for (a, b), ev in zip(chunks.bounds, chunks.events):
+                ds.wait_event(ev)
+                out[a:b].copy_(t[a:b], non_blocking=True)
+        t.record_stream(ds)
+        ds.synchronize()
+        return out
     out.copy_(t, non_blocking=True)
     torch.cuda.current_stream(t.device).synchronize()
     return out
@@ -54,19 +130,57 @@ class _DeviceToHost(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if g.numel() > 1 and all(st == 0 for st in g.stride()):
+            # gradient of a sum: one value expanded -- move the value, expand on the device
+            return g.as_strided((1,), (1,), g.storage_offset()).to(ctx.dev, non_blocking=True).expand(g.shape)
         return g.to(ctx.dev, non_blocking=True)
 
 
-def _prep(t, dev):
+def _prep(t, dev, chunked=False):
     if not t.is_cuda and t.requires_grad:
-        return _HostToDevice.apply(t, dev)
-    return t.to(device=dev, dtype=torch.float64).contiguous()
+        out = _HostToDevice.apply(t, dev, chunked)
+        if _HostToDevice.last_chunks is not None:
+            out._feos_chunks = _HostToDevice.last_chunks
+            _HostToDevice.last_chunks = None
+        return out
+    # (asynchronous for pinned sources; every property call synchronises before it returns)
+    return t.to(device=dev, dtype=torch.float64, non_blocking=True).contiguous()
+
+
+def _off(t, rows):
+    """Pointer to row ``rows`` of a contiguous tensor (chunked launches through the C ABI)."""
+    if t is None:
+        return None
+    stride = t.stride(0) if t.dim() > 1 else 1
+    return _lib.ptr_at(t, rows * stride * t.element_size())
+
+
+def _launch_chunked(params, ranges_events, launch):
+    """``launch(a, b)`` per pending chunk of ``params`` behind its event, or once over all rows."""
+    cur = torch.cuda.current_stream(params.device)
+    for (a, b), ev in ranges_events:
+        if ev is not None:
+            cur.wait_event(ev)
+        launch(a, b)
+
+
+def _record_chunk_events(bounds, launch, dev):
+    """Run ``launch(a, b)`` per range on the current stream, recording one event after each."""
+    cur = torch.cuda.current_stream(dev)
+    events = []
+    for a, b in bounds:
+        launch(a, b)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        events.append(ev)
+    return events
 
 
 def _back(t, out_device):
     """Return a result on the device the caller's tensors live on (the reference's `.to(self.m.device)`)."""
     if out_device.type == "cpu":
-        return _DeviceToHost.apply(t) if t.dtype == torch.float64 else t.cpu()
+        # masks too go through pinned memory: a pageable device->host copy runs at a fraction of PCIe speed
+        return _DeviceToHost.apply(t) if t.dtype == torch.float64 else _to_host(t)
     return t.to(out_device)
 
 
@@ -97,15 +211,19 @@ class _PureVle(torch.autograd.Function):
         rho = torch.empty((n, 2), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
+        ch = _chunks_of(params)
         with torch.cuda.device(dev):
-            _lib.timed_call(
-                "feos_dev_pure_vle_fwd", _lib.ptr(params), _lib.ptr(temperature), n, _lib.ptr(rho),
-                _lib.ptr(val) if which == 0 else None, _lib.ptr(val) if which == 1 else None,
-                _lib.ptr(failed), None, _stream(),
-            )
+            def launch(a, b):
+                _lib.timed_call(
+                    "feos_dev_pure_vle_fwd", _off(params, a), _off(temperature, a), b - a, _off(rho, a),
+                    _off(val, a) if which == 0 else None, _off(val, a) if which == 1 else None,
+                    _off(failed, a), None, _stream(),
+                )
+            _launch_chunked(params, zip(ch.bounds, ch.events) if ch else [((0, n), None)], launch)
             out, pos = compact(failed, val)
         ctx.save_for_backward(params, temperature, rho, failed, pos)
         ctx.which = which
+        ctx.to_host = ch is not None  # parameters came from the host: their gradient goes back there
         ctx.mark_non_differentiable(rho, failed)
         return out, failed, rho
 
@@ -117,11 +235,18 @@ class _PureVle(torch.autograd.Function):
         grad_params = torch.empty_like(params)
         grad_t = torch.empty_like(temperature) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(params.device):
-            _lib.timed_call(
-                "feos_dev_pure_vle_bwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(rho), _lib.ptr(failed),
-                _lib.ptr(pos), _lib.ptr(g) if ctx.which == 0 else None, _lib.ptr(g) if ctx.which == 1 else None, n,
-                _lib.ptr(grad_params), _lib.ptr(grad_t), _stream(),
-            )
+            def launch(a, b):
+                _lib.timed_call(
+                    "feos_dev_pure_vle_bwd", _off(params, a), _off(temperature, a), _off(rho, a), _off(failed, a),
+                    _off(pos, a), _lib.ptr(g) if ctx.which == 0 else None, _lib.ptr(g) if ctx.which == 1 else None, b - a,
+                    _off(grad_params, a), _off(grad_t, a), _stream(),
+                )
+            if ctx.to_host and n >= 2 * _CHUNK_MIN:
+                bounds = _chunk_bounds(n)
+                events = _record_chunk_events(bounds, launch, params.device)
+                grad_params._feos_chunks = _Chunks(bounds, events, grad_params._version)
+            else:
+                launch(0, n)
         return grad_params, grad_t, None
 
 
@@ -133,13 +258,17 @@ class _PureRhoTp(torch.autograd.Function):
         rho = torch.empty((n,), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
+        ch = _chunks_of(params)
         with torch.cuda.device(dev):
-            _lib.timed_call(
-                "feos_dev_pure_rho_tp_fwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(pressure), n,
-                _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None, _stream(),
-            )
+            def launch(a, b):
+                _lib.timed_call(
+                    "feos_dev_pure_rho_tp_fwd", _off(params, a), _off(temperature, a), _off(pressure, a), b - a,
+                    _off(rho, a), _off(val, a), _off(failed, a), None, _stream(),
+                )
+            _launch_chunked(params, zip(ch.bounds, ch.events) if ch else [((0, n), None)], launch)
             out, pos = compact(failed, val)
         ctx.save_for_backward(params, temperature, pressure, rho, failed, pos)
+        ctx.to_host = ch is not None
         ctx.mark_non_differentiable(rho, failed)
         return out, failed, rho
 
@@ -153,11 +282,18 @@ class _PureRhoTp(torch.autograd.Function):
         grad_t = torch.empty_like(temperature) if need_t else None
         grad_pr = torch.empty_like(pressure) if need_pr else None
         with torch.cuda.device(params.device):
-            _lib.timed_call(
-                "feos_dev_pure_rho_tp_bwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(pressure),
-                _lib.ptr(rho), _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, _lib.ptr(grad_params),
-                _lib.ptr(grad_t), _lib.ptr(grad_pr), _stream(),
-            )
+            def launch(a, b):
+                _lib.timed_call(
+                    "feos_dev_pure_rho_tp_bwd", _off(params, a), _off(temperature, a), _off(pressure, a),
+                    _off(rho, a), _off(failed, a), _off(pos, a), _lib.ptr(g), b - a, _off(grad_params, a),
+                    _off(grad_t, a), _off(grad_pr, a), _stream(),
+                )
+            if ctx.to_host and need_p and n >= 2 * _CHUNK_MIN:
+                bounds = _chunk_bounds(n)
+                events = _record_chunk_events(bounds, launch, params.device)
+                grad_params._feos_chunks = _Chunks(bounds, events, grad_params._version)
+            else:
+                launch(0, n)
         return grad_params, grad_t, grad_pr
 
 
@@ -170,8 +306,16 @@ class PcSaftPure:
         _lib.load()  # fail loudly before any work if the CUDA extension is missing
         self._out_device = parameters.device
         self._dev = _cuda_device(parameters)
-        self._params = _prep(parameters, self._dev)
         self._source = parameters
+        # host parameters are copied at the first property call, AFTER that call's (small) state tensors: the
+        # copy engine works in submission order and the first chunk's kernel needs its temperatures
+        self._params_dev = None if (not parameters.is_cuda and parameters.requires_grad) else _prep(parameters, self._dev)
+
+    @property
+    def _params(self):
+        if self._params_dev is None:
+            self._params_dev = _prep(self._source, self._dev, chunked=True)  # the consumers below wait per chunk
+        return self._params_dev
 
     @property
     def parameters(self):
@@ -210,6 +354,7 @@ class PcSaftPure:
         n = t.shape[0]
         a, p, dp = (torch.empty((n,), dtype=torch.float64, device=self._dev) for _ in range(3))
         with torch.cuda.device(self._dev):
+            _wait_chunks(self._params)
             _lib.call("feos_dev_pure_state", _lib.ptr(self._params.detach()), _lib.ptr(t.detach()), _lib.ptr(r.detach()),
                       n, _lib.ptr(a), _lib.ptr(p), _lib.ptr(dp), _stream())
         return self._back(a), self._back(p), self._back(dp)

@@ -163,6 +163,55 @@ def test_full_size_properties(ft):
         assert ((fd - x.grad[idx, col]).abs() / fd.abs()).max().item() < 1e-5
 
 
+def test_full_size_c3(ft):
+    """BASELINE config C3 at full size (10 M states, 2B association, equilibrium_liquid_density): every
+    sub-critical state converges, the returned densities satisfy the equilibrium conditions (sample), the value
+    is the Newton step of pcsaft_pure.py:226-233 and the gradient matches finite differences (sample)."""
+    n = 10_000_000
+    P, _, _ = _c2_grid(n, 7, assoc=True)
+    Pg = P.cuda()
+    m, eps = Pg[:, 0], Pg[:, 2]
+    tc0 = eps * (0.6380 + 0.7070 * m - 0.06418 * m * m)
+    lo, hi = 0.9 * tc0, 6.0 * tc0
+    model = ft.PcSaftPure(Pg)
+    for _ in range(22):  # per-state T_c by bisection on the mask (association raises it above the non-assoc value)
+        mid = 0.5 * (lo + hi)
+        failed, _ = model.vapor_pressure(mid)
+        lo = torch.where(failed, lo, mid)
+        hi = torch.where(failed, mid, hi)
+    g = torch.Generator().manual_seed(8)
+    tau = (0.55 + 0.40 * torch.rand(n, generator=g, dtype=F64)).cuda()
+    Tg = tau * lo
+    x = Pg.clone().requires_grad_(True)
+    nans, rl = ft.PcSaftPure(x).equilibrium_liquid_density(Tg)
+    assert not nans.any() and rl.shape[0] == n and torch.isfinite(rl).all()
+    rl.sum().backward()
+    assert torch.isfinite(x.grad).all()
+    # equilibrium conditions at the solver densities, and the Newton-step formula, on a sample
+    k = 200_000
+    rho, status = ft.PcSaft.vapor_pressure(P[:k].numpy(), Tg[:k].cpu().numpy())
+    assert not status.any()
+    rv, rl_s = torch.from_numpy(rho[:, 0]).cuda(), torch.from_numpy(rho[:, 1]).cuda()
+    m2 = ft.PcSaftPure(Pg[:k])
+    aV, pV, _ = m2.derivatives(Tg[:k], rv)
+    aL, pL, dpL = m2.derivatives(Tg[:k], rl_s)
+    assert ((pL - pV).abs() / pV).max().item() < 1e-8
+    assert ((aV / rv + pV / rv + rv.log()) - (aL / rl_s + pL / rl_s + rl_s.log())).abs().max().item() < 1e-9
+    p_mx = -(aV / rv - aL / rl_s + (rv / rl_s).log()) / (1 / rv - 1 / rl_s)
+    want = (rl_s - (pL - p_mx) / dpL) / (1e3 * 6.02214076e23 * 1e-30)
+    assert rel(rl[:k].detach().cpu(), want.cpu()) < 1e-10
+    idx = torch.arange(0, 64, device="cuda")
+    for col in (0, 2, 4, 5):
+        h = 1e-6 * Pg[idx, col]
+        Pp, Pm = Pg[idx].clone(), Pg[idx].clone()
+        Pp[:, col] += h
+        Pm[:, col] -= h
+        _, vp_ = ft.PcSaftPure(Pp).equilibrium_liquid_density(Tg[idx])
+        _, vm_ = ft.PcSaftPure(Pm).equilibrium_liquid_density(Tg[idx])
+        fd = (vp_ - vm_) / (2 * h)
+        assert ((fd - x.grad[idx, col]).abs() / fd.abs()).max().item() < 1e-5
+
+
 def test_liquid_density_full_size(ft):
     n = 200_000
     P, T, _ = _c2_grid(n, 6)
@@ -182,6 +231,45 @@ def test_liquid_density_full_size(ft):
     rho_n, status = ft.PcSaft.liquid_density(P[:1000].numpy(), T[:1000].numpy(), pr[:1000].cpu().numpy())
     assert not status.any()
     assert rel(rho_n / (1e3 * 6.02214076e23 * 1e-30), rho[:1000].detach().cpu()) < 1e-12
+
+
+def test_host_pipeline_matches_device_path(ft):
+    """Pinned host tensors in -> chunked, stream-pipelined copies and launches; results and gradients must be
+    bit-identical to the device-resident path (same kernels, same inputs), with failed rows in the middle."""
+    n = 700_000
+    P, T, tau = _c2_grid(n, 9)
+    T[1000:1100] = T[1000:1100] / tau[1000:1100] * 1.4
+    T[n - 50:] = T[n - 50:] / tau[n - 50:] * 1.4
+    xd = P.cuda().requires_grad_(True)
+    nans_d, vp_d = ft.PcSaftPure(xd).vapor_pressure(T.cuda())
+    pr = torch.zeros(n, dtype=F64, device="cuda")
+    pr[~nans_d] = 1.1 * vp_d.detach()
+    pr[nans_d] = 1e6
+    nans2_d, rho_d = ft.PcSaftPure(xd).liquid_density(T.cuda(), pr)
+    (vp_d * torch.linspace(0.5, 1.5, vp_d.shape[0], dtype=F64, device="cuda")).sum().backward()
+    g1 = xd.grad.clone()
+    xd.grad = None
+    rho_d.sum().backward()
+    xh = P.clone().pin_memory().requires_grad_(True)
+    Th, ph = T.clone().pin_memory(), pr.cpu().pin_memory()
+    model = ft.PcSaftPure(xh)
+    nans_h, vp_h = model.vapor_pressure(Th)
+    assert not vp_h.is_cuda and torch.equal(nans_h, nans_d.cpu()) and torch.equal(vp_h.detach(), vp_d.detach().cpu())
+    (vp_h * torch.linspace(0.5, 1.5, vp_h.shape[0], dtype=F64)).sum().backward()
+    assert torch.equal(xh.grad, g1.cpu())
+    xh.grad = None
+    nans2_h, rho_h = model.liquid_density(Th, ph)
+    assert torch.equal(nans2_h, nans2_d.cpu()) and torch.equal(rho_h.detach(), rho_d.detach().cpu())
+    rho_h.sum().backward()
+    assert torch.equal(xh.grad, xd.grad.cpu())
+    # both properties feeding one host leaf (gradient accumulation on the device before the copy back)
+    xh.grad = None
+    m2 = ft.PcSaftPure(xh)
+    (m2.vapor_pressure(Th)[1].sum() + m2.liquid_density(Th, ph)[1].sum()).backward()
+    xd.grad = None
+    m3 = ft.PcSaftPure(xd)
+    (m3.vapor_pressure(T.cuda())[1].sum() + m3.liquid_density(T.cuda(), pr)[1].sum()).backward()
+    assert torch.equal(xh.grad, xd.grad.cpu())
 
 
 def test_edge_cases(ft):
