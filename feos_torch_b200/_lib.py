@@ -24,6 +24,10 @@ SIGNATURES = {
     "feos_dev_pure_rho_tp_fwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_rho_tp_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_state": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_state_bwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_state_bwd": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_gc_state_bwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _i64,
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_point_fwd": ([_vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_state": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),

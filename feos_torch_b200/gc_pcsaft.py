@@ -147,6 +147,48 @@ class _GcPoint(torch.autograd.Function):
         return g_seg, g_kab, g_phi, g_t, None, None, None
 
 
+class _GcState(torch.autograd.Function):
+    """(a, p, mu, v) = derivatives(T, rho [N,2]); backward = dual passes of csrc/state_grad.cuh."""
+
+    @staticmethod
+    def forward(ctx, seg_params, kab, phi, temperature, density, tables):
+        pairs_dev, pair_index, n_pairs = tables
+        n = temperature.shape[0]
+        dev = temperature.device
+        a = torch.empty((n,), dtype=torch.float64, device=dev)
+        p = torch.empty((n,), dtype=torch.float64, device=dev)
+        mu = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        v = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("feos_dev_gc_state", _lib.ptr(pairs_dev), n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
+                      _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
+                      _lib.ptr(density), n, _lib.ptr(a), _lib.ptr(p), _lib.ptr(mu), _lib.ptr(v), _stream())
+        ctx.save_for_backward(seg_params, kab, phi, temperature, density, pairs_dev, pair_index)
+        ctx.n_pairs = n_pairs
+        return a, p, mu, v
+
+    @staticmethod
+    def backward(ctx, ga, gp, gmu, gv):
+        seg_params, kab, phi, temperature, density, pairs_dev, pair_index = ctx.saved_tensors
+        n = temperature.shape[0]
+        ga, gp, gmu, gv = (None if g is None else g.contiguous() for g in (ga, gp, gmu, gv))
+        need_seg, need_kab, need_phi, need_t, need_r = ctx.needs_input_grad[:5]
+        g_seg = torch.zeros_like(seg_params) if need_seg else None
+        g_kab = torch.zeros_like(kab) if need_kab and kab.shape[0] else None
+        g_phi = torch.empty_like(phi) if need_phi and phi is not None else None
+        g_t = torch.empty_like(temperature) if need_t else None
+        g_r = torch.empty_like(density) if need_r else None
+        if n:
+            with torch.cuda.device(temperature.device):
+                _lib.call("feos_dev_gc_state_bwd", _lib.ptr(pairs_dev), ctx.n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
+                          _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
+                          _lib.ptr(density), n, _lib.ptr(ga), _lib.ptr(gp), _lib.ptr(gmu), _lib.ptr(gv), _lib.ptr(g_seg),
+                          _lib.ptr(g_kab), _lib.ptr(g_phi), _lib.ptr(g_t), _lib.ptr(g_r), _stream())
+        if need_kab and g_kab is None:
+            g_kab = torch.zeros_like(kab)
+        return g_seg, g_kab, g_phi, g_t, g_r, None
+
+
 class GcPcSaftMix:
     """GcPcSaftMix(segment_identifier, parameter, segment_lists, bond_lists, binary_segment_records, phi=None)
     -- gc_pcsaft.py:14-22.  ``parameter`` = 8 tensors of shape [S] (m, sigma, epsilon_k, mu, kappa_ab,
@@ -195,19 +237,12 @@ class GcPcSaftMix:
         return self._point(temperature, vapor_molefracs, False)
 
     def derivatives(self, temperature, density):
-        """(a [N], p/kT [N], mu_i [N,2], v_i [N,2]) at (T, rho [N,2]) -- gc_pcsaft.py:443-468."""
-        t = _prep(temperature.detach(), self._dev)
-        r = _prep(density.detach(), self._dev)
-        n = t.shape[0]
-        a = torch.empty((n,), dtype=torch.float64, device=self._dev)
-        p = torch.empty((n,), dtype=torch.float64, device=self._dev)
-        mu = torch.empty((n, 2), dtype=torch.float64, device=self._dev)
-        v = torch.empty((n, 2), dtype=torch.float64, device=self._dev)
-        with torch.cuda.device(self._dev):
-            _lib.call("feos_dev_gc_state", _lib.ptr(self._pairs), self._n_pairs, _lib.ptr(self._seg.detach()), self._seg.shape[0],
-                      _lib.ptr(self._kab.detach()), self._kab.shape[0], _lib.ptr(self._pair_index),
-                      _lib.ptr(None if self._phi is None else self._phi.detach()), _lib.ptr(t), _lib.ptr(r), n,
-                      _lib.ptr(a), _lib.ptr(p), _lib.ptr(mu), _lib.ptr(v), _stream())
+        """(a [N], p/kT [N], mu_i [N,2], v_i [N,2]) at (T, rho [N,2]) -- gc_pcsaft.py:443-468; carries gradients
+        w.r.t. the segment parameters, k_ab, phi, T and rho."""
+        t = _prep(temperature, self._dev)
+        r = _prep(density, self._dev)
+        tables = (self._pairs, self._pair_index, self._n_pairs)
+        a, p, mu, v = _GcState.apply(self._seg, self._kab, self._phi, t, r, tables)
         return self._back(a), self._back(p), self._back(mu), self._back(v)
 
     def helmholtz_energy_density(self, temperature, density, kab=None):

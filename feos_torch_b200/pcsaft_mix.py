@@ -48,6 +48,38 @@ class _MixPoint(torch.autograd.Function):
         return gp, gk, gt, None, None
 
 
+class _MixState(torch.autograd.Function):
+    """(a, p, mu, v) = derivatives(T, rho [N,2]); backward = dual passes of csrc/state_grad.cuh."""
+
+    @staticmethod
+    def forward(ctx, params, kij, temperature, density):
+        n = temperature.shape[0]
+        dev = params.device
+        a = torch.empty((n,), dtype=torch.float64, device=dev)
+        p = torch.empty((n,), dtype=torch.float64, device=dev)
+        mu = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        v = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("feos_dev_mix_state", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(density), n,
+                      _lib.ptr(a), _lib.ptr(p), _lib.ptr(mu), _lib.ptr(v), _stream())
+        ctx.save_for_backward(params, kij, temperature, density)
+        return a, p, mu, v
+
+    @staticmethod
+    def backward(ctx, ga, gp, gmu, gv):
+        params, kij, temperature, density = ctx.saved_tensors
+        n = temperature.shape[0]
+        ga, gp, gmu, gv = (None if g is None else g.contiguous() for g in (ga, gp, gmu, gv))
+        need = ctx.needs_input_grad
+        out = [torch.empty_like(x) if nd else None for x, nd in zip((params, kij, temperature, density), need)]
+        if n:
+            with torch.cuda.device(params.device):
+                _lib.call("feos_dev_mix_state_bwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(density), n,
+                          _lib.ptr(ga), _lib.ptr(gp), _lib.ptr(gmu), _lib.ptr(gv), _lib.ptr(out[0]), _lib.ptr(out[1]),
+                          _lib.ptr(out[2]), _lib.ptr(out[3]), _stream())
+        return tuple(out)
+
+
 class PcSaftMix:
     """parameters [N, 2, 8] (rows as in PcSaftPure), kij [N, 2] = (k_ij, epsilon_k_aibj; 0 = combining rule)."""
 
@@ -102,17 +134,11 @@ class PcSaftMix:
         return self._point(temperature, vapor_molefracs, False)
 
     def derivatives(self, temperature, density):
-        """(a [N], p/kT [N], mu_i^res/kT [N,2], v_i [N,2]) at (T, rho [N,2]) -- pcsaft_mix.py:395-420."""
-        t = _prep(temperature.detach(), self._dev)
-        r = _prep(density.detach(), self._dev)
-        n = t.shape[0]
-        a = torch.empty((n,), dtype=torch.float64, device=self._dev)
-        p = torch.empty((n,), dtype=torch.float64, device=self._dev)
-        mu = torch.empty((n, 2), dtype=torch.float64, device=self._dev)
-        v = torch.empty((n, 2), dtype=torch.float64, device=self._dev)
-        with torch.cuda.device(self._dev):
-            _lib.call("feos_dev_mix_state", _lib.ptr(self._params.detach()), _lib.ptr(self._kij.detach()), _lib.ptr(t),
-                      _lib.ptr(r), n, _lib.ptr(a), _lib.ptr(p), _lib.ptr(mu), _lib.ptr(v), _stream())
+        """(a [N], p/kT [N], mu_i^res/kT [N,2], v_i [N,2]) at (T, rho [N,2]) -- pcsaft_mix.py:395-420; carries
+        gradients w.r.t. parameters, kij, T and rho like the reference's hyper-dual evaluation under autograd."""
+        t = _prep(temperature, self._dev)
+        r = _prep(density, self._dev)
+        a, p, mu, v = _MixState.apply(self._params, self._kij, t, r)
         return self._back(a), self._back(p), self._back(mu), self._back(v)
 
     def helmholtz_energy_density(self, temperature, density):

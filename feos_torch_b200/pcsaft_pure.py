@@ -297,6 +297,40 @@ class _PureRhoTp(torch.autograd.Function):
         return grad_params, grad_t, grad_pr
 
 
+def _grad_or_none(g):
+    return None if g is None else g.contiguous()
+
+
+class _PureState(torch.autograd.Function):
+    """(a, p, dp) = derivatives(T, rho); backward = one kernel over nested dual numbers (csrc/state_grad.cuh)."""
+
+    @staticmethod
+    def forward(ctx, params, temperature, density):
+        n = temperature.shape[0]
+        a, p, dp = (torch.empty((n,), dtype=torch.float64, device=params.device) for _ in range(3))
+        with torch.cuda.device(params.device):
+            _lib.call("feos_dev_pure_state", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(density), n,
+                      _lib.ptr(a), _lib.ptr(p), _lib.ptr(dp), _stream())
+        ctx.save_for_backward(params, temperature, density)
+        return a, p, dp
+
+    @staticmethod
+    def backward(ctx, ga, gp, gdp):
+        params, temperature, density = ctx.saved_tensors
+        n = temperature.shape[0]
+        ga, gp, gdp = _grad_or_none(ga), _grad_or_none(gp), _grad_or_none(gdp)
+        need_p, need_t, need_r = ctx.needs_input_grad
+        grad_p = torch.empty_like(params) if need_p else None
+        grad_t = torch.empty_like(temperature) if need_t else None
+        grad_r = torch.empty_like(density) if need_r else None
+        if n:
+            with torch.cuda.device(params.device):
+                _lib.call("feos_dev_pure_state_bwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(density), n,
+                          _lib.ptr(ga), _lib.ptr(gp), _lib.ptr(gdp), _lib.ptr(grad_p), _lib.ptr(grad_t), _lib.ptr(grad_r),
+                          _stream())
+        return grad_p, grad_t, grad_r
+
+
 class PcSaftPure:
     """parameters [N, 8] = m, sigma, epsilon_k, mu, kappa_ab, epsilon_k_ab, na, nb (README.md:12)."""
 
@@ -346,17 +380,13 @@ class PcSaftPure:
         val, failed, _ = _PureRhoTp.apply(self._params, t, p)
         return self._back(failed.bool()), self._back(val)
 
-    # ---- state functions (values only for now) -----------------------
+    # ---- state functions at given (T, rho), differentiable ---------------
     def derivatives(self, temperature, density):
-        """(a, p/kT, d(p/kT)/drho) at (T, rho [1/A^3]) -- pcsaft_pure.py:180-182."""
+        """(a, p/kT, d(p/kT)/drho) at (T, rho [1/A^3]) -- pcsaft_pure.py:180-182; carries gradients with
+        respect to the parameters, T and rho like the reference's Dual3 evaluation under torch autograd."""
         t = _prep(temperature, self._dev)
         r = _prep(density, self._dev)
-        n = t.shape[0]
-        a, p, dp = (torch.empty((n,), dtype=torch.float64, device=self._dev) for _ in range(3))
-        with torch.cuda.device(self._dev):
-            _wait_chunks(self._params)
-            _lib.call("feos_dev_pure_state", _lib.ptr(self._params.detach()), _lib.ptr(t.detach()), _lib.ptr(r.detach()),
-                      n, _lib.ptr(a), _lib.ptr(p), _lib.ptr(dp), _stream())
+        a, p, dp = _PureState.apply(_wait_chunks(self._params), t, r)
         return self._back(a), self._back(p), self._back(dp)
 
     def helmholtz_energy(self, temperature, density):

@@ -95,6 +95,14 @@ int feos_dev_pure_rho_tp_bwd(const double* params, const double* temperature, co
 int feos_dev_pure_state(const double* params, const double* temperature, const double* density, int64_t n,
                         double* a, double* p, double* dp, void* stream);
 
+/* Gradient of  sum_i g_a[i] a[i] + g_p[i] p[i] + g_dp[i] dp[i]  of feos_dev_pure_state with respect to the
+ * parameters [n,8], T [n] and the density [n]; replaces torch autograd through the reference's Dual3
+ * evaluation (pcsaft_pure.py:180-182, feos_torch/dual.py).  Any g_* may be NULL (= 0, not all), any
+ * output may be NULL. */
+int feos_dev_pure_state_bwd(const double* params, const double* temperature, const double* density, int64_t n,
+                            const double* g_a, const double* g_p, const double* g_dp, double* grad_params,
+                            double* grad_temperature, double* grad_density, void* stream);
+
 /* Host-buffer entry points with the reference's native signatures.
  * PcSaft.vapor_pressure(parameters f64[n,8], temperature f64[n]) -> (f64[n_ok,4], bool[n])
  * (src/pcsaft.rs:19-26): rho_out must hold n*4 doubles, the first *n_ok rows are filled with
@@ -129,6 +137,14 @@ int feos_dev_mix_point_bwd(const double* params, const double* kij, const double
 /* a, p/kT, mu_i^res/kT [n,2], v_i [n,2] at (T, rho [n,2]): PcSaftMix.derivatives (pcsaft_mix.py:395-420). */
 int feos_dev_mix_state(const double* params, const double* kij, const double* temperature, const double* density,
                        int64_t n, double* a, double* p, double* mu, double* v, void* stream);
+
+/* Gradient of  sum_i g_a a + g_p p + g_mu . mu + g_v . v  of feos_dev_mix_state w.r.t. params [n,2,8], kij [n,2],
+ * T [n] and rho [n,2]; replaces torch autograd through the reference's hyper-dual evaluation
+ * (pcsaft_mix.py:395-420, feos_torch/dual_torch.py).  g_mu, g_v are [n,2]; NULL conventions as above. */
+int feos_dev_mix_state_bwd(const double* params, const double* kij, const double* temperature, const double* density,
+                           int64_t n, const double* g_a, const double* g_p, const double* g_mu, const double* g_v,
+                           double* grad_params, double* grad_kij, double* grad_temperature, double* grad_density,
+                           void* stream);
 
 /* PcSaft.bubble_point / dew_point(parameters f64[n,2,8], kij f64[n,2], temperature, molefracs, pressure)
  * -> (f64[n_ok,4], bool[n]) with host buffers (src/pcsaft.rs:44-79).  `pressure` (the reference's
@@ -184,6 +200,16 @@ int feos_dev_gc_state(const feos_gc_pair* pairs, int32_t n_pairs, const double* 
                       const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                       const double* temperature, const double* density, int64_t n, double* a, double* p, double* mu,
                       double* v, void* stream);
+
+/* Gradient of the outputs of feos_dev_gc_state (weights as feos_dev_mix_state_bwd); replaces torch autograd
+ * through gc_pcsaft.py:443-468.  grad_seg_params [n_seg,8] and grad_kab [n_rec] are ACCUMULATED into (zero them
+ * first); grad_phi [n,2], grad_temperature [n], grad_density [n,2] are written.  Any output may be NULL. */
+int feos_dev_gc_state_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
+                          const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
+                          const double* temperature, const double* density, int64_t n, const double* g_a,
+                          const double* g_p, const double* g_mu, const double* g_v, double* grad_seg_params,
+                          double* grad_kab, double* grad_phi, double* grad_temperature, double* grad_density,
+                          void* stream);
 
 /* GcPcSaft.bubble_point / dew_point with host buffers -> (f64[n_ok,4], bool[n]) (src/gc_pcsaft.rs:71-99). */
 int feos_host_gc_point(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,

@@ -248,6 +248,51 @@ def gc_golden(ref, table):
     return out
 
 
+def state_grad_golden(ref, table):
+    """Autograd gradients of the reference's public state functions `derivatives` (pcsaft_pure.py:180-182,
+    pcsaft_mix.py:395-420, gc_pcsaft.py:443-468) with respect to parameters, k_ij / k_ab, phi, T and the
+    densities, for a weighted sum of the outputs (weights stored)."""
+    out = {}
+    rng = np.random.default_rng(7)
+    # pure
+    P = torch.tensor(cases.PURE_PARAMS, dtype=F64)
+    n = P.shape[0]
+    T = torch.linspace(280.0, 330.0, n, dtype=F64)
+    rho = torch.linspace(0.0008, 0.012, n, dtype=F64)
+    w = torch.tensor(rng.uniform(0.5, 1.5, (n, 3)))
+    x, t, r = P.clone().requires_grad_(True), T.clone().requires_grad_(True), rho.clone().requires_grad_(True)
+    a, p, dp = ref.PcSaftPure(x).derivatives(t, r)
+    (w[:, 0] * a + w[:, 1] * p + w[:, 2] * dp).sum().backward()
+    out["pure"] = {"params": tl(P), "T": tl(T), "rho": tl(rho), "w": tl(w), "a": tl(a), "p": tl(p), "dp": tl(dp),
+                   "grad_params": tl(x.grad), "grad_T": tl(t.grad), "grad_rho": tl(r.grad)}
+    # binary mixtures (all association / dipole categories of tests/test_pcsaft_mix.py:17-36)
+    P = torch.tensor(cases.MIX_PARAMS, dtype=F64)
+    K = torch.tensor(cases.MIX_KIJ, dtype=F64)
+    n = P.shape[0]
+    T = torch.linspace(290.0, 320.0, n, dtype=F64)
+    rho = torch.stack([torch.linspace(0.0008, 0.004, n, dtype=F64), torch.linspace(0.003, 0.001, n, dtype=F64)], dim=1)
+    w = torch.tensor(rng.uniform(0.5, 1.5, (n, 6)))
+    x, k, t, r = (v.clone().requires_grad_(True) for v in (P, K, T, rho))
+    a, p, mu, v = ref.PcSaftMix(x, k).derivatives(t, r)
+    (w[:, 0] * a + w[:, 1] * p + (w[:, 2:4] * mu).sum(1) + (w[:, 4:6] * v).sum(1)).sum().backward()
+    out["mix"] = {"T": tl(T), "rho": tl(rho), "w": tl(w), "grad_params": tl(x.grad), "grad_kij": tl(k.grad),
+                  "grad_T": tl(t.grad), "grad_rho": tl(r.grad)}
+    # group contribution (tests/test_gc_pcsaft.py:17-44)
+    ident, par = seg_args(table, requires_grad=True)
+    n = len(cases.GC_SEGMENTS)
+    kab = [torch.tensor(kk[2], dtype=F64, requires_grad=True) for kk in cases.GC_KAB]
+    phi = torch.tensor([cases.GC_PHI] * n, dtype=F64, requires_grad=True)
+    T = torch.linspace(290.0, 320.0, n, dtype=F64).requires_grad_(True)
+    rho = torch.stack([torch.linspace(0.0008, 0.002, n, dtype=F64), torch.linspace(0.002, 0.001, n, dtype=F64)], dim=1).requires_grad_(True)
+    w = torch.tensor(rng.uniform(0.5, 1.5, (n, 6)))
+    model = ref.GcPcSaftMix(ident, par, cases.GC_SEGMENTS, cases.GC_BONDS, [(a_, b_, kv) for (a_, b_, _), kv in zip(cases.GC_KAB, kab)], phi)
+    a, p, mu, v = model.derivatives(T, rho)
+    (w[:, 0] * a + w[:, 1] * p + (w[:, 2:4] * mu).sum(1) + (w[:, 4:6] * v).sum(1)).sum().backward()
+    out["gc"] = {"T": tl(T), "rho": tl(rho), "w": tl(w), "grad_seg": [tl(c.grad) for c in par], "grad_kab": [kk.grad.item() for kk in kab],
+                 "grad_phi": tl(phi.grad), "grad_T": tl(T.grad), "grad_rho": tl(rho.grad)}
+    return out
+
+
 def main():
     if not refshim.reference_available():
         raise SystemExit("reference sources not found; golden vectors can only be made in the build container")
@@ -255,7 +300,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     table = load_segments()
     which = sys.argv[1:] or ["pure", "mix", "gc"]
-    makers = {"pure": lambda: pure_golden(ref), "mix": lambda: mix_golden(ref), "gc": lambda: gc_golden(ref, table)}
+    makers = {"pure": lambda: pure_golden(ref), "mix": lambda: mix_golden(ref), "gc": lambda: gc_golden(ref, table),
+              "state_grad": lambda: state_grad_golden(ref, table)}
     for name in which:
         data = makers[name]()
         with open(os.path.join(OUT, f"{name}.json"), "w") as f:

@@ -32,3 +32,9 @@ def golden_mix():
 @pytest.fixture(scope="session")
 def golden_gc():
     return load_golden("gc")
+
+
+@pytest.fixture(scope="session")
+def golden_state():
+    """Gradients of the reference's `derivatives` (made by oracle/make_golden.py state_grad)."""
+    return load_golden("state_grad")

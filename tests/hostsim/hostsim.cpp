@@ -391,3 +391,64 @@ void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const d
   }
 }
 }
+
+// ---------------------------------------------------------------------------------------------
+// gradients of the public state functions (state_grad.cuh)
+// ---------------------------------------------------------------------------------------------
+#include "../../feos_torch_b200/csrc/state_grad.cuh"
+
+extern "C" {
+
+// grad [n,10]: d(ga a + gp p + gdp dp)/d(8 parameters, T, rho)
+void sim_pure_state_bwd(const double* params, const double* T, const double* rho, int64_t n, const double* ga,
+                        const double* gp, const double* gdp, double* grad) {
+  for (int64_t i = 0; i < n; ++i)
+    for (int f = 0; f < 10; f += 2) {
+      double o[2];
+      pure_state_grad_pass<2>(params + 8 * i, T[i], rho[i], f, ga[i], gp[i], gdp[i], o);
+      grad[10 * i + f] = o[0];
+      grad[10 * i + f + 1] = o[1];
+    }
+}
+
+// gw [n,6] = weights of (a, p, mu0, mu1, v0, v1); grad [n,21]
+void sim_mix_state_bwd(const double* params, const double* kij, const double* T, const double* rho, int64_t n,
+                       const double* gw, double* grad) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16], kk[2] = {kij[2 * i], kij[2 * i + 1]};
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    for (int f = 0; f < 21; f += 3) {
+      int ids[3] = {f, f + 1, f + 2};
+      double o[3];
+      mix_state_grad_pass<3>(prm, kk, T[i], rho[2 * i], rho[2 * i + 1], ids, gw + 6 * i, o);
+      for (int k = 0; k < 3; ++k) grad[21 * i + f + k] = o[k];
+    }
+  }
+}
+
+// grad_seg [n_seg,8], grad_kab [n_rec] accumulate; grad_phi [n,2], grad_t [n], grad_rho [n,2]
+void sim_gc_state_bwd(const GcPair* pairs, const double* seg, int n_seg, const double* kab, int n_rec,
+                      const int32_t* idx, const double* phi, const double* T, const double* rho, int64_t n,
+                      const double* gw, double* grad_seg, double* grad_kab, double* grad_phi, double* grad_t,
+                      double* grad_rho) {
+  for (int64_t i = 0; i < n; ++i) {
+    GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    const GcPair& pr = *s.pair;
+    int n_all = 8 * pr.nseg + n_rec + 5;
+    for (int f = 0; f < n_all; f += 3) {
+      int ids[3];
+      for (int k = 0; k < 3; ++k) ids[k] = (f + k < n_all) ? f + k : -1;
+      double o[3];
+      gc_state_grad_pass<3>(s, n_rec, rho[2 * i], rho[2 * i + 1], ids, gw + 6 * i, o);
+      for (int k = 0; k < 3 && ids[k] >= 0; ++k) {
+        int d = ids[k];
+        if (d < 8 * pr.nseg) grad_seg[8 * pr.seg[d >> 3] + (d & 7)] += o[k];
+        else if (d < 8 * pr.nseg + n_rec) grad_kab[d - 8 * pr.nseg] += o[k];
+        else if (d < 8 * pr.nseg + n_rec + 2) grad_phi[2 * i + d - 8 * pr.nseg - n_rec] = o[k];
+        else if (d == 8 * pr.nseg + n_rec + 2) grad_t[i] = o[k];
+        else grad_rho[2 * i + d - 8 * pr.nseg - n_rec - 3] = o[k];
+      }
+    }
+  }
+}
+}

@@ -150,3 +150,29 @@ def gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g, generic=False):
                            _p(T), _p(rho), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(g), _p(gs), _p(gk), _p(gp), _p(gt),
                            ctypes.c_int(int(generic)))
     return gs, gk, gp, gt
+
+
+def pure_state_bwd(params, T, rho, ga, gp, gdp):
+    params, T, rho, ga, gp, gdp = c64(params), c64(T), c64(rho), c64(ga), c64(gp), c64(gdp)
+    n = T.shape[0]
+    grad = np.zeros((n, 10))
+    lib().sim_pure_state_bwd(_p(params), _p(T), _p(rho), ctypes.c_int64(n), _p(ga), _p(gp), _p(gdp), _p(grad))
+    return grad
+
+
+def mix_state_bwd(params, kij, T, rho, gw):
+    params, kij, T, rho, gw = c64(params), c64(kij), c64(T), c64(rho), c64(gw)
+    n = T.shape[0]
+    grad = np.zeros((n, 21))
+    lib().sim_mix_state_bwd(_p(params), _p(kij), _p(T), _p(rho), ctypes.c_int64(n), _p(gw), _p(grad))
+    return grad
+
+
+def gc_state_bwd(pairs, seg, kab, idx, phi, T, rho, gw):
+    pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
+    rho, gw = c64(rho), c64(gw)
+    n = T.shape[0]
+    gs = np.zeros_like(seg); gk = np.zeros_like(kab); gp = np.zeros((n, 2)); gt = np.zeros(n); gr = np.zeros((n, 2))
+    lib().sim_gc_state_bwd(_p(pairs), _p(seg), ctypes.c_int(seg.shape[0]), _p(kab), ctypes.c_int(kab.shape[0]), _p(idx), _p(phi),
+                           _p(T), _p(rho), ctypes.c_int64(n), _p(gw), _p(gs), _p(gk), _p(gp), _p(gt), _p(gr))
+    return gs, gk, gp, gt, gr
