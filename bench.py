@@ -83,7 +83,7 @@ def parse_clocks(path):
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """Reference arm: the reference's CPU implementation of the path (oracle port: CPU solver restating
     feos + the reference's Newton-step gradient stage under torch autograd), all host threads."""
     if rank != 0:
@@ -122,7 +122,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 class C2:
@@ -405,7 +405,24 @@ class C5:
 WORKLOADS = {"c2": C2, "c3": C3, "c4": C4, "c5": C5}
 
 
+def _quiet_stdout():
+    """Libraries (NCCL with NCCL_DEBUG=VERSION/INFO) print to fd 1; the contract is ONE JSON line on stdout.
+    Route fd 1 to stderr for the run and return a writer onto the real stdout for that line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out = _quiet_stdout()
+    try:
+        _main(out)
+    finally:
+        out.flush()
+
+
+def _main(out):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -423,7 +440,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch.distributed as dist
@@ -533,7 +550,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
