@@ -1,0 +1,205 @@
+// Closed-form value, gradient and Hessian in the partial densities of the BASE part (hard sphere + hard
+// chain + dispersion) of the binary-mixture Helmholtz energy density -- the evaluation the bubble / dew
+// solvers call ~10 times per state.
+//
+// The generic path evaluates mix_helmholtz in H2<double> arithmetic (value, 2 first, 3 second derivatives
+// carried through every operation: ~1700 FP64 instructions, 37 KB of straight-line code).  Here the
+// structure of the model is used instead: all density dependence enters through
+//   zeta_0..zeta_3 (linear in rho), the bond weights B_b (linear), mbar (rational), Q1, Q2 (quadratic),
+// and the only non-linear variables are (zeta_2, eta = zeta_3) for the hard-sphere / hard-chain terms and
+// (eta, mbar) for dispersion.  The partial derivatives with respect to those few variables are written
+// out by hand and contracted with the (constant) gradients of the intermediates.  Same formulas as
+// mix_helmholtz (pcsaft_mix.py:56-106, gc_pcsaft.py:149-194), checked against it to round-off in
+// tests/test_hostsim_mix.py / test_hostsim_gc.py.
+#pragma once
+#include "pcsaft_mix.cuh"
+
+namespace feos {
+
+struct BaseH2 {
+  double a, g0, g1, h00, h01, h11;
+};
+
+// value, first and second derivative of a degree-6 polynomial
+FD void horner7_2(const double (&k)[7], double x, double& v, double& d1, double& d2) {
+  v = k[6];
+  d1 = 0.0;
+  d2 = 0.0;
+#pragma unroll
+  for (int n = 5; n >= 0; --n) {
+    d2 = d2 * x + d1;
+    d1 = d1 * x + v;
+    v = v * x + k[n];
+  }
+  d2 *= 2.0;
+}
+
+template <int NB, bool GC>
+FD BaseH2 mix_base_eval(const MixCoef<double, NB, GC>& c, double r0, double r1) {
+  const double z00 = c.z[0][0], z01 = c.z[0][1], z10 = c.z[1][0], z11 = c.z[1][1];
+  const double z20 = c.z[2][0], z21 = c.z[2][1], z30 = c.z[3][0], z31 = c.z[3][1];
+  const double zt0 = r0 * z00 + r1 * z01, zt1 = r0 * z10 + r1 * z11, zt2 = r0 * z20 + r1 * z21;
+  const double eta = r0 * z30 + r1 * z31;
+  const double om = 1.0 - eta, omi = 1.0 / om, omi2 = omi * omi, omi3 = omi2 * omi, omi4 = omi2 * omi2;
+  const double ie = 1.0 / eta, ie2 = ie * ie, ie3 = ie2 * ie;
+  const double L = log(om);
+  const double t2 = zt2 * zt2, t3 = t2 * zt2;
+  const double cs = 6.0 / kPi;
+
+  // ---- hard sphere: G = 3 z1 z2 / om + z2^3 / (eta om^2) + (z2^3 / eta^2 - z0) L --------------------
+  const double u = 2.0 * ie * omi3 - ie2 * omi2;  // d/d eta of 1 / (eta om^2)
+  double a = cs * (3.0 * zt1 * zt2 * omi + t3 * ie * omi2 + (t3 * ie2 - zt0) * L);
+  double A0 = -cs * L;
+  double A1 = cs * 3.0 * zt2 * omi;
+  double A2 = cs * 3.0 * (zt1 * omi + t2 * ie * omi2 + t2 * ie2 * L);
+  double A3 = cs * (3.0 * zt1 * zt2 * omi2 + t3 * u - 2.0 * t3 * ie3 * L - (t3 * ie2 - zt0) * omi);
+  const double H03 = cs * omi;
+  const double H12 = cs * 3.0 * omi;
+  const double H13 = cs * 3.0 * zt2 * omi2;
+  double H22 = cs * 6.0 * zt2 * (ie * omi2 + ie2 * L);
+  double H23 = cs * 3.0 * (zt1 * omi2 + t2 * u - 2.0 * t2 * ie3 * L - t2 * ie2 * omi);
+  double H33 = cs * (6.0 * zt1 * zt2 * omi3 + t3 * (6.0 * ie * omi4 - 4.0 * ie2 * omi3 + 2.0 * ie3 * omi2) +
+                     6.0 * t3 * ie2 * ie2 * L + 4.0 * t3 * ie3 * omi - (t3 * ie2 - zt0) * omi2);
+  double g0 = 0.0, g1 = 0.0, h00 = 0.0, h01 = 0.0, h11 = 0.0;  // parts that do not go through zeta_k
+
+  // ---- hard chain: - sum_b B_b ln g_b,  g = 1/om + 3 x + 2 x^2 om,  x = zeta_2 cd / om^2 -----------------
+  {
+    const int nb = (NB == 2) ? 2 : c.nbond;
+    for (int b = 0; b < nb; ++b) {
+      const double cd = c.cd[b], bn0 = c.bn[b][0], bn1 = c.bn[b][1];
+      const double B = r0 * bn0 + r1 * bn1;
+      const double x2 = omi2 * cd;         // dx/dzeta2
+      const double x = zt2 * x2;
+      const double x3 = 2.0 * x * omi;     // dx/deta
+      const double x23 = 2.0 * x2 * omi;
+      const double x33 = 3.0 * x3 * omi;
+      const double gx = 3.0 + 4.0 * x * om;  // dg/dx at fixed om
+      const double gg = omi + 3.0 * x + 2.0 * x * x * om;
+      const double gi = 1.0 / gg;
+      const double gd2 = gx * x2;
+      const double gd3 = omi2 + gx * x3 - 2.0 * x * x;
+      const double gxe = 4.0 * (x3 * om - x);  // d gx / d eta
+      const double gd22 = 4.0 * om * x2 * x2;
+      const double gd23 = gxe * x2 + gx * x23;
+      const double gd33 = 2.0 * omi3 + gxe * x3 + gx * x33 - 4.0 * x * x3;
+      const double f = log(gg);
+      const double f2 = gd2 * gi, f3 = gd3 * gi;
+      const double f22 = gd22 * gi - f2 * f2, f23 = gd23 * gi - f2 * f3, f33 = gd33 * gi - f3 * f3;
+      a -= B * f;
+      A2 -= B * f2;
+      A3 -= B * f3;
+      H22 -= B * f22;
+      H23 -= B * f23;
+      H33 -= B * f33;
+      g0 -= bn0 * f;
+      g1 -= bn1 * f;
+      const double t0 = f2 * z20 + f3 * z30, t1 = f2 * z21 + f3 * z31;
+      h00 -= 2.0 * bn0 * t0;
+      h01 -= bn0 * t1 + bn1 * t0;
+      h11 -= 2.0 * bn1 * t1;
+    }
+  }
+
+  // ---- dispersion: -pi [2 Q1 I1(eta, mbar) + Q2 K(eta, mbar)],  K = mbar C1 I2 ---------------------------
+  {
+    const double rti = 1.0 / (r0 + r1);
+    const double mb = (r0 * c.m[0] + r1 * c.m[1]) * rti;
+    const double m0 = (c.m[0] - mb) * rti, m1 = (c.m[1] - mb) * rti;  // d mbar / d rho_i
+    const double m00 = -2.0 * m0 * rti, m01 = -(m0 + m1) * rti, m11 = -2.0 * m1 * rti;
+    const double Q1 = r0 * r0 * c.q1[0] + 2.0 * r0 * r1 * c.q1[1] + r1 * r1 * c.q1[2];
+    const double Q2 = r0 * r0 * c.q2[0] + 2.0 * r0 * r1 * c.q2[1] + r1 * r1 * c.q2[2];
+    const double Q1_0 = 2.0 * (c.q1[0] * r0 + c.q1[1] * r1), Q1_1 = 2.0 * (c.q1[1] * r0 + c.q1[2] * r1);
+    const double Q2_0 = 2.0 * (c.q2[0] * r0 + c.q2[1] * r1), Q2_1 = 2.0 * (c.q2[1] * r0 + c.q2[2] * r1);
+    const double mi = 1.0 / mb, mi2 = mi * mi, mi3 = mi2 * mi;
+    const double w1 = 1.0 - mi, w2 = w1 * (1.0 - 2.0 * mi);
+    const double w1m = mi2, w1mm = -2.0 * mi3;
+    const double w2m = mi2 * (3.0 - 4.0 * mi), w2mm = mi3 * (12.0 * mi - 6.0);
+    double p0, p0e, p0ee, p1, p1e, p1ee, p2, p2e, p2ee;
+    horner7_2(cA0, eta, p0, p0e, p0ee);
+    horner7_2(cA1, eta, p1, p1e, p1ee);
+    horner7_2(cA2, eta, p2, p2e, p2ee);
+    const double I1 = p0 + w1 * p1 + w2 * p2;
+    const double I1e = p0e + w1 * p1e + w2 * p2e, I1ee = p0ee + w1 * p1ee + w2 * p2ee;
+    const double I1m = w1m * p1 + w2m * p2, I1em = w1m * p1e + w2m * p2e, I1mm = w1mm * p1 + w2mm * p2;
+    horner7_2(cB0, eta, p0, p0e, p0ee);
+    horner7_2(cB1, eta, p1, p1e, p1ee);
+    horner7_2(cB2, eta, p2, p2e, p2ee);
+    const double I2 = p0 + w1 * p1 + w2 * p2;
+    const double I2e = p0e + w1 * p1e + w2 * p2e, I2ee = p0ee + w1 * p1ee + w2 * p2ee;
+    const double I2m = w1m * p1 + w2m * p2, I2em = w1m * p1e + w2m * p2e, I2mm = w1mm * p1 + w2mm * p2;
+    // C1 = 1 / D,  D = 1 + mbar X(eta) + (1 - mbar) Y(eta)
+    const double e2 = eta * eta, e3 = e2 * eta;
+    const double xn = 8.0 * eta - 2.0 * e2, xn1 = 8.0 - 4.0 * eta;
+    const double omi5 = omi4 * omi;
+    const double X = xn * omi4;
+    const double Xe = xn1 * omi4 + 4.0 * xn * omi5;
+    const double Xee = -4.0 * omi4 + 8.0 * xn1 * omi5 + 20.0 * xn * omi5 * omi;
+    const double tmi = 1.0 / (2.0 - eta);
+    const double yn = 20.0 * eta - 27.0 * e2 + 12.0 * e3 - 2.0 * e2 * e2;
+    const double yn1 = 20.0 - 54.0 * eta + 36.0 * e2 - 8.0 * e3, yn2 = -54.0 + 72.0 * eta - 24.0 * e2;
+    const double s = omi2 * tmi * tmi, so = omi + tmi;
+    const double s1 = 2.0 * s * so;
+    const double s2 = 2.0 * s1 * so + 2.0 * s * (omi2 + tmi * tmi);
+    const double Y = yn * s, Ye = yn1 * s + yn * s1, Yee = yn2 * s + 2.0 * yn1 * s1 + yn * s2;
+    const double D = 1.0 + mb * X + (1.0 - mb) * Y;
+    const double De = mb * Xe + (1.0 - mb) * Ye, Dm = X - Y, Dee = mb * Xee + (1.0 - mb) * Yee, Dem = Xe - Ye;
+    const double C = 1.0 / D, C2 = C * C, C3 = C2 * C;
+    const double Ce = -C2 * De, Cm = -C2 * Dm;
+    const double Cee = 2.0 * C3 * De * De - C2 * Dee, Cem = 2.0 * C3 * De * Dm - C2 * Dem, Cmm = 2.0 * C3 * Dm * Dm;
+    // J = C1 I2 (bivariate product), K = mbar J
+    const double J = C * I2;
+    const double Je = Ce * I2 + C * I2e, Jm = Cm * I2 + C * I2m;
+    const double Jee = Cee * I2 + 2.0 * Ce * I2e + C * I2ee;
+    const double Jem = Cem * I2 + Ce * I2m + Cm * I2e + C * I2em;
+    const double Jmm = Cmm * I2 + 2.0 * Cm * I2m + C * I2mm;
+    const double K = mb * J, Ke = mb * Je, Km = J + mb * Jm;
+    const double Kee = mb * Jee, Kem = Je + mb * Jem, Kmm = 2.0 * Jm + mb * Jmm;
+    const double np = -kPi;
+    a += np * (2.0 * Q1 * I1 + Q2 * K);
+    A3 += np * (2.0 * Q1 * I1e + Q2 * Ke);
+    H33 += np * (2.0 * Q1 * I1ee + Q2 * Kee);
+    const double Sm = np * (2.0 * Q1 * I1m + Q2 * Km);
+    const double Sem = np * (2.0 * Q1 * I1em + Q2 * Kem);
+    const double Smm = np * (2.0 * Q1 * I1mm + Q2 * Kmm);
+    g0 += Sm * m0 + np * (2.0 * Q1_0 * I1 + Q2_0 * K);
+    g1 += Sm * m1 + np * (2.0 * Q1_1 * I1 + Q2_1 * K);
+    // e1_j = d I1 / d rho_j, ek_j = d K / d rho_j
+    const double e1_0 = I1e * z30 + I1m * m0, e1_1 = I1e * z31 + I1m * m1;
+    const double ek_0 = Ke * z30 + Km * m0, ek_1 = Ke * z31 + Km * m1;
+    h00 += Sem * 2.0 * z30 * m0 + Smm * m0 * m0 + Sm * m00 +
+           np * (4.0 * Q1_0 * e1_0 + 2.0 * Q2_0 * ek_0 + 4.0 * c.q1[0] * I1 + 2.0 * c.q2[0] * K);
+    h01 += Sem * (z30 * m1 + m0 * z31) + Smm * m0 * m1 + Sm * m01 +
+           np * (2.0 * (Q1_0 * e1_1 + Q1_1 * e1_0) + (Q2_0 * ek_1 + Q2_1 * ek_0) + 4.0 * c.q1[1] * I1 + 2.0 * c.q2[1] * K);
+    h11 += Sem * 2.0 * z31 * m1 + Smm * m1 * m1 + Sm * m11 +
+           np * (4.0 * Q1_1 * e1_1 + 2.0 * Q2_1 * ek_1 + 4.0 * c.q1[2] * I1 + 2.0 * c.q2[2] * K);
+  }
+
+  // ---- contraction with the gradients of zeta_k ----------------------------------------------------------
+  BaseH2 o;
+  o.a = a;
+  o.g0 = g0 + A0 * z00 + A1 * z10 + A2 * z20 + A3 * z30;
+  o.g1 = g1 + A0 * z01 + A1 * z11 + A2 * z21 + A3 * z31;
+  o.h00 = h00 + 2.0 * (H03 * z00 * z30 + H12 * z10 * z20 + H13 * z10 * z30 + H23 * z20 * z30) + H22 * z20 * z20 + H33 * z30 * z30;
+  o.h01 = h01 + H03 * (z00 * z31 + z30 * z01) + H12 * (z10 * z21 + z20 * z11) + H13 * (z10 * z31 + z30 * z11) +
+          H23 * (z20 * z31 + z30 * z21) + H22 * z20 * z21 + H33 * z30 * z31;
+  o.h11 = h11 + 2.0 * (H03 * z01 * z31 + H12 * z11 * z21 + H13 * z11 * z31 + H23 * z21 * z31) + H22 * z21 * z21 + H33 * z31 * z31;
+  return o;
+}
+
+// The evaluation the solvers and state kernels use: closed-form base part; the dipole and association
+// terms (only where present) in hyper-dual arithmetic on top.
+template <int NB, bool GC>
+FD MixEval mix_eval(const MixCoef<double, NB, GC>& c, double rho0, double rho1) {
+  BaseH2 b = mix_base_eval<NB, GC>(c, rho0, rho1);
+  H2<double> a;
+  a.re = b.a; a.g0 = b.g0; a.g1 = b.g1; a.h00 = b.h00; a.h01 = b.h01; a.h11 = b.h11;
+  if (c.dipolar || c.cat != kAssocNone) {
+    H2<double> r0(rho0), r1(rho1);
+    r0.g0 = 1.0;
+    r1.g1 = 1.0;
+    a = a + mix_helmholtz<double, H2<double>, NB, GC, 6>(c, r0, r1);
+  }
+  return mix_eval_from(a, rho0, rho1);
+}
+
+}  // namespace feos

@@ -16,7 +16,7 @@
 // Model must provide:  Eval eval(rho0, rho1) (a, mu[2], h00, h01, h11, p, dp[2], v[2]) and
 //                      double max_density(x0) (total density at packing fraction 0.5).
 #pragma once
-#include "pcsaft_mix.cuh"
+#include "mix_eval_fast.cuh"
 #include "pure_solver.cuh"
 
 namespace feos {

@@ -491,12 +491,18 @@ struct MixEval {
   double v[2];                     // partial molar volumes (reduced)
 };
 
+FD MixEval mix_eval_from(const H2<double>& a, double rho0, double rho1);
+
+// every term in hyper-dual arithmetic (the reference's way; mix_eval in mix_eval_fast.cuh is checked against it)
 template <int NB, bool GC>
-FD MixEval mix_eval(const MixCoef<double, NB, GC>& c, double rho0, double rho1) {
+FD MixEval mix_eval_generic(const MixCoef<double, NB, GC>& c, double rho0, double rho1) {
   H2<double> r0(rho0), r1(rho1);
   r0.g0 = 1.0;
   r1.g1 = 1.0;
-  H2<double> a = mix_helmholtz<double, H2<double>, NB, GC>(c, r0, r1);
+  return mix_eval_from(mix_helmholtz<double, H2<double>, NB, GC>(c, r0, r1), rho0, rho1);
+}
+
+FD MixEval mix_eval_from(const H2<double>& a, double rho0, double rho1) {
   MixEval e;
   e.a = a.re;
   e.mu[0] = a.g0;

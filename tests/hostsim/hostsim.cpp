@@ -452,3 +452,45 @@ void sim_gc_state_bwd(const GcPair* pairs, const double* seg, int n_seg, const d
   }
 }
 }
+
+// ---------------------------------------------------------------------------------------------
+// closed-form base evaluation (mix_eval_fast.cuh) against the generic H2 evaluation, PARTS = 1
+// ---------------------------------------------------------------------------------------------
+
+extern "C" {
+
+// out [n,12]: (a, g0, g1, h00, h01, h11) fast, then generic
+void sim_mix_base_eval(const double* params, const double* kij, const double* T, const double* rho, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16], kk[2] = {kij[2 * i], kij[2 * i + 1]};
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    MixCoef<double> c;
+    mix_coef<double>(c, prm, kk, T[i], false);
+    BaseH2 f = mix_base_eval<2, false>(c, rho[2 * i], rho[2 * i + 1]);
+    H2<double> r0(rho[2 * i]), r1(rho[2 * i + 1]);
+    r0.g0 = 1.0;
+    r1.g1 = 1.0;
+    H2<double> g = mix_helmholtz<double, H2<double>, 2, false, 1>(c, r0, r1);
+    double* o = out + 12 * i;
+    o[0] = f.a; o[1] = f.g0; o[2] = f.g1; o[3] = f.h00; o[4] = f.h01; o[5] = f.h11;
+    o[6] = g.re; o[7] = g.g0; o[8] = g.g1; o[9] = g.h00; o[10] = g.h01; o[11] = g.h11;
+  }
+}
+
+void sim_gc_base_eval(const GcPair* pairs, const double* seg, const double* kab, const int32_t* idx, const double* phi,
+                      const double* T, const double* rho, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    GcBinary b;
+    gc_binary_init(b, s);
+    BaseH2 f = mix_base_eval<kGcMaxBond, true>(b.c, rho[2 * i], rho[2 * i + 1]);
+    H2<double> r0(rho[2 * i]), r1(rho[2 * i + 1]);
+    r0.g0 = 1.0;
+    r1.g1 = 1.0;
+    H2<double> g = mix_helmholtz<double, H2<double>, kGcMaxBond, true, 1>(b.c, r0, r1);
+    double* o = out + 12 * i;
+    o[0] = f.a; o[1] = f.g0; o[2] = f.g1; o[3] = f.h00; o[4] = f.h01; o[5] = f.h11;
+    o[6] = g.re; o[7] = g.g0; o[8] = g.g1; o[9] = g.h00; o[10] = g.h01; o[11] = g.h11;
+  }
+}
+}

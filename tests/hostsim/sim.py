@@ -176,3 +176,20 @@ def gc_state_bwd(pairs, seg, kab, idx, phi, T, rho, gw):
     lib().sim_gc_state_bwd(_p(pairs), _p(seg), ctypes.c_int(seg.shape[0]), _p(kab), ctypes.c_int(kab.shape[0]), _p(idx), _p(phi),
                            _p(T), _p(rho), ctypes.c_int64(n), _p(gw), _p(gs), _p(gk), _p(gp), _p(gt), _p(gr))
     return gs, gk, gp, gt, gr
+
+
+def mix_base_eval(params, kij, T, rho):
+    params, kij, T, rho = c64(params), c64(kij), c64(T), c64(rho)
+    n = T.shape[0]
+    out = np.zeros((n, 12))
+    lib().sim_mix_base_eval(_p(params), _p(kij), _p(T), _p(rho), ctypes.c_int64(n), _p(out))
+    return out[:, :6], out[:, 6:]
+
+
+def gc_base_eval(pairs, seg, kab, idx, phi, T, rho):
+    pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
+    rho = c64(rho)
+    n = T.shape[0]
+    out = np.zeros((n, 12))
+    lib().sim_gc_base_eval(_p(pairs), _p(seg), _p(kab), _p(idx), _p(phi), _p(T), _p(rho), ctypes.c_int64(n), _p(out))
+    return out[:, :6], out[:, 6:]

@@ -121,3 +121,19 @@ def test_base_adjoint_equals_dual_passes(golden_gc):
         b = sim.gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g)
         for x, y in zip(a, b):
             assert np.abs(x - y).max() <= 1e-10 * np.abs(x).max()
+
+
+def test_closed_form_base_eval_equals_hyper_dual(golden_gc):
+    ident, seg = table(golden_gc)
+    n = len(cases.GC_SEGMENTS)
+    pairs, idx = build_pair_table(ident, cases.GC_SEGMENTS, cases.GC_BONDS, cases.GC_KAB)
+    kab = np.array([k[2] for k in cases.GC_KAB])
+    rng = np.random.default_rng(3)
+    reps = 50
+    idx = np.tile(idx, reps)
+    T = rng.uniform(200, 400, n * reps)
+    rho = np.exp(rng.uniform(np.log(1e-8), np.log(3e-3), (n * reps, 2)))
+    phi = np.array([cases.GC_PHI] * (n * reps))
+    fast, generic = sim.gc_base_eval(pairs, seg, kab, idx, phi, T, rho)
+    err = np.abs(fast - generic) / np.maximum(np.abs(generic), 1e-300)
+    assert err.max() < 1e-10 and np.median(err) < 1e-14

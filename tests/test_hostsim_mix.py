@@ -94,3 +94,26 @@ def test_mix_c4_grid_converges():
         assert np.abs(muV + np.log(rho[:, 0:2]) - muL - np.log(rho[:, 2:4])).max() < 1e-9
         comp = rho[:, 2] / rho[:, 2:4].sum(axis=1) if bubble else rho[:, 0] / rho[:, 0:2].sum(axis=1)
         assert np.abs(comp - z).max() < 1e-12
+
+
+def test_closed_form_base_eval_equals_hyper_dual():
+    """mix_base_eval (hand-derived value / gradient / Hessian of hard sphere + hard chain + dispersion) against
+    the same terms in generic H2 arithmetic, from ideal-gas to liquid packing fractions."""
+    rng = np.random.default_rng(0)
+    n = 4000
+    P = np.zeros((n, 2, 8))
+    P[:, :, 0] = rng.uniform(1, 4, (n, 2))
+    P[:, :, 1] = rng.uniform(3, 4, (n, 2))
+    P[:, :, 2] = rng.uniform(150, 350, (n, 2))
+    K = np.zeros((n, 2))
+    K[:, 0] = rng.uniform(-0.1, 0.1, n)
+    T = rng.uniform(150, 400, n)
+    eta = np.exp(rng.uniform(np.log(1e-7), np.log(0.5), n))
+    x = rng.uniform(0.01, 0.99, n)
+    d = P[:, :, 1] * (1 - 0.12 * np.exp(-3 * P[:, :, 2] / T[:, None]))
+    rt = eta / (np.pi / 6 * (x * P[:, 0, 0] * d[:, 0] ** 3 + (1 - x) * P[:, 1, 0] * d[:, 1] ** 3))
+    rho = np.stack([rt * x, rt * (1 - x)], 1)
+    fast, generic = sim.mix_base_eval(P.reshape(n, 16), K, T, rho)
+    err = np.abs(fast - generic) / np.maximum(np.abs(generic), 1e-300)
+    # both share the reference's cancellation at low density (zeta_2^3 / eta terms of the hard-sphere formula)
+    assert err.max() < 1e-10 and np.median(err) < 1e-14
