@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfeos_b200.so")
+# FEOS_B200_LIB: alternative build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("FEOS_B200_LIB") or os.path.join(_HERE, "libfeos_b200.so")
 
 _vp = ctypes.c_void_p
 _i64 = ctypes.c_int64

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace feos {
 
@@ -39,5 +40,15 @@ int scratch_alloc(void** p, size_t bytes, cudaStream_t s);  // cudaMallocAsync f
   } while (0)
 
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+// bubble / dew forward kernels: 0 = one thread per state (default), 1 = persistent work queue
+// (FEOS_B200_POINT_KERNEL=queue).  Measured on B200, 1 M C4 states (profiles/README.md): the queue keeps 32 of
+// 32 lanes busy in the evaluation (loop: 16) and matches the loop kernel for bubble points (2.18 vs 2.14 ms),
+// but for dew points the three bookkeeping phases of the state machine plus the evaluation no longer fit the
+// instruction cache (53 % of the stall samples are "no instruction") and it is 2.5x slower (5.79 vs 2.29 ms).
+inline int point_kernel_variant() {
+  const char* e = getenv("FEOS_B200_POINT_KERNEL");
+  return (e && e[0] == 'q') ? 1 : 0;
+}
 
 }  // namespace feos

@@ -9,12 +9,14 @@
 //                            memory per block and added to the global accumulators with one atomic per
 //                            entry and block;
 //   gc_state_kernel          a, p, mu_i, v_i at given (T, rho_1, rho_2)  (GcPcSaftMix.derivatives).
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 
 #include "../../include/feos_b200.h"
 #include "common.h"
 #include "gc_pcsaft.cuh"
+#include "point_queue.cuh"
 
 static_assert(sizeof(feos_gc_pair) == sizeof(feos::GcPair), "feos_gc_pair layout");
 static_assert(FEOS_GC_MAX_SEG == feos::kGcMaxSeg && FEOS_GC_MAX_BOND == feos::kGcMaxBond, "feos_gc_pair limits");
@@ -79,7 +81,10 @@ __device__ __forceinline__ void store_gc_point(int64_t i, int rc, bool bubble, d
   failed[i] = (rc == kStatusOk) ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(kGcFwdBlock)
+#ifndef FEOS_GC_FWD_MINB
+#define FEOS_GC_FWD_MINB 3
+#endif
+__global__ void __launch_bounds__(kGcFwdBlock, FEOS_GC_FWD_MINB)
 gc_point_fwd_kernel(GcArgs g, const double* __restrict__ molefrac, int64_t n, int bubble, double* __restrict__ rho,
                     double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
                     int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count) {
@@ -100,6 +105,34 @@ gc_point_fwd_kernel(GcArgs g, const double* __restrict__ molefrac, int64_t n, in
     return;
   }
   store_gc_point(i, rc, bubble != 0, z0, src.T_, st, se, es, ei, rho, value, failed);
+}
+
+// Persistent work-queue variant (point_queue.cuh)
+struct GcQueueSource {
+  GcArgs g;
+  const double* molefrac;
+  double* rho;
+  double* value;
+  uint8_t* failed;
+  __device__ __forceinline__ void dummy(GcBinary& b) const { gc_binary_init(b, make_source(g, 0)); }
+  __device__ __forceinline__ bool load(int i, GcBinary& b, double& z0, double& T) const {
+    GcSource src = make_source(g, i);
+    gc_binary_init(b, src);
+    T = src.T_;
+    z0 = molefrac[i];
+    return z0 > 0.0 && z0 < 1.0;
+  }
+  __device__ __forceinline__ void store(int i, int rc, bool bubble, double z0, double T, const PointMachine<GcBinary>& m) const {
+    store_gc_point(i, rc, bubble, z0, T, m.st, m.st_eval, m.es, m.ei, rho, value, failed);
+  }
+};
+
+__global__ void __launch_bounds__(kGcFwdBlock, 3)
+gc_point_queue_kernel(GcQueueSource src, int n, int bubble, int32_t* __restrict__ evals, int32_t* __restrict__ retry_list,
+                      int32_t* __restrict__ retry_count, int32_t* __restrict__ queue_head) {
+  extern __shared__ double smem[];
+  point_queue_body<GcBinary, GcQueueSource>(src, gc_model_slot(smem), n, bubble != 0, evals, retry_list, retry_count,
+                                            queue_head);
 }
 
 __global__ void __launch_bounds__(64)
@@ -274,18 +307,35 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   FEOS_ARG(temperature && molefracs && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
   GcArgs g{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
-  int32_t* ws = nullptr;
-  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s)) return rc_;
-  FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
+  int32_t* ws = nullptr;  // [0] = retry counter, [1] = queue head, [2 ..] = retry list
+  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
   static const int smem_ok = [] {
-    return cudaFuncSetAttribute(gc_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem);
+    cudaError_t e = cudaFuncSetAttribute(gc_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaFuncSetAttribute(gc_point_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem);
   }();
   FEOS_ARG(smem_ok == cudaSuccess);
-  gc_point_fwd_kernel<<<grid_for(n, kGcFwdBlock), kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure,
-                                                                           failed, evals, ws + 1, ws);
+  static const int variant = point_kernel_variant();
+  if (variant == 0 || n < 65536) {
+    gc_point_fwd_kernel<<<grid_for(n, kGcFwdBlock), kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure,
+                                                                             failed, evals, ws + 2, ws);
+  } else {
+    static int blocks = 0;
+    if (!blocks) {
+      int dev = 0, sms = 0, per_sm = 0;
+      FEOS_CUDA(cudaGetDevice(&dev));
+      FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_point_queue_kernel, kGcFwdBlock, kGcSmem));
+      blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    GcQueueSource src{g, molefracs, rho, pressure, failed};
+    int grid = (int)std::min<int64_t>(blocks, (n + kGcFwdBlock - 1) / kGcFwdBlock);
+    gc_point_queue_kernel<<<grid, kGcFwdBlock, kGcSmem, s>>>(src, (int)n, bubble, evals, ws + 2, ws, ws + 1);
+  }
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
-  gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, bubble, rho, pressure, failed, evals, ws + 1, ws);
+  gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, bubble, rho, pressure, failed, evals, ws + 2, ws);
   FEOS_LAUNCH_OK();
   FEOS_CUDA(cudaFreeAsync(ws, s));
   return 0;

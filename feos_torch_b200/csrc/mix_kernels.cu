@@ -7,11 +7,14 @@
 //   mix_point_bwd_kernel     gradient of the Newton-step pressure w.r.t. 2x8 parameters, k_ij, eps_AiBj
 //                            and T: 7 passes of 3 dual directions (mix_grad.cuh);
 //   mix_state_kernel         a, p, mu_i, v_i at given (T, rho_1, rho_2)  (PcSaftMix.derivatives).
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/feos_b200.h"
 #include "common.h"
 #include "mix_grad.cuh"
+#include "point_queue.cuh"
 
 namespace feos {
 
@@ -66,7 +69,10 @@ __device__ __forceinline__ void store_point(int64_t i, int rc, bool bubble, doub
   failed[i] = (rc == kStatusOk) ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(kMixBlock)
+#ifndef FEOS_MIX_FWD_MINB
+#define FEOS_MIX_FWD_MINB 2
+#endif
+__global__ void __launch_bounds__(kMixBlock, FEOS_MIX_FWD_MINB)
 mix_point_fwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
                      const double* __restrict__ temperature, const double* __restrict__ molefrac, int64_t n, int bubble,
                      double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
@@ -91,6 +97,44 @@ mix_point_fwd_kernel(const double* __restrict__ params, const double* __restrict
     return;
   }
   store_point<PcSaftBinary>(i, rc, bubble != 0, z0, T, st, se, es, ei, rho, value, failed);
+}
+
+// Persistent work-queue variant (point_queue.cuh): same solver as mix_point_fwd_kernel, cut into
+// one-evaluation trips so that Newton iterations of divergent lengths do not idle lanes.
+struct MixQueueSource {
+  const double* params;
+  const double* kij;
+  const double* temperature;
+  const double* molefrac;
+  double* rho;
+  double* value;
+  uint8_t* failed;
+  __device__ __forceinline__ void dummy(PcSaftBinary& b) const {
+    const double prm[16] = {1.0, 3.5, 150.0, 0, 0, 0, 0, 0, 1.0, 3.5, 150.0, 0, 0, 0, 0, 0};
+    const double kk[2] = {0.0, 0.0};
+    pcsaft_binary_init(b, prm, kk, 300.0);
+  }
+  __device__ __forceinline__ bool load(int i, PcSaftBinary& b, double& z0, double& T) const {
+    T = temperature[i];
+    z0 = molefrac[i];
+    double prm[16], kk[2];
+    load_mix(params, kij, i, prm, kk);
+    pcsaft_binary_init(b, prm, kk, T);
+    return z0 > 0.0 && z0 < 1.0;
+  }
+  __device__ __forceinline__ void store(int i, int rc, bool bubble, double z0, double T,
+                                        const PointMachine<PcSaftBinary>& m) const {
+    store_point<PcSaftBinary>(i, rc, bubble, z0, T, m.st, m.st_eval, m.es, m.ei, rho, value, failed);
+  }
+};
+
+__global__ void __launch_bounds__(kMixBlock, 2)
+mix_point_queue_kernel(MixQueueSource src, int n, int bubble, int32_t* __restrict__ evals,
+                       int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count,
+                       int32_t* __restrict__ queue_head) {
+  extern __shared__ double smem[];
+  point_queue_body<PcSaftBinary, MixQueueSource>(src, model_slot(smem), n, bubble != 0, evals, retry_list, retry_count,
+                                                 queue_head);
 }
 
 __global__ void __launch_bounds__(64)
@@ -254,19 +298,37 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && molefracs && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
-  int32_t* ws = nullptr;
-  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 1), s)) return rc_;
-  FEOS_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t), s));
+  int32_t* ws = nullptr;  // [0] = retry counter, [1] = queue head, [2 ..] = retry list
+  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
   static const int smem_ok = [] {
-    return cudaFuncSetAttribute(mix_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem);
+    cudaError_t e = cudaFuncSetAttribute(mix_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaFuncSetAttribute(mix_point_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem);
   }();
   FEOS_ARG(smem_ok == cudaSuccess);
-  mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, kMixSmem, s>>>(params, kij, temperature, molefracs, n, bubble,
-                                                                         rho, pressure, failed, evals, ws + 1, ws);
+  // default = one thread per state; FEOS_B200_POINT_KERNEL=queue selects the persistent work-queue kernel
+  static const int variant = point_kernel_variant();
+  if (variant == 0 || n < 65536) {
+    mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, kMixSmem, s>>>(params, kij, temperature, molefracs, n, bubble,
+                                                                           rho, pressure, failed, evals, ws + 2, ws);
+  } else {
+    static int blocks = 0;
+    if (!blocks) {
+      int dev = 0, sms = 0, per_sm = 0;
+      FEOS_CUDA(cudaGetDevice(&dev));
+      FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mix_point_queue_kernel, kMixBlock, kMixSmem));
+      blocks = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    MixQueueSource src{params, kij, temperature, molefracs, rho, pressure, failed};
+    int grid = (int)std::min<int64_t>(blocks, (n + kMixBlock - 1) / kMixBlock);
+    mix_point_queue_kernel<<<grid, kMixBlock, kMixSmem, s>>>(src, (int)n, bubble, evals, ws + 2, ws, ws + 1);
+  }
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
   mix_point_retry_kernel<<<retry_grid, 64, 0, s>>>(params, kij, temperature, molefracs, bubble, rho, pressure, failed,
-                                                  evals, ws + 1, ws);
+                                                  evals, ws + 2, ws);
   FEOS_LAUNCH_OK();
   FEOS_CUDA(cudaFreeAsync(ws, s));
   return 0;

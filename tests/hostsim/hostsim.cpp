@@ -178,6 +178,9 @@ void sim_pure_state(const double* params, const double* T, const double* rho, in
 // binary mixtures
 // ---------------------------------------------------------------------------------------------
 #include "../../feos_torch_b200/csrc/mix_grad.cuh"
+#include "../../feos_torch_b200/csrc/mix_machine.cuh"
+static int g_use_machine = 0;
+extern "C" void sim_use_point_machine(int on) { g_use_machine = on; }
 
 extern "C" {
 
@@ -203,7 +206,8 @@ void sim_mix_point(const double* params, const double* kij, const double* T, con
     PointState st, se;
     MixEval es, ei;
     int ne = 0;
-    int rc = point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
+    int rc = g_use_machine ? point_fast_machine(b, bubble != 0, z[i], st, es, ei, se, ne)
+                           : point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
     if (rc == kStatusRetry && use_robust) rc = point_robust(b, bubble != 0, z[i], st, es, ei, se, ne);
     status[i] = (uint8_t)rc;
     evals[i] = ne;
@@ -288,7 +292,8 @@ void sim_gc_point(const GcPair* pairs, const double* seg, const double* kab, con
     PointState st, se;
     MixEval es, ei;
     int ne = 0;
-    int rc = point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
+    int rc = g_use_machine ? point_fast_machine(b, bubble != 0, z[i], st, es, ei, se, ne)
+                           : point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
     if (rc == kStatusRetry) rc = point_robust(b, bubble != 0, z[i], st, es, ei, se, ne);
     status[i] = (uint8_t)rc;
     evals[i] = ne;

@@ -193,3 +193,8 @@ def gc_base_eval(pairs, seg, kab, idx, phi, T, rho):
     out = np.zeros((n, 12))
     lib().sim_gc_base_eval(_p(pairs), _p(seg), _p(kab), _p(idx), _p(phi), _p(T), _p(rho), ctypes.c_int64(n), _p(out))
     return out[:, :6], out[:, 6:]
+
+
+def use_point_machine(on):
+    """Route sim_mix_point / sim_gc_point through the resumable PointMachine (work-queue kernels) instead of the loop solver."""
+    lib().sim_use_point_machine(ctypes.c_int(int(on)))

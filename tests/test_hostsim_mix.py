@@ -117,3 +117,31 @@ def test_closed_form_base_eval_equals_hyper_dual():
     err = np.abs(fast - generic) / np.maximum(np.abs(generic), 1e-300)
     # both share the reference's cancellation at low density (zeta_2^3 / eta terms of the hard-sphere formula)
     assert err.max() < 1e-10 and np.median(err) < 1e-14
+
+
+def test_point_machine_equals_loop_solver(golden_mix):
+    """The resumable PointMachine the work-queue kernels run (one evaluation per trip) against the loop solver:
+    same densities, values, status and evaluation counts on the category grid and on a C4-shaped random grid
+    that includes states the fast path gives up on."""
+    rng = np.random.default_rng(5)
+    n = 3000
+    pa, pb = [1, 3.5, 150, 0, 0, 0, 0, 0], [1, 3.5, 200, 0, 0, 0, 0, 0]
+    P = np.tile(np.array(pa + pb, dtype=float), (n, 1))
+    K = np.zeros((n, 2))
+    K[:, 0] = rng.uniform(-0.15, -0.05, n)
+    T = rng.uniform(0.6, 1.05, n) * 150 * 1.2757  # up to above the critical temperature of the light component
+    z = rng.uniform(0.02, 0.98, n)
+    e = golden_mix["category_grid"]
+    grids = [(P, K, T, z), (np.array(e["params"]).reshape(-1, 16), np.array(e["kij"]), np.array(e["T"]), np.array(e["z"]))]
+    try:
+        for (Pg, Kg, Tg, zg) in grids:
+            for bubble in (True, False):
+                sim.use_point_machine(False)
+                a = sim.mix_point(Pg, Kg, Tg, zg, bubble, robust=False)
+                sim.use_point_machine(True)
+                b = sim.mix_point(Pg, Kg, Tg, zg, bubble, robust=False)
+                assert (a[2] == b[2]).all() and (a[3] == b[3]).all()
+                ok = a[2] == 0
+                assert ok.any() and np.array_equal(a[0][ok], b[0][ok]) and np.array_equal(a[1][ok], b[1][ok])
+    finally:
+        sim.use_point_machine(False)
