@@ -186,18 +186,114 @@ FD BaseH2 mix_base_eval(const MixCoef<double, NB, GC>& c, double r0, double r1) 
   return o;
 }
 
-// The evaluation the solvers and state kernels use: closed-form base part; the dipole and association
-// terms (only where present) in hyper-dual arithmetic on top.
+// Gross-Vrabec dipole term a = phi2^2 / (phi2 - phi3) in closed form (value, gradient, Hessian), added to `o`:
+//   phi2 = -pi sum_k tau_k(rho) ps_k J2_k(eta),  phi3 = -4/3 pi^2 sum_t tautau_t(rho) ts_t J3_t(eta)
+// with tau = (t0^2, t0 t1, t1^2), tautau = (t0^3, t0^2 t1, t1^2 t0, t1^3), t_i = rho_i mu2t_i and the pair /
+// triplet integrals J polynomial in eta (pcsaft_mix.py:156-208).
+template <class C>
+FD void mix_dipole_eval(const C& c, double r0, double r1, BaseH2& o) {
+  const double z30 = c.z[3][0], z31 = c.z[3][1];
+  const double eta = r0 * z30 + r1 * z31;
+  // polynomials in eta with two derivatives: PA_j (degree 4), PB_j (degree 2), PC_j (degree 3)
+  double pa[3], pa1[3], pa2[3], pb[3], pb1[3], pb2[3], pc[3], pc1[3], pc2[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double v = cAD[4][j], d1 = 0.0, d2 = 0.0;
+#pragma unroll
+    for (int n = 3; n >= 0; --n) {
+      d2 = d2 * eta + d1;
+      d1 = d1 * eta + v;
+      v = v * eta + cAD[n][j];
+    }
+    pa[j] = v; pa1[j] = d1; pa2[j] = 2.0 * d2;
+    v = cBD[2][j]; d1 = 0.0; d2 = 0.0;
+#pragma unroll
+    for (int n = 1; n >= 0; --n) {
+      d2 = d2 * eta + d1;
+      d1 = d1 * eta + v;
+      v = v * eta + cBD[n][j];
+    }
+    pb[j] = v; pb1[j] = d1; pb2[j] = 2.0 * d2;
+    v = cCD[3][j]; d1 = 0.0; d2 = 0.0;
+#pragma unroll
+    for (int n = 2; n >= 0; --n) {
+      d2 = d2 * eta + d1;
+      d1 = d1 * eta + v;
+      v = v * eta + cCD[n][j];
+    }
+    pc[j] = v; pc1[j] = d1; pc2[j] = 2.0 * d2;
+  }
+  const double u0 = c.mu2t[0], u1 = c.mu2t[1];
+  const double t0 = r0 * u0, t1 = r1 * u1;
+  // tau_k and tautau_t with their density derivatives: value, d/d rho0, d/d rho1, d00, d01, d11
+  const double tau[3][6] = {{t0 * t0, 2.0 * u0 * t0, 0.0, 2.0 * u0 * u0, 0.0, 0.0},
+                            {t0 * t1, u0 * t1, u1 * t0, 0.0, u0 * u1, 0.0},
+                            {t1 * t1, 0.0, 2.0 * u1 * t1, 0.0, 0.0, 2.0 * u1 * u1}};
+  const double ttt[4][6] = {{t0 * t0 * t0, 3.0 * u0 * t0 * t0, 0.0, 6.0 * u0 * u0 * t0, 0.0, 0.0},
+                            {t0 * t0 * t1, 2.0 * u0 * t0 * t1, u1 * t0 * t0, 2.0 * u0 * u0 * t1, 2.0 * u0 * u1 * t0, 0.0},
+                            {t1 * t1 * t0, u0 * t1 * t1, 2.0 * u1 * t1 * t0, 0.0, 2.0 * u0 * u1 * t1, 2.0 * u1 * u1 * t0},
+                            {t1 * t1 * t1, 0.0, 3.0 * u1 * t1 * t1, 0.0, 0.0, 6.0 * u1 * u1 * t1}};
+  // phi[6] = value, d0, d1, d00, d01, d11 (before the constant factors)
+  double p2[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, p3[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double w1 = c.pw1[k], w2 = c.pw2[k], pe = c.pe[k], ps = c.ps[k];
+    const double j = ps * ((pa[0] + w1 * pa[1] + w2 * pa[2]) + pe * (pb[0] + w1 * pb[1] + w2 * pb[2]));
+    const double j1 = ps * ((pa1[0] + w1 * pa1[1] + w2 * pa1[2]) + pe * (pb1[0] + w1 * pb1[1] + w2 * pb1[2]));
+    const double j2 = ps * ((pa2[0] + w1 * pa2[1] + w2 * pa2[2]) + pe * (pb2[0] + w1 * pb2[1] + w2 * pb2[2]));
+    const double* t = tau[k];
+    p2[0] += t[0] * j;
+    p2[1] += t[1] * j + t[0] * j1 * z30;
+    p2[2] += t[2] * j + t[0] * j1 * z31;
+    p2[3] += t[3] * j + 2.0 * t[1] * j1 * z30 + t[0] * j2 * z30 * z30;
+    p2[4] += t[4] * j + (t[1] * z31 + t[2] * z30) * j1 + t[0] * j2 * z30 * z31;
+    p2[5] += t[5] * j + 2.0 * t[2] * j1 * z31 + t[0] * j2 * z31 * z31;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double w1 = c.tw1[k], w2 = c.tw2[k], ts = c.ts[k];
+    const double j = ts * (pc[0] + w1 * pc[1] + w2 * pc[2]);
+    const double j1 = ts * (pc1[0] + w1 * pc1[1] + w2 * pc1[2]);
+    const double j2 = ts * (pc2[0] + w1 * pc2[1] + w2 * pc2[2]);
+    const double* t = ttt[k];
+    p3[0] += t[0] * j;
+    p3[1] += t[1] * j + t[0] * j1 * z30;
+    p3[2] += t[2] * j + t[0] * j1 * z31;
+    p3[3] += t[3] * j + 2.0 * t[1] * j1 * z30 + t[0] * j2 * z30 * z30;
+    p3[4] += t[4] * j + (t[1] * z31 + t[2] * z30) * j1 + t[0] * j2 * z30 * z31;
+    p3[5] += t[5] * j + 2.0 * t[2] * j1 * z31 + t[0] * j2 * z31 * z31;
+  }
+  const double k2 = -kPi, k3 = -4.0 / 3.0 * kPi * kPi;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    p2[q] *= k2;
+    p3[q] *= k3;
+  }
+  if (p2[0] == 0.0) return;  // no dipole-dipole pair at this composition: the term and its derivatives vanish
+  const double D = p2[0] - p3[0], Di = 1.0 / D, Di2 = Di * Di, Di3 = Di2 * Di;
+  const double f2 = p2[0] * (p2[0] - 2.0 * p3[0]) * Di2, f3 = p2[0] * p2[0] * Di2;
+  const double f22 = 2.0 * p3[0] * p3[0] * Di3, f23 = -2.0 * p2[0] * p3[0] * Di3, f33 = 2.0 * p2[0] * p2[0] * Di3;
+  o.a += p2[0] * p2[0] * Di;
+  o.g0 += f2 * p2[1] + f3 * p3[1];
+  o.g1 += f2 * p2[2] + f3 * p3[2];
+  o.h00 += f22 * p2[1] * p2[1] + 2.0 * f23 * p2[1] * p3[1] + f33 * p3[1] * p3[1] + f2 * p2[3] + f3 * p3[3];
+  o.h01 += f22 * p2[1] * p2[2] + f23 * (p2[1] * p3[2] + p3[1] * p2[2]) + f33 * p3[1] * p3[2] + f2 * p2[4] + f3 * p3[4];
+  o.h11 += f22 * p2[2] * p2[2] + 2.0 * f23 * p2[2] * p3[2] + f33 * p3[2] * p3[2] + f2 * p2[5] + f3 * p3[5];
+}
+
+// The evaluation the solvers and state kernels use: closed-form base and dipole parts; the association
+// term (only where present) in hyper-dual arithmetic on top.
 template <int NB, bool GC>
 FD MixEval mix_eval(const MixCoef<double, NB, GC>& c, double rho0, double rho1) {
   BaseH2 b = mix_base_eval<NB, GC>(c, rho0, rho1);
+  if (c.dipolar) mix_dipole_eval(c, rho0, rho1, b);
   H2<double> a;
   a.re = b.a; a.g0 = b.g0; a.g1 = b.g1; a.h00 = b.h00; a.h01 = b.h01; a.h11 = b.h11;
-  if (c.dipolar || c.cat != kAssocNone) {
+  if (c.cat != kAssocNone) {
     H2<double> r0(rho0), r1(rho1);
     r0.g0 = 1.0;
     r1.g1 = 1.0;
-    a = a + mix_helmholtz<double, H2<double>, NB, GC, 6>(c, r0, r1);
+    a = a + mix_helmholtz<double, H2<double>, NB, GC, 4>(c, r0, r1);
   }
   return mix_eval_from(a, rho0, rho1);
 }

@@ -499,3 +499,20 @@ void sim_gc_base_eval(const GcPair* pairs, const double* seg, const double* kab,
   }
 }
 }
+
+extern "C" {
+// out [n,12]: (a, mu0, mu1, h00, h01, h11) of mix_eval (closed-form base + dipole) and of mix_eval_generic
+void sim_mix_eval_pair(const double* params, const double* kij, const double* T, const double* rho, int64_t n, double* out) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16], kk[2] = {kij[2 * i], kij[2 * i + 1]};
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    MixCoef<double> c;
+    mix_coef<double>(c, prm, kk, T[i], false);
+    MixEval f = mix_eval<2, false>(c, rho[2 * i], rho[2 * i + 1]);
+    MixEval g = mix_eval_generic<2, false>(c, rho[2 * i], rho[2 * i + 1]);
+    double* o = out + 12 * i;
+    o[0] = f.a; o[1] = f.mu[0]; o[2] = f.mu[1]; o[3] = f.h00; o[4] = f.h01; o[5] = f.h11;
+    o[6] = g.a; o[7] = g.mu[0]; o[8] = g.mu[1]; o[9] = g.h00; o[10] = g.h01; o[11] = g.h11;
+  }
+}
+}

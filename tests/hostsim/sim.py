@@ -198,3 +198,11 @@ def gc_base_eval(pairs, seg, kab, idx, phi, T, rho):
 def use_point_machine(on):
     """Route sim_mix_point / sim_gc_point through the resumable PointMachine (work-queue kernels) instead of the loop solver."""
     lib().sim_use_point_machine(ctypes.c_int(int(on)))
+
+
+def mix_eval_pair(params, kij, T, rho):
+    params, kij, T, rho = c64(params), c64(kij), c64(T), c64(rho)
+    n = T.shape[0]
+    out = np.zeros((n, 12))
+    lib().sim_mix_eval_pair(_p(params), _p(kij), _p(T), _p(rho), ctypes.c_int64(n), _p(out))
+    return out[:, :6], out[:, 6:]

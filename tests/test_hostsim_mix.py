@@ -145,3 +145,23 @@ def test_point_machine_equals_loop_solver(golden_mix):
                 assert ok.any() and np.array_equal(a[0][ok], b[0][ok]) and np.array_equal(a[1][ok], b[1][ok])
     finally:
         sim.use_point_machine(False)
+
+
+def test_closed_form_eval_equals_hyper_dual_all_categories():
+    """mix_eval (closed-form base + dipole terms, hyper-dual association on top) against the fully hyper-dual
+    mix_eval_generic for every dipole / association category of tests/test_pcsaft_mix.py:17-36, with the segment
+    numbers varied across the m = 2 clamp of the dipole term."""
+    import cases
+
+    rng = np.random.default_rng(1)
+    reps = 100
+    P = np.tile(np.array(cases.MIX_PARAMS, dtype=float).reshape(-1, 16), (reps, 1))
+    K = np.tile(np.array(cases.MIX_KIJ), (reps, 1))
+    n = P.shape[0]
+    P[:, 0] *= rng.uniform(0.8, 1.3, n)
+    P[:, 8] *= rng.uniform(0.6, 1.2, n)
+    T = rng.uniform(200, 400, n)
+    rho = np.exp(rng.uniform(np.log(1e-8), np.log(4e-3), (n, 2)))
+    fast, generic = sim.mix_eval_pair(P, K, T, rho)
+    err = np.abs(fast - generic) / np.maximum(np.abs(generic), 1e-300)
+    assert err.max() < 1e-11 and np.median(err) < 1e-15
