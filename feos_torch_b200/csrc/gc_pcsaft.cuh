@@ -563,40 +563,7 @@ FD_NOINLINE void gc_dipole_adjoint(const GcSource& src, const GcCoef& c, const d
     mc[i] = m[i] <= 2.0 ? m[i] : 2.0;
   }
   double mcb[2] = {0.0, 0.0}, sgb[2] = {0.0, 0.0}, epb[2] = {0.0, 0.0}, gT = 0.0;
-  const int pi_[3] = {0, 0, 1}, pj_[3] = {0, 1, 1};
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int i = pi_[k], j = pj_[k];
-    const double* o = cb + 2 + 4 * k;  // pw1, pw2, pe, ps
-    double x = sqrt(mc[i] * mc[j]), xi = 1.0 / x;
-    double xb = (o[0] + o[1] * (3.0 - 4.0 * xi)) * xi * xi;
-    mcb[i] += xb * x / (2.0 * mc[i]);
-    mcb[j] += xb * x / (2.0 * mc[j]);
-    double pe = c.pe[k];
-    epb[i] += o[2] * pe / (2.0 * ep[i]);
-    epb[j] += o[2] * pe / (2.0 * ep[j]);
-    gT -= o[2] * pe * ti;
-    double sij = 0.5 * (sg[i] + sg[j]);
-    double sb = -1.5 * o[3] * c.ps[k] / sij;  // (d ps / d sij) / 2
-    sgb[i] += sb;
-    sgb[j] += sb;
-  }
-  const int ti_[4] = {0, 0, 0, 1}, tj_[4] = {0, 0, 1, 1}, tk_[4] = {0, 1, 1, 1};
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int i = ti_[t], j = tj_[t], k = tk_[t];
-    const double* o = cb + 14 + 3 * t;  // tw1, tw2, ts
-    double y = cbrt(mc[i] * mc[j] * mc[k]), yi = 1.0 / y;
-    double yb = (o[0] + o[1] * (3.0 - 4.0 * yi)) * yi * yi * y / 3.0;
-    mcb[i] += yb / mc[i];
-    mcb[j] += yb / mc[j];
-    mcb[k] += yb / mc[k];
-    double tb = -0.5 * o[2] * c.ts[t];
-    double sij = 0.5 * (sg[i] + sg[j]), sik = 0.5 * (sg[i] + sg[k]), sjk = 0.5 * (sg[j] + sg[k]);
-    sgb[i] += tb / sij + tb / sik;
-    sgb[j] += tb / sij + tb / sjk;
-    sgb[k] += tb / sik + tb / sjk;
-  }
+  dipole_coef_adjoint(c, mc, sg, ep, ti, cb, mcb, sgb, epb, gT);
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     double mi = 1.0 / m[i];

@@ -116,10 +116,11 @@ FD void base_phase_begin(BasePhase<R>& s, const C& c, const R& rho0, const R& rh
 // hard chain, one bond type: a = - B ln g,  g = 1/om + 3 x + 2 x^2 om,  x = z2 cd / om^2.
 // Returns d a / d cd and adds the zeta_2 / zeta_3 partials.
 template <class R>
-FD R base_phase_bond(BasePhase<R>& s, double cd, double bn0, double bn1) {
+FD R base_phase_bond(BasePhase<R>& s, double cd, double bn0, double bn1, R* lng = nullptr) {
   R x = s.cz * cd;
   R x2 = x * x;
   R gg = s.omi + 3.0 * x + (2.0 * x2) * s.om;
+  if (lng) *lng = ad_log(gg);
   R gx = 3.0 + 4.0 * (x * s.om);
   R w = (s.rho0 * bn0 + s.rho1 * bn1) * ad_recip(gg);  // B / g
   R wgx = w * gx;
@@ -182,9 +183,11 @@ FD double point_comb(double gi, const D1& gs, const PointWeights& q) {
 
 // cbar[idx] = d p_red / d coef[idx] for the base coefficients in the flat order of FEOS_VISIT_COEF:
 // z[k][i] -> 2 k + i, m[i] -> 8 + i, q1[k] -> 10 + k, q2[k] -> 13 + k, cd[b] -> 16 + b.
+// bnbar (optional, [2 NB]): adjoints of the bond numbers bn[b][i] (a_hc = - sum_b (rho . bn_b) ln g_b); they are
+// parameters (m_i - 1) for the homosegmented model and constants (counts) for the group-contribution model.
 template <int NB, bool GC>
 FD_NOINLINE void mix_base_coef_adjoint(const MixCoef<double, NB, GC>& c, const double (&spec)[2], const double (&inc)[2],
-                                       const PointWeights& q, double* cbar) {
+                                       const PointWeights& q, double* cbar, double* bnbar = nullptr) {
   BasePhase<double> pi;
   BasePhase<D1> ps;
   const double i0 = inc[0], i1 = inc[1];
@@ -195,9 +198,19 @@ FD_NOINLINE void mix_base_coef_adjoint(const MixCoef<double, NB, GC>& c, const d
 #pragma unroll 1
   for (int b = 0; b < nb; ++b) {
     double cd = c.cd[b], bn0 = c.bn[b][0], bn1 = c.bn[b][1];
-    double gi = base_phase_bond(pi, cd, bn0, bn1);
-    D1 gs = base_phase_bond(ps, cd, bn0, bn1);
-    cbar[16 + b] = point_comb(gi, gs, q);
+    if (bnbar) {
+      double li;
+      D1 ls;
+      double gi = base_phase_bond(pi, cd, bn0, bn1, &li);
+      D1 gs = base_phase_bond(ps, cd, bn0, bn1, &ls);
+      cbar[16 + b] = point_comb(gi, gs, q);
+      bnbar[2 * b] = point_comb(-(li * i0), -(ls * s0), q);
+      bnbar[2 * b + 1] = point_comb(-(li * i1), -(ls * s1), q);
+    } else {
+      double gi = base_phase_bond(pi, cd, bn0, bn1);
+      D1 gs = base_phase_bond(ps, cd, bn0, bn1);
+      cbar[16 + b] = point_comb(gi, gs, q);
+    }
   }
   base_phase_end(pi, c);
   base_phase_end(ps, c);
@@ -351,6 +364,162 @@ FD_NOINLINE void mix_dipole_coef_adjoint(const MixCoef<double, NB, GC>& c, const
     o[1] = point_comb((wi * c.ts[t]) * di.pc[2], (ws * c.ts[t]) * ds.pc[2], q);
     o[2] = point_comb(wi * di.j3[t], ws * ds.j3[t], q);
   }
+}
+
+// ---- reverse sweeps through the coefficient stage -------------------------------------------------------
+// Adjoint of dipole_coef (pcsaft_mix.cuh): cb = adjoints of the 26 dipole coefficients in the flat order
+// (mu2t[2]; pw1, pw2, pe, ps per pair; tw1, tw2, ts per triplet).  ADDS the adjoints of the (clamped) segment
+// numbers mc_i, the molecule diameters sg_i and energies ep_i, and of T.
+template <class C>
+FD void dipole_coef_adjoint(const C& c, const double (&mc)[2], const double (&sg)[2], const double (&ep)[2], double ti,
+                            const double* cb, double (&mcb)[2], double (&sgb)[2], double (&epb)[2], double& gT) {
+  const int pi_[3] = {0, 0, 1}, pj_[3] = {0, 1, 1};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = pi_[k], j = pj_[k];
+    const double* o = cb + 2 + 4 * k;  // pw1, pw2, pe, ps
+    double x = sqrt(mc[i] * mc[j]), xi = 1.0 / x;
+    double xb = (o[0] + o[1] * (3.0 - 4.0 * xi)) * xi * xi;
+    mcb[i] += xb * x / (2.0 * mc[i]);
+    mcb[j] += xb * x / (2.0 * mc[j]);
+    double pe = c.pe[k];
+    epb[i] += o[2] * pe / (2.0 * ep[i]);
+    epb[j] += o[2] * pe / (2.0 * ep[j]);
+    gT -= o[2] * pe * ti;
+    double sij = 0.5 * (sg[i] + sg[j]);
+    double sb = -1.5 * o[3] * c.ps[k] / sij;  // (d ps / d sij) / 2
+    sgb[i] += sb;
+    sgb[j] += sb;
+  }
+  const int ti_[4] = {0, 0, 0, 1}, tj_[4] = {0, 0, 1, 1}, tk_[4] = {0, 1, 1, 1};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int i = ti_[t], j = tj_[t], k = tk_[t];
+    const double* o = cb + 14 + 3 * t;  // tw1, tw2, ts
+    double y = cbrt(mc[i] * mc[j] * mc[k]), yi = 1.0 / y;
+    double yb = (o[0] + o[1] * (3.0 - 4.0 * yi)) * yi * yi * y / 3.0;
+    mcb[i] += yb / mc[i];
+    mcb[j] += yb / mc[j];
+    mcb[k] += yb / mc[k];
+    double tb = -0.5 * o[2] * c.ts[t];
+    double sij = 0.5 * (sg[i] + sg[j]), sik = 0.5 * (sg[i] + sg[k]), sjk = 0.5 * (sg[j] + sg[k]);
+    sgb[i] += tb / sij + tb / sik;
+    sgb[j] += tb / sij + tb / sjk;
+    sgb[k] += tb / sik + tb / sjk;
+  }
+}
+
+// Reverse sweep through mix_coef for a NON-ASSOCIATING binary: given the coefficient adjoints (cbar: flat order of
+// the base group 0 .. 17 then, if dipolar, the 26 dipole coefficients; bnbar: bond numbers) it returns
+//   out[0..15] = d p_red / d(parameters of the two components), out[16] = d/d k_ij, out[17] = 0, out[18] = d/d T.
+FD_NOINLINE void mix_coef_sweep(const double (&prm)[16], const double (&kij)[2], double T, const MixCoef<double>& c,
+                                const double* cbar, const double* bnbar, double (&out)[19]) {
+  const double ti = 1.0 / T;
+  double mb[2], sb[2], eb[2], mub[2] = {0.0, 0.0}, kb = 0.0, Tb = 0.0;
+  double d[2], ex[2], dbar[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double m = prm[8 * i], s = prm[8 * i + 1], e = prm[8 * i + 2];
+    ex[i] = exp(-3.0 * e * ti);
+    d[i] = s * (1.0 - 0.12 * ex[i]);
+    const double dd = d[i];
+    const double z0 = cbar[i], z1 = cbar[2 + i], z2 = cbar[4 + i], z3 = cbar[6 + i];
+    mb[i] = (kPi / 6.0) * (z0 + dd * (z1 + dd * (z2 + dd * z3))) + cbar[8 + i] + bnbar[3 * i];  // bn[i][i]: index 2 i + i
+    dbar[i] = (kPi / 6.0) * m * (z1 + dd * (2.0 * z2 + 3.0 * dd * z3)) + 0.5 * cbar[16 + i];
+    sb[i] = eb[i] = 0.0;
+  }
+  // dispersion: q1[k] (10 + k), q2[k] = q1[k] e_k (13 + k)
+  {
+    const double e00 = prm[2] * ti, e11 = prm[10] * ti;
+    const double e01 = sqrt(prm[2] * prm[10]) * ti * (1.0 - kij[0]);
+    const double s01 = 0.5 * (prm[1] + prm[9]);
+    double tb = cbar[10] + cbar[13] * e00;  // adjoint of q1[0]
+    double ebar = (cbar[13] + tb / e00) * c.q1[0];
+    mb[0] += 2.0 * tb * c.q1[0] / prm[0];
+    sb[0] += 3.0 * tb * c.q1[0] / prm[1];
+    eb[0] += ebar * ti;
+    Tb -= ebar * e00 * ti;
+    tb = cbar[12] + cbar[15] * e11;
+    ebar = (cbar[15] + tb / e11) * c.q1[2];
+    mb[1] += 2.0 * tb * c.q1[2] / prm[8];
+    sb[1] += 3.0 * tb * c.q1[2] / prm[9];
+    eb[1] += ebar * ti;
+    Tb -= ebar * e11 * ti;
+    tb = cbar[11] + cbar[14] * e01;
+    ebar = (cbar[14] + tb / e01) * c.q1[1] * e01;  // e01 times the adjoint of e01
+    mb[0] += tb * c.q1[1] / prm[0];
+    mb[1] += tb * c.q1[1] / prm[8];
+    const double s01b = 1.5 * tb * c.q1[1] / s01;  // (d / d s01) / 2
+    sb[0] += s01b;
+    sb[1] += s01b;
+    eb[0] += 0.5 * ebar / prm[2];
+    eb[1] += 0.5 * ebar / prm[10];
+    Tb -= ebar * ti;
+    kb -= ebar / (1.0 - kij[0]);
+  }
+  // dipole group
+  if (c.dipolar) {
+    const double* cb = cbar + 18;
+    double mc[2], sg[2], ep[2], mcb[2] = {0.0, 0.0}, sgb[2] = {0.0, 0.0}, epb[2] = {0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mc[i] = prm[8 * i] <= 2.0 ? prm[8 * i] : 2.0;
+      sg[i] = prm[8 * i + 1];
+      ep[i] = prm[8 * i + 2];
+    }
+    dipole_coef_adjoint(c, mc, sg, ep, ti, cb, mcb, sgb, epb, Tb);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double m = prm[8 * i], mu = prm[8 * i + 3];
+      // mu2t_i = mu_i^2 kDipoleScale / (m_i T)
+      mub[i] += cb[i] * 2.0 * mu * kDipoleScale * ti / m;
+      mb[i] -= cb[i] * c.mu2t[i] / m;
+      Tb -= cb[i] * c.mu2t[i] * ti;
+      if (m <= 2.0) mb[i] += mcb[i];
+      sb[i] += sgb[i];
+      eb[i] += epb[i];
+    }
+  }
+  // d_i = sigma_i (1 - 0.12 exp(-3 eps_i / T))
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double s = prm[8 * i + 1], e = prm[8 * i + 2];
+    sb[i] += dbar[i] * d[i] / s;
+    const double de = dbar[i] * s * 0.36 * ex[i] * ti;
+    eb[i] += de;
+    Tb -= de * e * ti;
+  }
+#pragma unroll
+  for (int k = 0; k < 19; ++k) out[k] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    out[8 * i] = mb[i];
+    out[8 * i + 1] = sb[i];
+    out[8 * i + 2] = eb[i];
+    out[8 * i + 3] = mub[i];
+  }
+  out[16] = kb;
+  out[18] = Tb;
+}
+
+// Closed-form gradient of the bubble / dew pressure [Pa] of a NON-ASSOCIATING binary with respect to all 19
+// inputs (2 x 8 parameters, k_ij, eps_AiBj (= 0 here), T), times g: coefficient adjoints (closed form) and one
+// reverse sweep through the coefficient stage.  Replaces 7 forward-mode passes of 3 directions each.
+// (cbar / bnbar live in one struct: see the compiler note in gc_pcsaft.cuh.)
+FD void mix_point_grad_closed(const double (&prm)[16], const double (&kij)[2], double T, const MixCoef<double>& c,
+                              const double (&spec)[2], const double (&inc)[2], const PointWeights& q, double p_red,
+                              double g, double (&out)[19]) {
+  struct {
+    double cbar[18 + 26];
+    double bnbar[4];
+  } w;
+  mix_base_coef_adjoint<2, false>(c, spec, inc, q, w.cbar, w.bnbar);
+  if (c.dipolar) mix_dipole_coef_adjoint<2, false>(c, spec, inc, q, w.cbar, 18);
+  mix_coef_sweep(prm, kij, T, c, w.cbar, w.bnbar, out);
+  const double scale = g * T * kPaPerRed;
+#pragma unroll
+  for (int k = 0; k < 19; ++k) out[k] *= scale;
+  out[18] += g * p_red * kPaPerRed;  // explicit factor T of p = p_red T kB / A^3
 }
 
 // out[k] = g * d(p_bubble/dew [Pa]) / d(direction ids[k])

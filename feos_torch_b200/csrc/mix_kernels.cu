@@ -5,7 +5,8 @@
 //                            go to a retry list handled by
 //   mix_point_retry_kernel   the robust path over the compacted retry list;
 //   mix_point_bwd_kernel     gradient of the Newton-step pressure w.r.t. 2x8 parameters, k_ij, eps_AiBj
-//                            and T: 7 passes of 3 dual directions (mix_grad.cuh);
+//                            and T: closed-form coefficient adjoints + reverse sweep for non-associating
+//                            states, passes of 3 dual directions for associating ones (mix_grad.cuh);
 //   mix_state_kernel         a, p, mu_i, v_i at given (T, rho_1, rho_2)  (PcSaftMix.derivatives).
 #include <algorithm>
 #include <cstdlib>
@@ -160,6 +161,11 @@ mix_point_retry_kernel(const double* __restrict__ params, const double* __restri
   }
 }
 
+// a only (the incipient phase of the Newton-step pressure needs no derivatives)
+__device__ __noinline__ double mix_value(const MixCoef<double>& c, double r0, double r1) {
+  return mix_helmholtz<double, double, 2, false>(c, r0, r1);
+}
+
 __global__ void __launch_bounds__(kMixBlock)
 mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
                      const double* __restrict__ temperature, const double* __restrict__ rho,
@@ -187,13 +193,27 @@ mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict
   if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
   else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
   PointWeights q;
+  double gi = g[pos ? (int64_t)pos[i] : i];
   {
     PcSaftBinary b;
     pcsaft_binary_init(b, prm, kk, T);
     MixEval es = b.eval(spec[0], spec[1]);
     q = point_weights(es, spec, inc);
+    if (b.c.cat == kAssocNone) {
+      // non-associating state: closed-form coefficient adjoints + one reverse sweep through the coefficient stage
+      double p_red = point_pressure(es, mix_value(b.c, inc[0], inc[1]), spec, inc);
+      double o[19];
+      mix_point_grad_closed(prm, kk, T, b.c, spec, inc, q, p_red, gi, o);
+      if (grad_params) {
+        double2* gp = reinterpret_cast<double2*>(grad_params + 16 * i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gp[k] = make_double2(o[2 * k], o[2 * k + 1]);
+      }
+      if (grad_kij) reinterpret_cast<double2*>(grad_kij)[i] = make_double2(o[16], o[17]);
+      if (grad_t) grad_t[i] = o[18];
+      return;
+    }
   }
-  double gi = g[pos ? (int64_t)pos[i] : i];
   // only the directions whose gradient is requested (a k_ij fit needs 1 pass instead of 7)
   int dirs[24];
   int nd = 0;

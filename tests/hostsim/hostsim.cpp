@@ -180,6 +180,8 @@ void sim_pure_state(const double* params, const double* T, const double* rho, in
 #include "../../feos_torch_b200/csrc/mix_grad.cuh"
 #include "../../feos_torch_b200/csrc/mix_machine.cuh"
 static int g_use_machine = 0;
+static int g_mix_bwd_closed = 1;
+extern "C" void sim_mix_bwd_closed(int on) { g_mix_bwd_closed = on; }
 extern "C" void sim_use_point_machine(int on) { g_use_machine = on; }
 
 extern "C" {
@@ -240,6 +242,13 @@ void sim_mix_point_bwd(const double* params, const double* kij, const double* T,
     else { spec[0] = r[0]; spec[1] = r[1]; inc[0] = r[2]; inc[1] = r[3]; }
     MixEval es = b.eval(spec[0], spec[1]);
     PointWeights q = point_weights(es, spec, inc);
+    if (g_mix_bwd_closed && b.c.cat == kAssocNone) {
+      double p_red = point_pressure(es, mix_helmholtz<double, double, 2, false>(b.c, inc[0], inc[1]), spec, inc);
+      double o[19];
+      mix_point_grad_closed(prm, kk, T[i], b.c, spec, inc, q, p_red, g[i], o);
+      for (int k = 0; k < 19; ++k) grad[19 * i + k] = o[k];
+      continue;
+    }
     for (int f = 0; f < 21; f += 3) {
       double g3[3];
       int ids[3] = {f < 19 ? f : -1, f + 1 < 19 ? f + 1 : -1, f + 2 < 19 ? f + 2 : -1};

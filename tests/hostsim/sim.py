@@ -206,3 +206,8 @@ def mix_eval_pair(params, kij, T, rho):
     out = np.zeros((n, 12))
     lib().sim_mix_eval_pair(_p(params), _p(kij), _p(T), _p(rho), ctypes.c_int64(n), _p(out))
     return out[:, :6], out[:, 6:]
+
+
+def mix_bwd_closed(on):
+    """sim_mix_point_bwd: closed-form adjoints + reverse sweep (what the kernel runs for non-associating states) or the dual passes."""
+    lib().sim_mix_bwd_closed(ctypes.c_int(int(on)))

@@ -165,3 +165,25 @@ def test_closed_form_eval_equals_hyper_dual_all_categories():
     fast, generic = sim.mix_eval_pair(P, K, T, rho)
     err = np.abs(fast - generic) / np.maximum(np.abs(generic), 1e-300)
     assert err.max() < 1e-11 and np.median(err) < 1e-15
+
+
+def test_closed_form_gradient_equals_dual_passes(golden_mix):
+    """mix_point_grad_closed (closed-form coefficient adjoints + reverse sweep through mix_coef, the path of the
+    non-associating states) against the forward-mode passes over all 19 input directions."""
+    e = golden_mix["category_grid"]
+    P, K, T, z = np.array(e["params"]).reshape(-1, 16), np.array(e["kij"]), np.array(e["T"]), np.array(e["z"])
+    g = np.linspace(0.5, 1.5, len(T))
+    try:
+        for bubble in (True, False):
+            rho, val, st, ev = sim.mix_point(P, K, T, z, bubble)
+            ok = st == 0
+            sim.mix_bwd_closed(False)
+            a = sim.mix_point_bwd(P[ok], K[ok], T[ok], rho[ok], bubble, g[ok])
+            sim.mix_bwd_closed(True)
+            b = sim.mix_point_bwd(P[ok], K[ok], T[ok], rho[ok], bubble, g[ok])
+            scale = np.abs(a).max(axis=1, keepdims=True)
+            assert (np.abs(a - b) / scale).max() < 1e-10
+            nonassoc = (P[ok][:, 6] + P[ok][:, 7] + P[ok][:, 14] + P[ok][:, 15]) == 0
+            assert nonassoc.sum() >= 8 and (np.abs(a - b)[nonassoc] > 0).any()  # the closed-form path did run
+    finally:
+        sim.mix_bwd_closed(True)
