@@ -114,30 +114,37 @@ FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& p
 #pragma unroll
     for (int k = 0; k < 3; ++k) c.q1[k] = c.q2[k] = P(0.0);
   } else {
+    // sqrt(eps_a eps_b phi_i phi_j) = sqrt(eps_a) sqrt(eps_b) sqrt(phi_i phi_j): one square root per segment and
+    // per (i, j) instead of three per segment pair
     P phi0 = src.phi(0), phi1 = src.phi(1);
-    P pp[3] = {phi0 * phi0, phi0 * phi1, phi1 * phi1};
+    P sp[3] = {phi0 * ti, ad_sqrt(phi0 * phi1) * ti, phi1 * ti};  // sqrt(phi_i phi_j) / T
+    P se[kGcMaxSeg];
+    for (int a = 0; a < ns; ++a) {
+      P e = src.seg(a, 2);
+      // eps = 0 segments (">C<" of the Sauer table): the term and its derivatives are taken as zero
+      // (the reference's sqrt(0) yields NaN gradients there)
+      se[a] = (ad_primal(e) == 0.0) ? P(0.0) : ad_sqrt(e);
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) c.q1[k] = c.q2[k] = P(0.0);
     for (int a = 0; a < ns; ++a) {
-      P ma = src.seg(a, 0), sa = src.seg(a, 1), ea = src.seg(a, 2);
+      P ma = src.seg(a, 0), sa = src.seg(a, 1);
+      if (ad_primal(se[a]) == 0.0) continue;
       for (int b = 0; b < ns; ++b) {
-        P mb = src.seg(b, 0), sb = src.seg(b, 1), eb = src.seg(b, 2);
+        if (ad_primal(se[b]) == 0.0) continue;
+        P mb = src.seg(b, 0), sb = src.seg(b, 1);
         P sab = 0.5 * (sa + sb);
-        P s3 = sab * sab * sab;
-        P ee = ea * eb;
-        P mm = ma * mb;
+        P ms3 = (ma * mb) * (sab * sab * sab);
+        P see = se[a] * se[b];
         // ij = 00, 01, 11 (the 10 term equals the 01 term by symmetry of k_ab)
         const int ci[3] = {0, 0, 1}, cj[3] = {0, 1, 1};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           double nn = pr.cnt[ci[k]][a] * pr.cnt[cj[k]][b];
           if (nn == 0.0) continue;
-          // eps = 0 segments (">C<" of the Sauer table): the term and its derivatives are taken as zero
-          // (the reference's sqrt(0) yields NaN gradients there)
-          if (ad_primal(ee) == 0.0) continue;
-          P eab = ad_sqrt(ee * pp[k]) * ti;
+          P eab = see * sp[k];
           if (k == 1) eab = eab * (1.0 - src.kab_of(a, b));
-          P t = (nn * mm) * eab * s3;
+          P t = (nn * ms3) * eab;
           c.q1[k] = c.q1[k] + t;
           c.q2[k] = c.q2[k] + t * eab;
         }
@@ -497,43 +504,62 @@ FD_NOINLINE void gc_base_adjoint(const GcSource& src, const GcCoef& c, const dou
     gseg[8 * a + 2] += de;
     gT -= de * e * ti;
   }
-  // q1[k] = sum_ab nn_k m_a m_b eab s3ab (indices 10 + k), q2[k] = sum ... eab^2 (13 + k)
+  // q1[k] = sum_ab nn_k m_a m_b eab s3ab (indices 10 + k), q2[k] = sum ... eab^2 (13 + k),
+  // eab = sqrt(eps_a) sqrt(eps_b) sqrt(phi_i phi_j) / T (1 - k_ab [i != j]).  Reciprocals and square roots are
+  // taken once per segment; the pair loop holds one division (1 / sigma_ab).
   const double phi0 = src.phi(0), phi1 = src.phi(1);
-  const double pp[3] = {phi0 * phi0, phi0 * phi1, phi1 * phi1};
-  double ppb[3] = {0.0, 0.0, 0.0};
+  const double sp[3] = {phi0 * ti, sqrt(phi0 * phi1) * ti, phi1 * ti};
+  double se[kGcMaxSeg], im[kGcMaxSeg], ie[kGcMaxSeg], ga[kGcMaxSeg], gs[kGcMaxSeg], ge[kGcMaxSeg];
   for (int a = 0; a < ns; ++a) {
-    double ma = src.seg(a, 0), sa = src.seg(a, 1), ea = src.seg(a, 2);
+    double m = src.seg(a, 0), e = src.seg(a, 2);
+    se[a] = sqrt(e);
+    im[a] = 1.0 / m;
+    ie[a] = e == 0.0 ? 0.0 : 0.5 / e;
+    ga[a] = gs[a] = ge[a] = 0.0;
+  }
+  double eacc[3] = {0.0, 0.0, 0.0};  // sum of eab * (adjoint of eab) per (i, j)
+  for (int a = 0; a < ns; ++a) {
+    if (se[a] == 0.0) continue;
+    double ma = src.seg(a, 0), sa = src.seg(a, 1);
     for (int b = 0; b < ns; ++b) {
-      double mb = src.seg(b, 0), sb = src.seg(b, 1), eb = src.seg(b, 2);
-      double ee = ea * eb;
-      if (ee == 0.0) continue;
+      if (se[b] == 0.0) continue;
+      double mb = src.seg(b, 0), sb = src.seg(b, 1);
       double sab = 0.5 * (sa + sb), s3 = sab * sab * sab;
+      double isab = 1.5 / sab;  // d s3 / d sigma_a = 1.5 s3 / sab
+      double ms3 = ma * mb * s3, see = se[a] * se[b];
       const int ci[3] = {0, 0, 1}, cj[3] = {0, 1, 1};
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         double nn = pr.cnt[ci[k]][a] * pr.cnt[cj[k]][b];
         if (nn == 0.0) continue;
         double kab = (k == 1) ? src.kab_of(a, b) : 0.0;
-        double eab = sqrt(ee * pp[k]) * ti * (1.0 - kab);
-        double t = nn * ma * mb * eab * s3;
+        double eab = see * sp[k] * (1.0 - kab);
+        double t = nn * ms3 * eab;
         double tb = cbar[10 + k] + cbar[13 + k] * eab;       // adjoint of t
         double eb_ = (tb + cbar[13 + k] * eab) * t;          // eab * (adjoint of eab)
         double tt = tb * t;
-        gseg[8 * a] += tt / ma;
-        gseg[8 * b] += tt / mb;
-        double sg = tt * 1.5 / sab;                          // d s3 / d sigma_a = 1.5 s3 / sab
-        gseg[8 * a + 1] += sg;
-        gseg[8 * b + 1] += sg;
-        gseg[8 * a + 2] += 0.5 * eb_ / ea;
-        gseg[8 * b + 2] += 0.5 * eb_ / eb;
-        ppb[k] += 0.5 * eb_ / pp[k];
-        gT -= eb_ * ti;
+        ga[a] += tt * im[a];
+        ga[b] += tt * im[b];
+        double sg = tt * isab;
+        gs[a] += sg;
+        gs[b] += sg;
+        ge[a] += eb_ * ie[a];
+        ge[b] += eb_ * ie[b];
+        eacc[k] += eb_;
         if (k == 1 && pr.krec[a][b] >= 0) gkab[kGcMaxSeg * a + b] += -eb_ / (1.0 - kab);
       }
     }
   }
-  gphi[0] += 2.0 * phi0 * ppb[0] + phi1 * ppb[1];
-  gphi[1] += phi0 * ppb[1] + 2.0 * phi1 * ppb[2];
+  for (int a = 0; a < ns; ++a) {
+    gseg[8 * a] += ga[a];
+    gseg[8 * a + 1] += gs[a];
+    gseg[8 * a + 2] += ge[a];
+  }
+  gT -= (eacc[0] + eacc[1] + eacc[2]) * ti;
+  // eab ~ sqrt(phi_i phi_j): d/d phi_0 = (eacc_00 + eacc_01 / 2) / phi_0, d/d phi_1 likewise
+  double ppb[3] = {eacc[0], eacc[1], eacc[2]};
+  gphi[0] += (ppb[0] + 0.5 * ppb[1]) / phi0;
+  gphi[1] += (0.5 * ppb[1] + ppb[2]) / phi1;
   *gT_out += gT;
   (void)c;
 }
