@@ -430,7 +430,8 @@ def _main(out):
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (BASELINE.json metric)")
     ap.add_argument("--n", type=int, default=0, help="states per GPU per step (default: the workload's BASELINE size)")
-    ap.add_argument("--ref-n", type=int, default=20_000, help="states per step of the reference arm / cpu_baseline")
+    ap.add_argument("--ref-n", type=int, default=50_000, help="states per step of the reference arm (about 7 s per step)")
+    ap.add_argument("--cpu-n", type=int, default=100_000, help="states of the cpu_baseline sample (one pass, about 15 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
@@ -532,7 +533,7 @@ def _main(out):
     e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
     cpu = None
     if not args.no_cpu_baseline and args.workload == "c2":
-        cpu = cpu_baseline(args.ref_n)
+        cpu = cpu_baseline(args.cpu_n)
     line = {
         "metric": {"c2": METRIC, "c3": "pcsaft_equilibrium_liquid_density_solves_plus_grads_per_s",
                    "c4": "pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s",
