@@ -74,14 +74,15 @@ struct PointMachine {
         }
         return kStatusRetry;
       }
-      double u0 = log(rho * x[0]) + e.mu[0] - e.v[0] * e.p;
-      double u1 = log(rho * x[1]) + e.mu[1] - e.v[1] * e.p;
-      double eu0 = exp(u0), eu1 = exp(u1);
-      double delta = (eu0 + eu1 - e.p) / dps;
+      double w0 = e.mu[0] - e.v[0] * e.p, w1 = e.mu[1] - e.v[1] * e.p;
+      double r0 = rho * x[0], r1 = rho * x[1];
+      double delta = (r0 * exp(w0) + r1 * exp(w1) - e.p) / dps;
       delta = fmax(delta, -0.3 * rho);
       rho += delta;
       if (!(fabs(delta) < kStartTol * rho)) return it >= kStartIter ? kStatusRetry : kRunning;
       // the density iteration has converged: point_solve() continues
+      double u0 = log(r0) + w0, u1 = log(r1) + w1;
+      double eu0 = exp(u0), eu1 = exp(u1);
       if (bubble) {
         st.s = log(rho);
         st.u[0] = u0;

@@ -140,12 +140,17 @@ FD int liquid_start(const Model& mdl, double x0, double& rho, double (&u)[2], in
       }
       return kStatusRetry;
     }
-    u[0] = log(rho * x[0]) + e.mu[0] - e.v[0] * e.p;
-    u[1] = log(rho * x[1]) + e.mu[1] - e.v[1] * e.p;
-    double delta = (exp(u[0]) + exp(u[1]) - e.p) / dps;
+    // ideal-vapour partial densities rho x_i exp(mu_i - v_i p); their logarithms are only needed at the end
+    double w0 = e.mu[0] - e.v[0] * e.p, w1 = e.mu[1] - e.v[1] * e.p;
+    double r0 = rho * x[0], r1 = rho * x[1];
+    double delta = (r0 * exp(w0) + r1 * exp(w1) - e.p) / dps;
     delta = fmax(delta, -0.3 * rho);
     rho += delta;
-    if (fabs(delta) < tol * rho) return kStatusOk;
+    if (fabs(delta) < tol * rho) {
+      u[0] = log(r0) + w0;
+      u[1] = log(r1) + w1;
+      return kStatusOk;
+    }
   }
   return kStatusRetry;
 }
