@@ -20,22 +20,25 @@ SIGNATURES = {
     "feos_b200_launch_count": ([], _i64),
     "feos_b200_measure_fp64_peak": ([ctypes.c_int, _vp], ctypes.c_int),
     "feos_dev_compact": ([_vp, _i64, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp], ctypes.c_int),
-    "feos_dev_pure_vle_fwd": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_order": ([_vp, _vp, _i64, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_vle_fwd": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_vle_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_pure_rho_tp_fwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_rho_tp_fwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_rho_tp_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_state": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_state_bwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_state_bwd": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_state_bwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _i64,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_mix_point_fwd": ([_vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_order": ([_vp, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
+    "feos_dev_gc_point_order": ([_vp, ctypes.c_int32, _vp, _vp, _i64, ctypes.c_int, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_fwd": ([_vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_state": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_fwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _i64,
-                               ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+                               ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_bwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp,
-                               _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+                               _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_state": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _i64,
                            _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_host_gc_point": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp,
@@ -95,6 +98,36 @@ def timed_call(name, *args):
     call(name, *args)
     e1.record()
     TIMINGS.setdefault(name, []).append((e0, e1))
+
+
+# Bubble / dew batches of at least this many states are solved in the state order of csrc/order.cuh (states with
+# the same code path and neighbouring (T, x) share a warp); FEOS_B200_STATE_ORDER=0 keeps the input order (A/B runs).
+ORDER_MIN_STATES = 1 << 14
+
+
+def state_order_enabled(n):
+    return n >= ORDER_MIN_STATES and os.environ.get("FEOS_B200_STATE_ORDER", "1") != "0"
+
+
+# The order is a property of the data set: a fit loop solves the same (T, x) tensors every iteration, so the
+# permutation is kept for the last few (T, x) pairs, recognised by storage address + version counter.  ANY
+# permutation of 0 .. n-1 gives the same results, so a stale entry (memory reused for other values) can cost
+# speed but never correctness.
+_ORDER_CACHE = []
+_ORDER_CACHE_SIZE = 8
+
+
+def cached_order(kind, a, b, compute):
+    """``compute()`` -> int32 order tensor, memoised on (kind, tensors a and b)."""
+    key = (kind, a.data_ptr(), a._version, b.data_ptr(), b._version, a.shape[0], a.device)
+    for k, (e_key, order) in enumerate(_ORDER_CACHE):
+        if e_key == key:
+            _ORDER_CACHE.insert(0, _ORDER_CACHE.pop(k))
+            return order
+    order = compute()
+    _ORDER_CACHE.insert(0, (key, order))
+    del _ORDER_CACHE[_ORDER_CACHE_SIZE:]
+    return order
 
 
 def measure_fp64_peak(iters=20000):

@@ -41,6 +41,9 @@ int scratch_alloc(void** p, size_t bytes, cudaStream_t s);  // cudaMallocAsync f
 
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
+// batches below this size are launch-bound: the host entry points skip the state order (order.cuh)
+constexpr int64_t kOrderMinStates = 1 << 14;
+
 // bubble / dew forward kernels: 0 = one thread per state (default), 1 = persistent work queue
 // (FEOS_B200_POINT_KERNEL=queue).  Measured on B200, 1 M C4 states (profiles/README.md): the queue keeps 32 of
 // 32 lanes busy in the evaluation (loop: 16) and matches the loop kernel for bubble points (2.18 vs 2.14 ms),

@@ -87,10 +87,12 @@ __device__ __forceinline__ void store_gc_point(int64_t i, int rc, bool bubble, d
 __global__ void __launch_bounds__(kGcFwdBlock, FEOS_GC_FWD_MINB)
 gc_point_fwd_kernel(GcArgs g, const double* __restrict__ molefrac, int64_t n, int bubble, double* __restrict__ rho,
                     double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
-                    int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count) {
+                    int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count,
+                    const int32_t* __restrict__ order) {
   extern __shared__ double smem[];
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (order) i = order[i];  // states of one molecule pair and similar (T, x) share a warp (order.cuh)
   GcSource src = make_source(g, i);
   GcBinary& b = gc_model_slot(smem);
   gc_binary_init(b, src);
@@ -159,28 +161,34 @@ __global__ void __launch_bounds__(kGcBlock)
 gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ rho, const uint8_t* __restrict__ failed,
                     const int32_t* __restrict__ pos, const double* __restrict__ gout, int64_t n, int bubble,
                     double* __restrict__ grad_seg, double* __restrict__ grad_kab, double* __restrict__ grad_phi,
-                    double* __restrict__ grad_t) {
+                    double* __restrict__ grad_t, const int32_t* __restrict__ order) {
   extern __shared__ double acc[];  // [8 n_seg + n_rec] block-level sums of the shared-parameter gradients
   const int n_acc = 8 * n_seg + n_rec;
   for (int k = threadIdx.x; k < n_acc; k += blockDim.x) acc[k] = 0.0;
   __syncthreads();
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t i = t < n ? (order ? (int64_t)order[t] : t) : -1;
+  const bool valid = i >= 0 && !failed[i];
+  // every per-thread array whose address is handed to the (deliberately out-of-line) pass functions lives
+  // in ONE stack object: as separate locals nvcc 12.9 -O3 overlapped them on sm_100a (see gc_pcsaft.cuh)
+  struct Scratch {
+    GcBinary b;
+    double cbar[kGcMaxCoef];
+    double gseg[8 * kGcMaxSeg];
+    double gkab[kGcMaxSeg * kGcMaxSeg];
+    int dirs[kGcMaxDirs + 4];
+    GcDualCoef cd;
+    double* seed[kGcMaxCoef];
+  } w;
+  const GcPair* my_pair = nullptr;
+  if (i >= 0) {
     double gphi[2] = {0.0, 0.0}, gt = 0.0;
-    if (!failed[i]) {
+    if (valid) {
       GcSource src = make_source(g, i);
       const GcPair& pr = *src.pair;
-      // every per-thread array whose address is handed to the (deliberately out-of-line) pass functions lives
-      // in ONE stack object: as separate locals nvcc 12.9 -O3 overlapped them on sm_100a (see gc_pcsaft.cuh)
-      struct Scratch {
-        GcBinary b;
-        double cbar[kGcMaxCoef];
-        double gseg[8 * kGcMaxSeg];
-        double gkab[kGcMaxSeg * kGcMaxSeg];
-        int dirs[kGcMaxDirs + 4];
-        GcDualCoef cd;
-        double* seed[kGcMaxCoef];
-      } w;
+      my_pair = src.pair;
       GcBinary& b = w.b;
       double* cbar = w.cbar;
       double* gseg = w.gseg;
@@ -208,14 +216,6 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
         for (int c2 = 0; c2 < pr.nseg; ++c2) gkab[kGcMaxSeg * a + c2] = 0.0;
       gc_base_adjoint(src, b.c, cbar, gseg, gp2, &gtr, gkab);
       if (b.c.dipolar) gc_dipole_adjoint(src, b.c, cbar + 16 + b.c.nbond, gseg, &gtr);
-      if (grad_kab) {
-        for (int a = 0; a < pr.nseg; ++a)
-          for (int c2 = 0; c2 < pr.nseg; ++c2) {
-            int r = pr.krec[a][c2];
-            double v = gkab[kGcMaxSeg * a + c2] * scale;
-            if (r >= 0 && v != 0.0) atomicAdd(&acc[8 * n_seg + r], v);
-          }
-      }
       // association group (only for pairs that associate): dual passes, 4 directions each
       int n_dir = gc_active_directions(src, b.c, n_rec, dirs);
       for (int k = 0; k < 4; ++k) dirs[n_dir + k] = -1;
@@ -231,16 +231,62 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
           else gtr += g4[k];
         }
       }
-      for (int k = 0; k < 8 * pr.nseg; ++k) {
-        double v = gseg[k] * scale;
-        if (grad_seg && v != 0.0) atomicAdd(&acc[8 * pr.seg[k >> 3] + (k & 7)], v);
-      }
+      for (int k = 0; k < 8 * pr.nseg; ++k) gseg[k] *= scale;
+      for (int a = 0; a < pr.nseg; ++a)
+        for (int c2 = 0; c2 < pr.nseg; ++c2) gkab[kGcMaxSeg * a + c2] *= scale;
       gphi[0] = gp2[0] * scale;
       gphi[1] = gp2[1] * scale;
       gt = gtr * scale + gi * p_red * kPaPerRed;  // explicit factor T of p = p_red T kB/A^3
     }
     if (grad_phi) reinterpret_cast<double2*>(grad_phi)[i] = make_double2(gphi[0], gphi[1]);
     if (grad_t) grad_t[i] = gt;
+  }
+  // C. shared-parameter gradients -> block accumulators.  Shared-memory f64 atomics are compare-and-swap loops;
+  // in the state order of order.cuh a warp holds ONE molecule pair, i.e. 32 lanes adding to the same addresses.
+  // Such a warp sums each entry with shuffles and issues one atomic; mixed warps fall back to per-lane atomics.
+  const unsigned vm = __ballot_sync(full, valid);
+  if (vm) {
+    const unsigned long long mine = (unsigned long long)my_pair;
+    const unsigned long long lead = __shfl_sync(full, mine, __ffs(vm) - 1);
+    if (__all_sync(full, !valid || mine == lead)) {
+      const GcPair& pr = *reinterpret_cast<const GcPair*>(lead);
+      const int ns = pr.nseg;
+      if (grad_seg) {
+        for (int k = 0; k < 8 * ns; ++k) {
+          double v = valid ? w.gseg[k] : 0.0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+          if (lane == 0 && v != 0.0) atomicAdd(&acc[8 * pr.seg[k >> 3] + (k & 7)], v);
+        }
+      }
+      if (grad_kab) {
+        for (int a = 0; a < ns; ++a)
+          for (int c2 = 0; c2 < ns; ++c2) {
+            const int r = pr.krec[a][c2];
+            if (r < 0) continue;  // uniform over the warp: same pair
+            double v = valid ? w.gkab[kGcMaxSeg * a + c2] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+            if (lane == 0 && v != 0.0) atomicAdd(&acc[8 * n_seg + r], v);
+          }
+      }
+    } else if (valid) {
+      const GcPair& pr = *my_pair;
+      if (grad_seg) {
+        for (int k = 0; k < 8 * pr.nseg; ++k) {
+          double v = w.gseg[k];
+          if (v != 0.0) atomicAdd(&acc[8 * pr.seg[k >> 3] + (k & 7)], v);
+        }
+      }
+      if (grad_kab) {
+        for (int a = 0; a < pr.nseg; ++a)
+          for (int c2 = 0; c2 < pr.nseg; ++c2) {
+            int r = pr.krec[a][c2];
+            double v = w.gkab[kGcMaxSeg * a + c2];
+            if (r >= 0 && v != 0.0) atomicAdd(&acc[8 * n_seg + r], v);
+          }
+      }
+    }
   }
   __syncthreads();
   for (int k = threadIdx.x; k < n_acc; k += blockDim.x) {
@@ -299,7 +345,7 @@ extern "C" {
 int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* molefracs, int64_t n, int bubble, double* rho,
-                          double* pressure, uint8_t* failed, int32_t* evals, void* stream) {
+                          double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -319,7 +365,7 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   static const int variant = point_kernel_variant();
   if (variant == 0 || n < 65536) {
     gc_point_fwd_kernel<<<grid_for(n, kGcFwdBlock), kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure,
-                                                                             failed, evals, ws + 2, ws);
+                                                                             failed, evals, ws + 2, ws, order);
   } else {
     static int blocks = 0;
     if (!blocks) {
@@ -345,7 +391,7 @@ int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* rho, const uint8_t* failed, const int32_t* pos,
                           const double* g, int64_t n, int bubble, double* grad_seg_params, double* grad_kab,
-                          double* grad_phi, double* grad_temperature, void* stream) {
+                          double* grad_phi, double* grad_temperature, const int32_t* order, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -364,7 +410,7 @@ int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   }();
   shmem += (size_t)pad;
   gc_point_bwd_kernel<<<grid_for(n, kGcBlock), kGcBlock, shmem, (cudaStream_t)stream>>>(
-      a, n_seg, n_rec, rho, failed, pos, g, n, bubble, grad_seg_params, grad_kab, grad_phi, grad_temperature);
+      a, n_seg, n_rec, rho, failed, pos, g, n, bubble, grad_seg_params, grad_kab, grad_phi, grad_temperature, order);
   FEOS_LAUNCH_OK();
   return 0;
 }
@@ -408,9 +454,21 @@ int feos_host_gc_point(const feos_gc_pair* pairs, int32_t n_pairs, const double*
   if (phi) FEOS_CUDA(cudaMemcpyAsync(dphi.p, phi, 16 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dz.p, molefracs, 8 * n, cudaMemcpyHostToDevice, 0));
+  DevBuf dorder;
+  const bool ordered = n >= kOrderMinStates;
+  if (ordered) {
+    if (dorder.alloc(4 * n)) {
+      set_error("cudaMalloc failed for %lld states", (long long)n);
+      return -2;
+    }
+    if (int rc = feos_dev_gc_point_order(didx.as<int32_t>(), n_pairs, dt.as<double>(), dz.as<double>(), n, 0,
+                                         dorder.as<int32_t>(), nullptr))
+      return rc;
+  }
   int rc = feos_dev_gc_point_fwd(dpairs.as<feos_gc_pair>(), n_pairs, dseg.as<double>(), n_seg, dkab.as<double>(), n_rec,
                                  didx.as<int32_t>(), phi ? dphi.as<double>() : nullptr, dt.as<double>(), dz.as<double>(),
-                                 n, bubble, drho.as<double>(), nullptr, dfail.as<uint8_t>(), nullptr, nullptr);
+                                 n, bubble, drho.as<double>(), nullptr, dfail.as<uint8_t>(), nullptr,
+                                 ordered ? dorder.as<int32_t>() : nullptr, nullptr);
   if (rc) return rc;
   std::vector<double> rho(4 * (size_t)n);
   FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 32 * n, cudaMemcpyDeviceToHost, 0));

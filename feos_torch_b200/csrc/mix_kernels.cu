@@ -77,10 +77,12 @@ __global__ void __launch_bounds__(kMixBlock, FEOS_MIX_FWD_MINB)
 mix_point_fwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
                      const double* __restrict__ temperature, const double* __restrict__ molefrac, int64_t n, int bubble,
                      double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
-                     int32_t* __restrict__ evals, int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count) {
+                     int32_t* __restrict__ evals, int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count,
+                     const int32_t* __restrict__ order) {
   extern __shared__ double smem[];
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (order) i = order[i];  // states of similar (T, x) and code path share a warp (order.cuh)
   double T = temperature[i], z0 = molefrac[i];
   PcSaftBinary& b = model_slot(smem);
   {
@@ -171,9 +173,10 @@ mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict
                      const double* __restrict__ temperature, const double* __restrict__ rho,
                      const uint8_t* __restrict__ failed, const int32_t* __restrict__ pos, const double* __restrict__ g,
                      int64_t n, int bubble, double* __restrict__ grad_params, double* __restrict__ grad_kij,
-                     double* __restrict__ grad_t) {
+                     double* __restrict__ grad_t, const int32_t* __restrict__ order) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (order) i = order[i];
   if (failed[i]) {
     if (grad_params) {
       double2* gp = reinterpret_cast<double2*>(grad_params + 16 * i);
@@ -290,8 +293,19 @@ int host_point(const double* params, const double* kij, const double* temperatur
   FEOS_CUDA(cudaMemcpyAsync(dk.p, kij, 16 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dz.p, molefracs, 8 * n, cudaMemcpyHostToDevice, 0));
+  DevBuf dorder;
+  const bool ordered = n >= kOrderMinStates;
+  if (ordered) {
+    if (dorder.alloc(4 * n)) {
+      set_error("cudaMalloc failed for %lld states", (long long)n);
+      return -2;
+    }
+    if (int rc = feos_dev_mix_point_order(dp.as<double>(), dt.as<double>(), dz.as<double>(), n, dorder.as<int32_t>(), nullptr))
+      return rc;
+  }
   int rc = feos_dev_mix_point_fwd(dp.as<double>(), dk.as<double>(), dt.as<double>(), dz.as<double>(), n, bubble,
-                                  drho.as<double>(), nullptr, dfail.as<uint8_t>(), nullptr, nullptr);
+                                  drho.as<double>(), nullptr, dfail.as<uint8_t>(), nullptr,
+                                  ordered ? dorder.as<int32_t>() : nullptr, nullptr);
   if (rc) return rc;
   std::vector<double> rho(4 * (size_t)n);
   FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 32 * n, cudaMemcpyDeviceToHost, 0));
@@ -312,7 +326,7 @@ extern "C" {
 
 int feos_dev_mix_point_fwd(const double* params, const double* kij, const double* temperature,
                            const double* molefracs, int64_t n, int bubble, double* rho, double* pressure,
-                           uint8_t* failed, int32_t* evals, void* stream) {
+                           uint8_t* failed, int32_t* evals, const int32_t* order, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -331,7 +345,7 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   static const int variant = point_kernel_variant();
   if (variant == 0 || n < 65536) {
     mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, kMixSmem, s>>>(params, kij, temperature, molefracs, n, bubble,
-                                                                           rho, pressure, failed, evals, ws + 2, ws);
+                                                                           rho, pressure, failed, evals, ws + 2, ws, order);
   } else {
     static int blocks = 0;
     if (!blocks) {
@@ -356,13 +370,14 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
 
 int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
                            const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble,
-                           double* grad_params, double* grad_kij, double* grad_temperature, void* stream) {
+                           double* grad_params, double* grad_kij, double* grad_temperature, const int32_t* order,
+                           void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && rho && failed && g);
   mix_point_bwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, (cudaStream_t)stream>>>(
-      params, kij, temperature, rho, failed, pos, g, n, bubble, grad_params, grad_kij, grad_temperature);
+      params, kij, temperature, rho, failed, pos, g, n, bubble, grad_params, grad_kij, grad_temperature, order);
   FEOS_LAUNCH_OK();
   return 0;
 }

@@ -67,9 +67,10 @@ __global__ void __launch_bounds__(kBlock, 4)
 pure_vle_fwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature, int64_t n,
                     double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
                     uint8_t* __restrict__ failed, int32_t* __restrict__ evals, int32_t* __restrict__ retry_list,
-                    int32_t* __restrict__ retry_count) {
+                    int32_t* __restrict__ retry_count, const int32_t* __restrict__ order) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (order) i = order[i];  // states of similar (m, T / T_c) and code path share a warp (order.cuh)
   PureRow r = load_row(params, i);
   double T = temperature[i];
   PureCoef<double> c;
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(kBlock, 5)
 pure_vle_queue_kernel(const double* __restrict__ params, const double* __restrict__ temperature, int n,
                       double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
                       uint8_t* __restrict__ failed, int32_t* __restrict__ evals, int32_t* __restrict__ retry_list,
-                      int32_t* __restrict__ retry_count, int32_t* __restrict__ queue_head) {
+                      int32_t* __restrict__ retry_count, int32_t* __restrict__ queue_head,
+                      const int32_t* __restrict__ order) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   bool active = false, exhausted = false;
@@ -138,7 +140,7 @@ pure_vle_queue_kernel(const double* __restrict__ params, const double* __restric
           base = __shfl_sync(full, base, 0);
           int mine = base + __popc(idle & ((1u << lane) - 1u));
           if (!active && mine < n) {
-            idx = mine;
+            idx = order ? order[mine] : mine;
             PureRow r = load_row(params, idx);
             T = temperature[idx];
             double rho_max;
@@ -251,9 +253,11 @@ pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict_
 __global__ void __launch_bounds__(kBlock, 4)
 pure_rho_tp_fwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                        const double* __restrict__ pressure, int64_t n, double* __restrict__ rho,
-                       double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals) {
+                       double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
+                       const int32_t* __restrict__ order) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (order) i = order[i];
   PureRow r = load_row(params, i);
   double T = temperature[i];
   PureCoef<double> c;
@@ -341,13 +345,28 @@ struct DevBuf {
   template <class T>
   T* as() { return (T*)p; }
 };
+
+// state order for the host entry points: large batches without associating states (see feos_dev_pure_vle_fwd);
+// buf stays NULL = input order otherwise
+int host_order(DevBuf& buf, const double* host_params, const double* params, const double* temperature, int64_t n) {
+  if (n < kOrderMinStates) return 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const double* r = host_params + 8 * i;
+    if (r[4] != 0.0 && r[5] != 0.0 && r[6] + r[7] > 0.0) return 0;
+  }
+  if (buf.alloc(4 * n)) {
+    set_error("cudaMalloc failed for %lld states", (long long)n);
+    return -2;
+  }
+  return feos_dev_pure_order(params, temperature, n, buf.as<int32_t>(), nullptr);
+}
 }  // namespace
 
 extern "C" {
 
 int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64_t n, double* rho,
                           double* vapor_pressure, double* liquid_density, uint8_t* failed, int32_t* evals,
-                          void* stream) {
+                          const int32_t* order, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -356,16 +375,18 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
   int32_t* ws = nullptr;  // [0] = retry counter, [1] = queue head, [2..n+1] = retry list
   if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
   FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
-  static const int variant = [] {
-    // default = persistent work-queue kernel; "loop" = one thread per state.  Measured on B200 (1 M C2
-    // states, ncu): queue 0.566 ms with 22.4 of 32 lanes active per instruction, loop 0.572 ms with 16.9
-    // (profiles/README.md)
-    const char* e = getenv("FEOS_B200_PURE_VLE_KERNEL");
-    return (e && e[0] == 'l') ? 0 : 1;
-  }();
+  // FEOS_B200_PURE_VLE_KERNEL = "loop" (one thread per state) / "queue" (persistent work queue) for A/B runs.
+  // Default: states in input order -> queue (1 M C2 states, ncu: 0.566 ms, 22.4 of 32 lanes active per
+  // instruction; loop 0.572 ms, 16.9 lanes); states in the order of order.cuh -> loop (warps are homogeneous,
+  // so the queue's bookkeeping buys nothing: 0.40 ms against 0.49 ms, profiles/README.md).  The callers pass an
+  // order only for batches without associating states: their T_c is far from the key's estimate, the order does
+  // not align their iteration counts, and the loop kernel is slower on them (10 M C3 states: 10.0 vs 7.6 ms).
+  const char* env = getenv("FEOS_B200_PURE_VLE_KERNEL");
+  const int forced = !env ? -1 : (env[0] == 'l' ? 0 : (env[0] == 'q' ? 1 : -1));
+  const int variant = forced >= 0 ? forced : (order ? 0 : 1);
   if (variant == 0 || n < 65536) {
     pure_vle_fwd_kernel<<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, n, rho, vapor_pressure,
-                                                             liquid_density, failed, evals, ws + 2, ws);
+                                                             liquid_density, failed, evals, ws + 2, ws, order);
   } else {
     static int blocks = 0;
     if (!blocks) {
@@ -377,7 +398,7 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
     }
     int grid = (int)std::min<int64_t>(blocks, (n + kBlock - 1) / kBlock);
     pure_vle_queue_kernel<<<grid, kBlock, 0, s>>>(params, temperature, (int)n, rho, vapor_pressure, liquid_density,
-                                                failed, evals, ws + 2, ws, ws + 1);
+                                                failed, evals, ws + 2, ws, ws + 1, order);
   }
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
@@ -409,13 +430,13 @@ int feos_dev_pure_vle_bwd(const double* params, const double* temperature, const
 
 int feos_dev_pure_rho_tp_fwd(const double* params, const double* temperature, const double* pressure,
                              int64_t n, double* rho, double* liquid_density, uint8_t* failed, int32_t* evals,
-                             void* stream) {
+                             const int32_t* order, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
   FEOS_ARG(params && temperature && pressure && rho && failed);
   pure_rho_tp_fwd_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(params, temperature, pressure, n, rho,
-                                                                                 liquid_density, failed, evals);
+                                                                                 liquid_density, failed, evals, order);
   FEOS_LAUNCH_OK();
   return 0;
 }
@@ -463,8 +484,10 @@ int feos_host_pcsaft_vapor_pressure(const double* params, const double* temperat
   }
   FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 64 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
+  DevBuf dorder;
+  if (int rc = host_order(dorder, params, dp.as<double>(), dt.as<double>(), n)) return rc;
   int rc = feos_dev_pure_vle_fwd(dp.as<double>(), dt.as<double>(), n, drho.as<double>(), nullptr, nullptr,
-                                 dfail.as<uint8_t>(), nullptr, nullptr);
+                                 dfail.as<uint8_t>(), nullptr, dorder.as<int32_t>(), nullptr);
   if (rc) return rc;
   std::vector<double> rho(2 * (size_t)n);
   FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 16 * n, cudaMemcpyDeviceToHost, 0));
@@ -498,8 +521,10 @@ int feos_host_pcsaft_liquid_density(const double* params, const double* temperat
   FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 64 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dpr.p, pressure, 8 * n, cudaMemcpyHostToDevice, 0));
+  DevBuf dorder;
+  if (int rc = host_order(dorder, params, dp.as<double>(), dt.as<double>(), n)) return rc;
   int rc = feos_dev_pure_rho_tp_fwd(dp.as<double>(), dt.as<double>(), dpr.as<double>(), n, drho.as<double>(), nullptr,
-                                    dfail.as<uint8_t>(), nullptr, nullptr);
+                                    dfail.as<uint8_t>(), nullptr, dorder.as<int32_t>(), nullptr);
   if (rc) return rc;
   std::vector<double> rho((size_t)n);
   FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 8 * n, cudaMemcpyDeviceToHost, 0));

@@ -113,21 +113,33 @@ class _GcPoint(torch.autograd.Function):
         rho = torch.empty((n, 4), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
+        order = order_bwd = None
         with torch.cuda.device(dev):
+            if _lib.state_order_enabled(n):
+                # forward: states of one molecule pair and neighbouring (T, x) share a warp (csrc/order.cuh);
+                # backward (no iteration): grouped by pair only, input order inside a pair keeps its accesses local
+                def compute(pair_only):
+                    o = torch.empty((n,), dtype=torch.int32, device=dev)
+                    _lib.timed_call("feos_dev_gc_point_order", _lib.ptr(pair_index), n_pairs, _lib.ptr(temperature),
+                                    _lib.ptr(molefracs), n, pair_only, _lib.ptr(o), _stream())
+                    return o
+                order = _lib.cached_order(("gc", pair_index.data_ptr()), temperature, molefracs, lambda: compute(0))
+                order_bwd = _lib.cached_order(("gc-pair", pair_index.data_ptr()), temperature, molefracs, lambda: compute(1))
             _lib.timed_call(
                 "feos_dev_gc_point_fwd", _lib.ptr(pairs_dev), n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                 _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
-                _lib.ptr(molefracs), n, int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None, _stream(),
+                _lib.ptr(molefracs), n, int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None,
+                _lib.ptr(order), _stream(),
             )
             out, pos = compact(failed, val)
-        ctx.save_for_backward(seg_params, kab, phi, temperature, rho, failed, pos, pairs_dev, pair_index)
+        ctx.save_for_backward(seg_params, kab, phi, temperature, rho, failed, pos, pairs_dev, pair_index, order_bwd)
         ctx.bubble, ctx.n_pairs = int(bubble), n_pairs
         ctx.mark_non_differentiable(rho, failed)
         return out, failed, rho
 
     @staticmethod
     def backward(ctx, g_val, _g_failed, _g_rho):
-        seg_params, kab, phi, temperature, rho, failed, pos, pairs_dev, pair_index = ctx.saved_tensors
+        seg_params, kab, phi, temperature, rho, failed, pos, pairs_dev, pair_index, order = ctx.saved_tensors
         n = temperature.shape[0]
         g = g_val.contiguous()
         need_seg, need_kab, need_phi, need_t = ctx.needs_input_grad[:4]
@@ -140,7 +152,7 @@ class _GcPoint(torch.autograd.Function):
                 "feos_dev_gc_point_bwd", _lib.ptr(pairs_dev), ctx.n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                 _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature), _lib.ptr(rho),
                 _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, ctx.bubble, _lib.ptr(g_seg), _lib.ptr(g_kab),
-                _lib.ptr(g_phi), _lib.ptr(g_t), _stream(),
+                _lib.ptr(g_phi), _lib.ptr(g_t), _lib.ptr(order), _stream(),
             )
         if need_kab and g_kab is None:
             g_kab = torch.zeros_like(kab)

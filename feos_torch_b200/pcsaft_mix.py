@@ -19,20 +19,31 @@ class _MixPoint(torch.autograd.Function):
         rho = torch.empty((n, 4), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
+        order = None
         with torch.cuda.device(dev):
+            if _lib.state_order_enabled(n):
+                # states with the same code path and neighbouring (T, x) share a warp (csrc/order.cuh)
+                def compute():
+                    o = torch.empty((n,), dtype=torch.int32, device=dev)
+                    _lib.timed_call("feos_dev_mix_point_order", _lib.ptr(params), _lib.ptr(temperature),
+                                    _lib.ptr(molefracs), n, _lib.ptr(o), _stream())
+                    return o
+                order = _lib.cached_order("mix", temperature, molefracs, compute)
             _lib.timed_call(
                 "feos_dev_mix_point_fwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(molefracs), n,
-                int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None, _stream(),
+                int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None, _lib.ptr(order), _stream(),
             )
             out, pos = compact(failed, val)
-        ctx.save_for_backward(params, kij, temperature, rho, failed, pos)
+        # the backward kernel runs no iteration: the order only pays where code paths are mixed, and costs
+        # scattered gradient writes otherwise -- it keeps the input order
+        ctx.save_for_backward(params, kij, temperature, rho, failed, pos, None)
         ctx.bubble = int(bubble)
         ctx.mark_non_differentiable(rho, failed)
         return out, failed, rho
 
     @staticmethod
     def backward(ctx, g_val, _g_failed, _g_rho):
-        params, kij, temperature, rho, failed, pos = ctx.saved_tensors
+        params, kij, temperature, rho, failed, pos, order = ctx.saved_tensors
         n = temperature.shape[0]
         g = g_val.contiguous()
         need_p, need_k, need_t = ctx.needs_input_grad[:3]
@@ -43,7 +54,7 @@ class _MixPoint(torch.autograd.Function):
             _lib.timed_call(
                 "feos_dev_mix_point_bwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(rho),
                 _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, ctx.bubble, _lib.ptr(gp), _lib.ptr(gk), _lib.ptr(gt),
-                _stream(),
+                _lib.ptr(order), _stream(),
             )
         return gp, gk, gt, None, None
 

@@ -200,6 +200,27 @@ def compact(failed, values, out_cols=None):
     return out[:k], pos
 
 
+def _state_order(params, temperature):
+    """Permutation that puts states of the same code path and similar (m, T / T_c) into one warp
+    (csrc/order.cuh), for batches large enough to be throughput-bound; ``None`` = input order.  Not used with
+    chunked host uploads (every chunk is launched on its own rows as soon as it has arrived)."""
+    n = temperature.shape[0]
+    if not _lib.state_order_enabled(n):
+        return None
+
+    def compute():
+        # associating states: their T_c is far from the key's estimate, so the order does not align their
+        # iteration counts, and the work-queue kernel (input order) is the faster one (C3: 7.6 vs 10.0 ms per
+        # 10 M states).  One host synchronisation per data set; the answer is cached with the order.
+        p = params.detach()
+        if bool(((p[:, 4] != 0) & (p[:, 5] != 0) & ((p[:, 6] + p[:, 7]) > 0)).any()):
+            return None
+        o = torch.empty((n,), dtype=torch.int32, device=params.device)
+        _lib.timed_call("feos_dev_pure_order", _lib.ptr(params), _lib.ptr(temperature), n, _lib.ptr(o), _stream())
+        return o
+    return _lib.cached_order("pure", params, temperature, compute)
+
+
 class _PureVle(torch.autograd.Function):
     """which = 0: vapor pressure [Pa]; which = 1: saturated liquid density [kmol/m^3].
     Returns (compacted values [n_ok], failed [n] uint8, rho [n, 2])."""
@@ -213,11 +234,13 @@ class _PureVle(torch.autograd.Function):
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
         ch = _chunks_of(params)
         with torch.cuda.device(dev):
+            order = _state_order(params, temperature) if ch is None else None
+
             def launch(a, b):
                 _lib.timed_call(
                     "feos_dev_pure_vle_fwd", _off(params, a), _off(temperature, a), b - a, _off(rho, a),
                     _off(val, a) if which == 0 else None, _off(val, a) if which == 1 else None,
-                    _off(failed, a), None, _stream(),
+                    _off(failed, a), None, _lib.ptr(order), _stream(),
                 )
             _launch_chunked(params, zip(ch.bounds, ch.events) if ch else [((0, n), None)], launch)
             out, pos = compact(failed, val)
@@ -260,10 +283,12 @@ class _PureRhoTp(torch.autograd.Function):
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
         ch = _chunks_of(params)
         with torch.cuda.device(dev):
+            order = _state_order(params, temperature) if ch is None else None
+
             def launch(a, b):
                 _lib.timed_call(
                     "feos_dev_pure_rho_tp_fwd", _off(params, a), _off(temperature, a), _off(pressure, a), b - a,
-                    _off(rho, a), _off(val, a), _off(failed, a), None, _stream(),
+                    _off(rho, a), _off(val, a), _off(failed, a), None, _lib.ptr(order), _stream(),
                 )
             _launch_chunked(params, zip(ch.bounds, ch.events) if ch else [((0, n), None)], launch)
             out, pos = compact(failed, val)

@@ -52,6 +52,17 @@ int feos_dev_compact(const uint8_t* failed, int64_t n, int32_t* pos, int64_t* n_
 /* pure component: PcSaft.vapor_pressure / PcSaft.liquid_density                               */
 /* ------------------------------------------------------------------------------------------ */
 
+/* State order of the iterative (forward) kernels.  One thread solves one state, so a warp runs as long as its
+ * slowest lane; the forward kernels take an optional permutation `order` [n] (thread t works on state order[t],
+ * NULL = input order) that puts states with the same code path (dipole / association terms, GC molecule pair)
+ * and neighbouring reduced temperature (and composition) into the same warp: a key kernel + one radix sort of
+ * (key, index) pairs (csrc/order.cuh).  Results do not depend on the order.  No counterpart in the reference
+ * (rayon schedules states one by one, src/pcsaft.rs:86-92); the feos_host_* entry points apply it themselves
+ * to batches of >= 16384 states.
+ *   params [n,8], temperature [n]     in
+ *   order [n]   permutation of 0 .. n-1, keyed on (code path, chain length bin, T / T_c estimate)   out */
+int feos_dev_pure_order(const double* params, const double* temperature, int64_t n, int32_t* order, void* stream);
+
 /* Pure-component vapour-liquid equilibrium at T.
  * Replaces PyPcSaft::vapor_pressure -> vapor_pressure_ (src/pcsaft.rs:19-26, :82-103) and fuses the
  * Newton-step property formulas of PcSaftPure.vapor_pressure / equilibrium_liquid_density
@@ -61,10 +72,11 @@ int feos_dev_compact(const uint8_t* failed, int64_t n, int32_t* pos, int64_t* n_
  *   vapor_pressure [n] in Pa            (may be NULL)    out
  *   liquid_density [n] in kmol/m^3      (may be NULL)    out  (saturated liquid density)
  *   failed [n]                                           out
- *   evals [n]  Helmholtz evaluations used (may be NULL)  out  (roofline accounting) */
+ *   evals [n]  Helmholtz evaluations used (may be NULL)  out  (roofline accounting)
+ *   order [n]  state order from feos_dev_pure_order (may be NULL)  in */
 int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64_t n, double* rho,
                           double* vapor_pressure, double* liquid_density, uint8_t* failed, int32_t* evals,
-                          void* stream);
+                          const int32_t* order, void* stream);
 
 /* Gradient of  sum_i g_vp[i] * vapor_pressure[i] + g_rho[i] * liquid_density[i]  with respect to the
  * parameters and the temperature at the converged densities (implicit-function theorem); replaces
@@ -81,7 +93,7 @@ int feos_dev_pure_vle_bwd(const double* params, const double* temperature, const
  *   rho [n] converged density in 1/A^3, liquid_density [n] in kmol/m^3 (may be NULL) */
 int feos_dev_pure_rho_tp_fwd(const double* params, const double* temperature, const double* pressure,
                              int64_t n, double* rho, double* liquid_density, uint8_t* failed, int32_t* evals,
-                             void* stream);
+                             const int32_t* order, void* stream);
 
 /* Gradient of sum_i g[i] * liquid_density[i] w.r.t. parameters, T and p (any output may be NULL);
  * `pos` as above. */
@@ -117,22 +129,34 @@ int feos_host_pcsaft_liquid_density(const double* params, const double* temperat
 /* binary mixture with k_ij: PcSaft.bubble_point / PcSaft.dew_point                            */
 /* ------------------------------------------------------------------------------------------ */
 
+/* State order of the bubble / dew kernels (see feos_dev_pure_order), keyed on (code path, T / eps_bar bin, x).
+ *   params [n,2,8], temperature [n], molefracs [n]      in
+ *   order [n]   permutation of 0 .. n-1                  out */
+int feos_dev_mix_point_order(const double* params, const double* temperature, const double* molefracs, int64_t n,
+                             int32_t* order, void* stream);
+/*   pair_index [n] (state -> molecule pair, 0 <= pair_index < n_pairs), temperature [n], molefracs [n];
+ *   pair_only != 0: grouped by molecule pair, input order inside a pair (for the backward kernel, which runs
+ *   no iteration: only the code path matters and neighbouring states keep its memory accesses local) */
+int feos_dev_gc_point_order(const int32_t* pair_index, int32_t n_pairs, const double* temperature,
+                            const double* molefracs, int64_t n, int pair_only, int32_t* order, void* stream);
+
 /* Binary bubble (bubble = 1, `molefracs` = liquid x_1) or dew (bubble = 0, vapour y_1) point at T.
  * Replaces PyPcSaft::bubble_point / dew_point -> bubble_point_ / dew_point_ (src/pcsaft.rs:44-79,
  * :150-214) and fuses the Newton-step pressure of PcSaftMix.bubble_point / dew_point
  * (feos_torch/pcsaft_mix.py:422-468).
  *   params [n,2,8], kij [n,2] = (k_ij, eps_AiBj; 0 = combining rule), temperature [n], molefracs [n]
  *   rho [n,4] = (rho_V1, rho_V2, rho_L1, rho_L2) in 1/A^3 (filter_binary order, src/pcsaft.rs:225-228)
- *   pressure [n] in Pa (may be NULL), failed [n], evals [n] (may be NULL) */
+ *   pressure [n] in Pa (may be NULL), failed [n], evals [n] (may be NULL), order [n] (may be NULL, see above) */
 int feos_dev_mix_point_fwd(const double* params, const double* kij, const double* temperature,
                            const double* molefracs, int64_t n, int bubble, double* rho, double* pressure,
-                           uint8_t* failed, int32_t* evals, void* stream);
+                           uint8_t* failed, int32_t* evals, const int32_t* order, void* stream);
 
 /* Gradient of sum_i g[i] * pressure[i] w.r.t. params [n,2,8], kij [n,2] and T [n] (any may be NULL);
  * replaces torch autograd through pcsaft_mix.py:435-444 / :459-468.  `pos` as for the pure path. */
 int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
                            const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble,
-                           double* grad_params, double* grad_kij, double* grad_temperature, void* stream);
+                           double* grad_params, double* grad_kij, double* grad_temperature, const int32_t* order,
+                           void* stream);
 
 /* a, p/kT, mu_i^res/kT [n,2], v_i [n,2] at (T, rho [n,2]): PcSaftMix.derivatives (pcsaft_mix.py:395-420). */
 int feos_dev_mix_state(const double* params, const double* kij, const double* temperature, const double* density,
@@ -179,12 +203,13 @@ typedef struct feos_gc_pair {
  *   pairs [n_pairs], seg_params [n_seg,8] (rows as the PC-SAFT parameter rows), kab [n_rec] values of
  *   the binary segment records, pair_index [n] (state -> pair), phi [n,2] (may be NULL = 1),
  *   temperature [n].  Device pointers for feos_dev_*, host pointers for feos_host_*.
+ *   order [n] (may be NULL): state order from feos_dev_gc_point_order, see feos_dev_mix_point_order.
  * Replaces PyGcPcSaft::bubble_point / dew_point -> bubble_point_ / dew_point_ (src/gc_pcsaft.rs:71-99,
  * :103-171) fused with GcPcSaftMix.bubble_point / dew_point (feos_torch/gc_pcsaft.py:470-512). */
 int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* molefracs, int64_t n, int bubble, double* rho,
-                          double* pressure, uint8_t* failed, int32_t* evals, void* stream);
+                          double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order, void* stream);
 
 /* Gradient of sum_i g[i] * pressure[i].  grad_seg_params [n_seg,8] and grad_kab [n_rec] are shared by
  * all states and are ACCUMULATED into (zero them first); grad_phi [n,2] and grad_temperature [n] are
@@ -193,7 +218,7 @@ int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* rho, const uint8_t* failed, const int32_t* pos,
                           const double* g, int64_t n, int bubble, double* grad_seg_params, double* grad_kab,
-                          double* grad_phi, double* grad_temperature, void* stream);
+                          double* grad_phi, double* grad_temperature, const int32_t* order, void* stream);
 
 /* a, p/kT, mu_i, v_i at (T, rho [n,2]): GcPcSaftMix.derivatives (gc_pcsaft.py:443-468). */
 int feos_dev_gc_state(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,

@@ -525,3 +525,29 @@ void sim_mix_eval_pair(const double* params, const double* kij, const double* T,
   }
 }
 }
+
+// ---- sort keys of the bubble / dew state order (csrc/order.cuh) ------------------------------------------
+#include "../../feos_torch_b200/csrc/order.cuh"
+
+extern "C" {
+void sim_mix_order_key(const double* params, const double* T, const double* z, int64_t n, uint64_t* keys) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16];
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    keys[i] = mix_order_key(prm, T[i], z[i]);
+  }
+}
+void sim_gc_order_key(const int32_t* pair, const double* T, const double* z, int64_t n, uint64_t* keys) {
+  for (int64_t i = 0; i < n; ++i) keys[i] = gc_order_key(pair[i], T[i], z[i]);
+}
+int sim_order_bits(int which) { return which == 0 ? kMixOrderBits : kOrderStateBits; }
+}
+
+extern "C" void sim_pure_order_key(const double* params, const double* T, int64_t n, uint64_t* keys) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[8];
+    for (int k = 0; k < 8; ++k) prm[k] = params[8 * i + k];
+    keys[i] = feos::pure_order_key(prm, T[i]);
+  }
+}
+extern "C" int sim_pure_order_bits() { return feos::kPureOrderBits; }

@@ -211,3 +211,29 @@ def mix_eval_pair(params, kij, T, rho):
 def mix_bwd_closed(on):
     """sim_mix_point_bwd: closed-form adjoints + reverse sweep (what the kernel runs for non-associating states) or the dual passes."""
     lib().sim_mix_bwd_closed(ctypes.c_int(int(on)))
+
+
+def mix_order_key(params, T, z):
+    params, T, z = c64(params), c64(T), c64(z)
+    keys = np.empty(T.shape[0], dtype=np.uint64)
+    lib().sim_mix_order_key(_p(params), _p(T), _p(z), ctypes.c_int64(T.shape[0]), _p(keys))
+    return keys
+
+
+def gc_order_key(pair, T, z):
+    pair = np.ascontiguousarray(pair, dtype=np.int32)
+    T, z = c64(T), c64(z)
+    keys = np.empty(T.shape[0], dtype=np.uint64)
+    lib().sim_gc_order_key(_p(pair), _p(T), _p(z), ctypes.c_int64(T.shape[0]), _p(keys))
+    return keys
+
+
+def order_bits(which):
+    return int(lib().sim_order_bits(which))
+
+
+def pure_order_key(params, T):
+    params, T = c64(params), c64(T)
+    keys = np.empty(T.shape[0], dtype=np.uint64)
+    lib().sim_pure_order_key(_p(params), _p(T), ctypes.c_int64(T.shape[0]), _p(keys))
+    return keys, int(lib().sim_pure_order_bits())

@@ -46,7 +46,7 @@ def test_version_and_error_text(built):
 def test_argument_errors_do_not_cross_abi(built):
     lib = built.load()
     # n < 0 is rejected before any CUDA call; the text is retrievable and nothing is thrown
-    rc = lib.feos_dev_pure_vle_fwd(None, None, -1, None, None, None, None, None, None)
+    rc = lib.feos_dev_pure_vle_fwd(None, None, -1, None, None, None, None, None, None, None)
     assert rc == -1
     assert b"invalid argument" in lib.feos_b200_last_error()
     with pytest.raises(built.FeosB200Error):

@@ -153,3 +153,49 @@ def test_full_size_c5(ft, golden_gc):
     _, pL, muL, _ = m3.derivatives(T[:k], r[:, 2:4].contiguous())
     assert ((pV - pL).abs() / r[:, 2:4].sum(dim=1))[ok].max().item() < 1e-12
     assert (muV + r[:, 0:2].log() - muL - r[:, 2:4].log())[ok].abs().max().item() < 1e-9
+
+
+def test_state_order_is_a_permutation_and_changes_no_result(ft, golden_gc, monkeypatch):
+    """csrc/order.cuh for the GC path: states are solved grouped by molecule pair, then (T bin, x).  Complete
+    permutation; pressures, masks, densities and per-state gradients bit-identical to the input-order run; the
+    shared k_ab gradient (atomic sums, order-dependent rounding) to 1e-12."""
+    from feos_torch_b200 import _lib
+
+    n = 100_000
+    g = torch.Generator().manual_seed(12)
+    ident, par = seg_args(golden_gc)
+    which = torch.randint(0, 8, (n,), generator=g).tolist()  # rows 5-7 associate
+    segs = [cases.GC_SEGMENTS[w] for w in which]
+    bonds = [cases.GC_BONDS[w] for w in which]
+    T = (150.0 + 100.0 * torch.rand(n, generator=g, dtype=F64)).cuda().requires_grad_(True)
+    z = (0.05 + 0.9 * torch.rand(n, generator=g, dtype=F64)).cuda()
+    p0 = torch.full((n,), 1e5, dtype=F64, device="cuda")
+    phi = torch.tensor([cases.GC_PHI], dtype=F64, device="cuda").expand(n, 2).contiguous().requires_grad_(True)
+    kab = torch.tensor(0.03, dtype=F64, device="cuda", requires_grad=True)
+    model = ft.GcPcSaftMix(ident, par, segs, bonds, [("CH3", "CH=O", kab), (">CH", "HCOO", -0.01)], phi)
+
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    for pair_only in (0, 1):
+        _lib.call("feos_dev_gc_point_order", _lib.ptr(model._pair_index), model._n_pairs, _lib.ptr(T.detach()), _lib.ptr(z), n,
+                  pair_only, _lib.ptr(order), torch.cuda.current_stream().cuda_stream)
+        assert torch.equal(torch.sort(order.long()).values, torch.arange(n, device="cuda"))
+        sorted_pairs = model._pair_index[order.long()]
+        assert (sorted_pairs.diff() >= 0).all()
+        if pair_only:  # stable: input order inside a pair
+            assert (order.long().diff()[sorted_pairs.diff() == 0] > 0).all()
+
+    def run(bubble):
+        T.grad = phi.grad = kab.grad = None
+        p, nans = (model.bubble_point if bubble else model.dew_point)(T, z, p0)
+        p.sum().backward()
+        return p.detach().clone(), nans.clone(), T.grad.clone(), phi.grad.clone(), kab.grad.clone()
+
+    for bubble in (True, False):
+        monkeypatch.setenv("FEOS_B200_STATE_ORDER", "1")
+        a = run(bubble)
+        monkeypatch.setenv("FEOS_B200_STATE_ORDER", "0")
+        b = run(bubble)
+        assert (~a[1]).float().mean().item() > 0.5
+        for x, y in zip(a[:4], b[:4]):
+            assert torch.equal(x, y)
+        assert abs(a[4].item() - b[4].item()) <= 1e-12 * abs(b[4].item())

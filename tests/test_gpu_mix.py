@@ -178,3 +178,46 @@ def test_edge_cases(ft):
     # host tensors in, host tensors out
     p2, _ = ft.PcSaftMix(P.cpu(), K.cpu()).bubble_point(T.cpu(), z.cpu(), torch.full((3,), 1e5, dtype=F64))
     assert not p2.is_cuda and torch.equal(p2, p.cpu())
+
+
+def test_state_order_is_a_permutation_and_changes_no_result(ft, monkeypatch):
+    """csrc/order.cuh: the bubble / dew kernels solve large batches in a (code path, T bin, x) order.  The
+    permutation must be complete, and pressures, masks and per-state gradients must be bit-identical to the
+    input-order run (every state is computed by the same instructions either way)."""
+    from feos_torch_b200 import _lib
+
+    n = 200_000
+    g = torch.Generator().manual_seed(11)
+    rows = torch.tensor([cases.MIX_DEW["params"][0], cases.MIX_DEW["params"][1],
+                         [1.5, 3.4, 230.0, 2.0, 0, 0, 0, 0], [1.2, 3.3, 220.0, 0, 0.03, 2000.0, 1, 1]], dtype=F64)
+    first = torch.randint(0, 4, (n,), generator=g)
+    second = torch.randint(0, 4, (n,), generator=g)
+    P = torch.stack([rows[first], rows[second]], dim=1).cuda().requires_grad_(True)
+    K = torch.tensor([[-0.05, 0.0]], dtype=F64).expand(n, 2).contiguous().cuda().requires_grad_(True)
+    T = (120.0 + 120.0 * torch.rand(n, generator=g, dtype=F64)).cuda()
+    z = (0.02 + 0.96 * torch.rand(n, generator=g, dtype=F64)).cuda()
+    p0 = torch.full((n,), 1e5, dtype=F64, device="cuda")
+
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.call("feos_dev_mix_point_order", _lib.ptr(P.detach()), _lib.ptr(T), _lib.ptr(z), n, _lib.ptr(order),
+              torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(torch.sort(order.long()).values, torch.arange(n, device="cuda"))
+    # grouped by code path: dipolar / associating flags are constant over long runs of the order
+    flags = ((P.detach()[:, :, 3] != 0).any(dim=1).long() + 2 * (P.detach()[:, 0, 6] > 0).long() + 4 * (P.detach()[:, 1, 6] > 0).long())
+    assert (flags[order.long()].diff() != 0).sum().item() <= 8
+
+    def run(bubble):
+        P.grad = K.grad = None
+        m = ft.PcSaftMix(P, K)
+        p, nans = (m.bubble_point if bubble else m.dew_point)(T, z, p0)
+        p.sum().backward()
+        return p.detach().clone(), nans.clone(), P.grad.clone(), K.grad.clone()
+
+    for bubble in (True, False):
+        monkeypatch.setenv("FEOS_B200_STATE_ORDER", "1")
+        a = run(bubble)
+        monkeypatch.setenv("FEOS_B200_STATE_ORDER", "0")
+        b = run(bubble)
+        assert 0.3 < (~a[1]).float().mean().item()  # a mixed grid: converged and failed states both occur
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)

@@ -233,9 +233,13 @@ def test_liquid_density_full_size(ft):
     assert rel(rho_n / (1e3 * 6.02214076e23 * 1e-30), rho[:1000].detach().cpu()) < 1e-12
 
 
-def test_host_pipeline_matches_device_path(ft):
+def test_host_pipeline_matches_device_path(ft, monkeypatch):
     """Pinned host tensors in -> chunked, stream-pipelined copies and launches; results and gradients must be
-    bit-identical to the device-resident path (same kernels, same inputs), with failed rows in the middle."""
+    bit-identical to the device-resident path (same kernels, same inputs), with failed rows in the middle.
+    The chunked path launches every chunk in input order on the work-queue kernel, so the device-resident
+    run is pinned to the same kernel here (in state order it would use the one-thread-per-state kernel, whose
+    results agree to round-off, not bit for bit)."""
+    monkeypatch.setenv("FEOS_B200_STATE_ORDER", "0")
     n = 700_000
     P, T, tau = _c2_grid(n, 9)
     T[1000:1100] = T[1000:1100] / tau[1000:1100] * 1.4
@@ -292,3 +296,73 @@ def test_edge_cases(ft):
     # all states failed
     nans, vp = ft.PcSaftPure(row.detach().repeat(4, 1)).vapor_pressure(torch.full((4,), 2000.0, dtype=F64, device="cuda"))
     assert nans.all() and vp.numel() == 0
+
+
+def test_state_order_is_a_permutation_and_changes_no_result(ft, monkeypatch):
+    """csrc/order.cuh for the pure path: large batches are solved in a (code path, chain length bin, T / T_c)
+    order.  Complete permutation, grouped by code path; with the kernel variant fixed, pressures, densities,
+    masks and gradients are bit-identical to the input-order run (every state is computed by the same
+    instructions either way)."""
+    from feos_torch_b200 import _lib
+
+    n = 300_000
+    P0, T0, _ = _c2_grid(n // 2, 21)
+    P1, T1, _ = _c2_grid(n - n // 2, 22, assoc=True)
+    g = torch.Generator().manual_seed(23)
+    perm = torch.randperm(n, generator=g)
+    P = torch.cat([P0, P1])[perm].contiguous()
+    P[::7, 3] = 1.8  # every seventh state dipolar
+    T = torch.cat([T0, T1])[perm].contiguous()
+    T[::50] *= 3.0  # a super-critical slice: failed states
+    P, T = P.cuda(), T.cuda()
+    p = torch.exp(torch.empty(n, dtype=F64).uniform_(np.log(1e5), np.log(1e7), generator=g)).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    order = torch.empty(n, dtype=torch.int32, device="cuda")
+    _lib.call("feos_dev_pure_order", _lib.ptr(P), _lib.ptr(T), n, _lib.ptr(order), stream)
+    assert torch.equal(torch.sort(order.long()).values, torch.arange(n, device="cuda"))
+    flags = (P[:, 3] != 0).long() + 2 * (P[:, 6] > 0).long()
+    assert (flags[order.long()].diff() != 0).sum().item() <= 3
+
+    # C ABI, all code paths (associating states included), both kernel variants: order vs input order
+    for variant in ("loop", "queue"):
+        monkeypatch.setenv("FEOS_B200_PURE_VLE_KERNEL", variant)
+        res = []
+        for o in (order, None):
+            rho = torch.empty((n, 2), dtype=F64, device="cuda")
+            vp, rl, rt = (torch.empty(n, dtype=F64, device="cuda") for _ in range(3))
+            f1, f2 = (torch.empty(n, dtype=torch.uint8, device="cuda") for _ in range(2))
+            rho2 = torch.empty(n, dtype=F64, device="cuda")
+            _lib.call("feos_dev_pure_vle_fwd", _lib.ptr(P), _lib.ptr(T), n, _lib.ptr(rho), _lib.ptr(vp), _lib.ptr(rl),
+                      _lib.ptr(f1), None, _lib.ptr(o), stream)
+            _lib.call("feos_dev_pure_rho_tp_fwd", _lib.ptr(P), _lib.ptr(T), _lib.ptr(p), n, _lib.ptr(rho2), _lib.ptr(rt),
+                      _lib.ptr(f2), None, _lib.ptr(o), stream)
+            res.append((rho, vp, rl, f1, rho2, rt, f2))
+        assert 0.5 < (res[0][3] == 0).float().mean().item() < 1.0
+        for x, y in zip(*res):
+            assert torch.equal(x.nan_to_num(nan=-1.0), y.nan_to_num(nan=-1.0))
+
+    # public API on the non-associating half (the wrapper orders such batches): values, masks, gradients
+    keep = (P[:, 6] == 0)
+    Pn, Tn, pn = P[keep].contiguous().requires_grad_(True), T[keep].contiguous(), p[keep].contiguous()
+    monkeypatch.setenv("FEOS_B200_PURE_VLE_KERNEL", "loop")
+
+    def run():
+        out = []
+        m = ft.PcSaftPure(Pn)
+        for call in (lambda: m.vapor_pressure(Tn), lambda: m.equilibrium_liquid_density(Tn), lambda: m.liquid_density(Tn, pn)):
+            Pn.grad = None
+            nans, val = call()
+            val.sum().backward()
+            out += [nans.clone(), val.detach().clone(), Pn.grad.clone()]
+        return out
+
+    launches = _lib.launch_count()
+    monkeypatch.setenv("FEOS_B200_STATE_ORDER", "1")
+    a = run()
+    ordered_launches = _lib.launch_count() - launches
+    monkeypatch.setenv("FEOS_B200_STATE_ORDER", "0")
+    b = run()
+    assert ordered_launches > _lib.launch_count() - launches - ordered_launches  # the order kernels did run
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
