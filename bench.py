@@ -47,13 +47,6 @@ def make_workload(n, seed, device):
     params[:, 0], params[:, 1], params[:, 2] = m, sigma, eps
     T = tau * tc
     p = torch.exp(math.log(1e5) + r() * math.log(100.0))
-    key = os.environ.get("FEOS_BENCH_SORT")
-    if key:  # experiment
-        mb = ((m - 1.0) / 3.0 * 15.999).floor()
-        tb = ((tau - 0.5) / 1.0 * 31.999).floor()
-        k = {"tau": tau, "m": m, "mtau": mb * 10 + tau, "taum": tb * 10 + m}[key]
-        idx = torch.argsort(k)
-        params, T, p = params[idx].contiguous(), T[idx].contiguous(), p[idx].contiguous()
     return params, T, p
 
 
@@ -187,8 +180,11 @@ class C2:
         evals = torch.zeros(n, dtype=torch.int32, device=self.dev)
         rho = torch.empty((n, 2), dtype=torch.float64, device=self.dev)
         failed = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        from feos_torch_b200.pcsaft_pure import _state_order
+
+        order = _state_order(self.params.detach(), self.T)  # the same order (hence kernel variant) as the timed calls
         _lib.call("feos_dev_pure_vle_fwd", _lib.ptr(self.params.detach()), _lib.ptr(self.T), n, _lib.ptr(rho), None, None,
-                  _lib.ptr(failed), _lib.ptr(evals), None, torch.cuda.current_stream().cuda_stream)
+                  _lib.ptr(failed), _lib.ptr(evals), _lib.ptr(order), torch.cuda.current_stream().cuda_stream)
         return evals.double().mean().item()
 
 
@@ -211,7 +207,7 @@ class C3:
     with the per-state T_c from `critical_temperature`."""
     name = "C3: PcSaftPure equilibrium_liquid_density fwd+bwd, synthetic 2B-associating (params,T) pairs"
     dominant = "feos_dev_pure_vle_fwd"
-    kernel = "pure_vle_fwd_kernel(+retry)"
+    kernel = "pure_vle_queue_kernel(+retry)"
     flops_per_eval = F_D2
     io_bytes_per_state = 64 + 8 + 16 + 8 + 1
     traffic_per_state = None
@@ -285,13 +281,6 @@ class C4:
         self.kij = torch.tensor([-0.1, 0.0], dtype=torch.float64, device=dev, requires_grad=True)
         self.T_h = ((0.6 + 0.25 * torch.rand(n, generator=g, dtype=torch.float64)) * 150 * 1.2757).pin_memory()
         self.z_h = (0.05 + 0.9 * torch.rand(n, generator=g, dtype=torch.float64)).pin_memory()
-        key = os.environ.get("FEOS_BENCH_SORT")
-        if key:  # experiment
-            tb = ((self.T_h - self.T_h.min()) / (self.T_h.max() - self.T_h.min()) * 31.999).floor()
-            zb = ((self.z_h - 0.05) / 0.9 * 31.999).floor()
-            k = {"T": self.T_h, "z": self.z_h, "Tz": tb * 2 + self.z_h, "zT": zb * 1000 + self.T_h}[key]
-            idx = torch.argsort(k)
-            self.T_h, self.z_h = self.T_h[idx].pin_memory(), self.z_h[idx].pin_memory()
         self.T, self.z = self.T_h.to(dev), self.z_h.to(dev)
         self.p0 = torch.full((n,), 1e5, dtype=torch.float64, device=dev)
         with torch.no_grad():
@@ -362,8 +351,6 @@ class C5:
         self.par = tuple(torch.tensor([table[i][k] for i in self.ident], dtype=torch.float64, device=dev) for k in range(8))
         g = torch.Generator().manual_seed(3000 + rank)
         which = torch.randint(0, 5, (n,), generator=g).tolist()
-        if os.environ.get("FEOS_BENCH_C5_SORTED"):
-            which = sorted(which)  # experiment: states grouped by molecule pair
         pairs = [(cases.GC_SEGMENTS[i], cases.GC_BONDS[i]) for i in range(5)]
         self.segs = [pairs[w][0] for w in which]
         self.bonds = [pairs[w][1] for w in which]
