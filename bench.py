@@ -182,7 +182,7 @@ class C2:
         failed = torch.empty(n, dtype=torch.uint8, device=self.dev)
         from feos_torch_b200.pcsaft_pure import _state_order
 
-        order = _state_order(self.params.detach(), self.T)  # the same order (hence kernel variant) as the timed calls
+        order = _state_order(self.params.detach(), self.T, (self.params, self.T))  # same order (hence kernel variant) as the timed calls
         _lib.call("feos_dev_pure_vle_fwd", _lib.ptr(self.params.detach()), _lib.ptr(self.T), n, _lib.ptr(rho), None, None,
                   _lib.ptr(failed), _lib.ptr(evals), _lib.ptr(order), torch.cuda.current_stream().cuda_stream)
         return evals.double().mean().item()
@@ -207,7 +207,7 @@ class C3:
     with the per-state T_c from `critical_temperature`."""
     name = "C3: PcSaftPure equilibrium_liquid_density fwd+bwd, synthetic 2B-associating (params,T) pairs"
     dominant = "feos_dev_pure_vle_fwd"
-    kernel = "pure_vle_queue_kernel(+retry)"
+    kernel = "pure_vle_fwd_kernel(+retry)"
     flops_per_eval = F_D2
     io_bytes_per_state = 64 + 8 + 16 + 8 + 1
     traffic_per_state = None

@@ -110,22 +110,26 @@ def state_order_enabled(n):
 
 
 # The order is a property of the data set: a fit loop solves the same (T, x) tensors every iteration, so the
-# permutation is kept for the last few (T, x) pairs, recognised by storage address + version counter.  ANY
-# permutation of 0 .. n-1 gives the same results, so a stale entry (memory reused for other values) can cost
-# speed but never correctness.
+# permutation is kept for the last few data sets, recognised by the IDENTITY of the caller's tensor objects (weak
+# references) and their version counters -- storage addresses are not enough: the caching allocator hands the
+# address of a freed temperature tensor to the next one, and a permutation built for other temperatures, while
+# still giving correct results (any permutation does), no longer aligns the iteration counts.
 _ORDER_CACHE = []
 _ORDER_CACHE_SIZE = 8
 
 
-def cached_order(kind, a, b, compute):
-    """``compute()`` -> int32 order tensor, memoised on (kind, tensors a and b)."""
-    key = (kind, a.data_ptr(), a._version, b.data_ptr(), b._version, a.shape[0], a.device)
-    for k, (e_key, order) in enumerate(_ORDER_CACHE):
-        if e_key == key:
+def cached_order(kind, tensors, compute):
+    """``compute()`` -> int32 order tensor (or None), memoised on (kind, identity + version of ``tensors``)."""
+    import weakref
+
+    versions = tuple(t._version for t in tensors)
+    _ORDER_CACHE[:] = [e for e in _ORDER_CACHE if all(r() is not None for r in e[1])]
+    for k, (e_kind, refs, e_versions, order) in enumerate(_ORDER_CACHE):
+        if e_kind == kind and e_versions == versions and len(refs) == len(tensors) and all(r() is t for r, t in zip(refs, tensors)):
             _ORDER_CACHE.insert(0, _ORDER_CACHE.pop(k))
             return order
     order = compute()
-    _ORDER_CACHE.insert(0, (key, order))
+    _ORDER_CACHE.insert(0, (kind, tuple(weakref.ref(t) for t in tensors), versions, order))
     del _ORDER_CACHE[_ORDER_CACHE_SIZE:]
     return order
 

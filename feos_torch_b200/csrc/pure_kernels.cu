@@ -63,7 +63,10 @@ __device__ __forceinline__ void store_vle(int64_t i, int st, double rho_l, doubl
   failed[i] = (st == kStatusOk) ? 0 : 1;
 }
 
-__global__ void __launch_bounds__(kBlock, 4)
+#ifndef FEOS_PURE_FWD_MINB
+#define FEOS_PURE_FWD_MINB 4
+#endif
+__global__ void __launch_bounds__(kBlock, FEOS_PURE_FWD_MINB)
 pure_vle_fwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature, int64_t n,
                     double* __restrict__ rho, double* __restrict__ vp, double* __restrict__ rleq,
                     uint8_t* __restrict__ failed, int32_t* __restrict__ evals, int32_t* __restrict__ retry_list,
@@ -346,14 +349,9 @@ struct DevBuf {
   T* as() { return (T*)p; }
 };
 
-// state order for the host entry points: large batches without associating states (see feos_dev_pure_vle_fwd);
-// buf stays NULL = input order otherwise
-int host_order(DevBuf& buf, const double* host_params, const double* params, const double* temperature, int64_t n) {
+// state order for the host entry points (large batches only; buf stays NULL = input order otherwise)
+int host_order(DevBuf& buf, const double* params, const double* temperature, int64_t n) {
   if (n < kOrderMinStates) return 0;
-  for (int64_t i = 0; i < n; ++i) {
-    const double* r = host_params + 8 * i;
-    if (r[4] != 0.0 && r[5] != 0.0 && r[6] + r[7] > 0.0) return 0;
-  }
   if (buf.alloc(4 * n)) {
     set_error("cudaMalloc failed for %lld states", (long long)n);
     return -2;
@@ -378,9 +376,8 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
   // FEOS_B200_PURE_VLE_KERNEL = "loop" (one thread per state) / "queue" (persistent work queue) for A/B runs.
   // Default: states in input order -> queue (1 M C2 states, ncu: 0.566 ms, 22.4 of 32 lanes active per
   // instruction; loop 0.572 ms, 16.9 lanes); states in the order of order.cuh -> loop (warps are homogeneous,
-  // so the queue's bookkeeping buys nothing: 0.40 ms against 0.49 ms, profiles/README.md).  The callers pass an
-  // order only for batches without associating states: their T_c is far from the key's estimate, the order does
-  // not align their iteration counts, and the loop kernel is slower on them (10 M C3 states: 10.0 vs 7.6 ms).
+  // so the queue's bookkeeping buys nothing: 0.40 ms against 0.49 ms; 10 M associating C3 states: 6.9 ms
+  // against 7.0 ms, and 7.6 ms for the queue in input order, profiles/README.md).
   const char* env = getenv("FEOS_B200_PURE_VLE_KERNEL");
   const int forced = !env ? -1 : (env[0] == 'l' ? 0 : (env[0] == 'q' ? 1 : -1));
   const int variant = forced >= 0 ? forced : (order ? 0 : 1);
@@ -485,7 +482,7 @@ int feos_host_pcsaft_vapor_pressure(const double* params, const double* temperat
   FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 64 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
   DevBuf dorder;
-  if (int rc = host_order(dorder, params, dp.as<double>(), dt.as<double>(), n)) return rc;
+  if (int rc = host_order(dorder, dp.as<double>(), dt.as<double>(), n)) return rc;
   int rc = feos_dev_pure_vle_fwd(dp.as<double>(), dt.as<double>(), n, drho.as<double>(), nullptr, nullptr,
                                  dfail.as<uint8_t>(), nullptr, dorder.as<int32_t>(), nullptr);
   if (rc) return rc;
@@ -522,7 +519,7 @@ int feos_host_pcsaft_liquid_density(const double* params, const double* temperat
   FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dpr.p, pressure, 8 * n, cudaMemcpyHostToDevice, 0));
   DevBuf dorder;
-  if (int rc = host_order(dorder, params, dp.as<double>(), dt.as<double>(), n)) return rc;
+  if (int rc = host_order(dorder, dp.as<double>(), dt.as<double>(), n)) return rc;
   int rc = feos_dev_pure_rho_tp_fwd(dp.as<double>(), dt.as<double>(), dpr.as<double>(), n, drho.as<double>(), nullptr,
                                     dfail.as<uint8_t>(), nullptr, dorder.as<int32_t>(), nullptr);
   if (rc) return rc;

@@ -106,25 +106,15 @@ def _check_association(pairs, seg_params):
 
 class _GcPoint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, seg_params, kab, phi, temperature, molefracs, bubble, tables):
+    def forward(ctx, seg_params, kab, phi, temperature, molefracs, bubble, tables, orders):
         pairs_dev, pair_index, n_pairs = tables
+        order, order_bwd = orders
         n = temperature.shape[0]
         dev = temperature.device
         rho = torch.empty((n, 4), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
-        order = order_bwd = None
         with torch.cuda.device(dev):
-            if _lib.state_order_enabled(n):
-                # forward: states of one molecule pair and neighbouring (T, x) share a warp (csrc/order.cuh);
-                # backward (no iteration): grouped by pair only, input order inside a pair keeps its accesses local
-                def compute(pair_only):
-                    o = torch.empty((n,), dtype=torch.int32, device=dev)
-                    _lib.timed_call("feos_dev_gc_point_order", _lib.ptr(pair_index), n_pairs, _lib.ptr(temperature),
-                                    _lib.ptr(molefracs), n, pair_only, _lib.ptr(o), _stream())
-                    return o
-                order = _lib.cached_order(("gc", pair_index.data_ptr()), temperature, molefracs, lambda: compute(0))
-                order_bwd = _lib.cached_order(("gc-pair", pair_index.data_ptr()), temperature, molefracs, lambda: compute(1))
             _lib.timed_call(
                 "feos_dev_gc_point_fwd", _lib.ptr(pairs_dev), n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                 _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
@@ -156,7 +146,7 @@ class _GcPoint(torch.autograd.Function):
             )
         if need_kab and g_kab is None:
             g_kab = torch.zeros_like(kab)
-        return g_seg, g_kab, g_phi, g_t, None, None, None
+        return g_seg, g_kab, g_phi, g_t, None, None, None, None
 
 
 class _GcState(torch.autograd.Function):
@@ -237,7 +227,21 @@ class GcPcSaftMix:
         t = _prep(temperature, self._dev)
         z = _prep(molefracs.detach(), self._dev)
         tables = (self._pairs, self._pair_index, self._n_pairs)
-        val, failed, _ = _GcPoint.apply(self._seg, self._kab, self._phi, t, z, bubble, tables)
+        orders = (None, None)
+        n = t.shape[0]
+        if _lib.state_order_enabled(n):
+            # forward: states of one molecule pair and neighbouring (T, x) share a warp (csrc/order.cuh); backward
+            # (no iteration): grouped by pair only, input order inside a pair keeps its accesses local.  The data
+            # set is recognised by the caller's (T, x) tensor objects in the next iteration of a fit loop.
+            def compute(pair_only):
+                o = torch.empty((n,), dtype=torch.int32, device=self._dev)
+                with torch.cuda.device(self._dev):
+                    _lib.timed_call("feos_dev_gc_point_order", _lib.ptr(self._pair_index), self._n_pairs, _lib.ptr(t),
+                                    _lib.ptr(z), n, pair_only, _lib.ptr(o), _stream())
+                return o
+            key = (self._pair_index, temperature, molefracs)
+            orders = (_lib.cached_order("gc", key, lambda: compute(0)), _lib.cached_order("gc-pair", key, lambda: compute(1)))
+        val, failed, _ = _GcPoint.apply(self._seg, self._kab, self._phi, t, z, bubble, tables, orders)
         return self._back(val), self._back(failed.bool())
 
     def bubble_point(self, temperature, liquid_molefracs, pressure):

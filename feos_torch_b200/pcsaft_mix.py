@@ -13,22 +13,13 @@ from .pcsaft_pure import _back, _cuda_device, _prep, _stream, compact
 
 class _MixPoint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, params, kij, temperature, molefracs, bubble):
+    def forward(ctx, params, kij, temperature, molefracs, bubble, order):
         n = temperature.shape[0]
         dev = params.device
         rho = torch.empty((n, 4), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
-        order = None
         with torch.cuda.device(dev):
-            if _lib.state_order_enabled(n):
-                # states with the same code path and neighbouring (T, x) share a warp (csrc/order.cuh)
-                def compute():
-                    o = torch.empty((n,), dtype=torch.int32, device=dev)
-                    _lib.timed_call("feos_dev_mix_point_order", _lib.ptr(params), _lib.ptr(temperature),
-                                    _lib.ptr(molefracs), n, _lib.ptr(o), _stream())
-                    return o
-                order = _lib.cached_order("mix", temperature, molefracs, compute)
             _lib.timed_call(
                 "feos_dev_mix_point_fwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(molefracs), n,
                 int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None, _lib.ptr(order), _stream(),
@@ -56,7 +47,7 @@ class _MixPoint(torch.autograd.Function):
                 _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, ctx.bubble, _lib.ptr(gp), _lib.ptr(gk), _lib.ptr(gt),
                 _lib.ptr(order), _stream(),
             )
-        return gp, gk, gt, None, None
+        return gp, gk, gt, None, None, None
 
 
 class _MixState(torch.autograd.Function):
@@ -132,7 +123,19 @@ class PcSaftMix:
     def _point(self, temperature, molefracs, bubble):
         t = _prep(temperature, self._dev)
         z = _prep(molefracs.detach(), self._dev)
-        val, failed, _ = _MixPoint.apply(self._params, self._kij, t, z, bubble)
+        order = None
+        n = t.shape[0]
+        if _lib.state_order_enabled(n):
+            # states with the same code path and neighbouring (T, x) share a warp (csrc/order.cuh); the data set
+            # is recognised by the caller's (T, x) tensor objects in the next iteration of a fit loop
+            def compute():
+                o = torch.empty((n,), dtype=torch.int32, device=self._dev)
+                with torch.cuda.device(self._dev):
+                    _lib.timed_call("feos_dev_mix_point_order", _lib.ptr(self._params), _lib.ptr(t), _lib.ptr(z), n,
+                                    _lib.ptr(o), _stream())
+                return o
+            order = _lib.cached_order("mix", (temperature, molefracs), compute)
+        val, failed, _ = _MixPoint.apply(self._params, self._kij, t, z, bubble, order)
         return self._back(val), self._back(failed.bool())
 
     def bubble_point(self, temperature, liquid_molefracs, pressure):

@@ -200,25 +200,21 @@ def compact(failed, values, out_cols=None):
     return out[:k], pos
 
 
-def _state_order(params, temperature):
+def _state_order(params, temperature, key):
     """Permutation that puts states of the same code path and similar (m, T / T_c) into one warp
     (csrc/order.cuh), for batches large enough to be throughput-bound; ``None`` = input order.  Not used with
-    chunked host uploads (every chunk is launched on its own rows as soon as it has arrived)."""
+    chunked host uploads (every chunk is launched on its own rows as soon as it has arrived).  ``key``: the
+    caller's own tensor objects, by which the data set is recognised in the next iteration of a fit loop."""
     n = temperature.shape[0]
-    if not _lib.state_order_enabled(n):
+    if not _lib.state_order_enabled(n) or _chunks_of(params) is not None:
         return None
 
     def compute():
-        # associating states: their T_c is far from the key's estimate, so the order does not align their
-        # iteration counts, and the work-queue kernel (input order) is the faster one (C3: 7.6 vs 10.0 ms per
-        # 10 M states).  One host synchronisation per data set; the answer is cached with the order.
-        p = params.detach()
-        if bool(((p[:, 4] != 0) & (p[:, 5] != 0) & ((p[:, 6] + p[:, 7]) > 0)).any()):
-            return None
         o = torch.empty((n,), dtype=torch.int32, device=params.device)
         _lib.timed_call("feos_dev_pure_order", _lib.ptr(params), _lib.ptr(temperature), n, _lib.ptr(o), _stream())
         return o
-    return _lib.cached_order("pure", params, temperature, compute)
+    with torch.cuda.device(params.device):
+        return _lib.cached_order("pure", key, compute)
 
 
 class _PureVle(torch.autograd.Function):
@@ -226,7 +222,7 @@ class _PureVle(torch.autograd.Function):
     Returns (compacted values [n_ok], failed [n] uint8, rho [n, 2])."""
 
     @staticmethod
-    def forward(ctx, params, temperature, which):
+    def forward(ctx, params, temperature, which, order):
         n = temperature.shape[0]
         dev = params.device
         rho = torch.empty((n, 2), dtype=torch.float64, device=dev)
@@ -234,7 +230,8 @@ class _PureVle(torch.autograd.Function):
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
         ch = _chunks_of(params)
         with torch.cuda.device(dev):
-            order = _state_order(params, temperature) if ch is None else None
+            if ch is not None:
+                order = None  # chunked host upload: every chunk is launched on its own rows
 
             def launch(a, b):
                 _lib.timed_call(
@@ -270,12 +267,12 @@ class _PureVle(torch.autograd.Function):
                 grad_params._feos_chunks = _Chunks(bounds, events, grad_params._version)
             else:
                 launch(0, n)
-        return grad_params, grad_t, None
+        return grad_params, grad_t, None, None
 
 
 class _PureRhoTp(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, params, temperature, pressure):
+    def forward(ctx, params, temperature, pressure, order):
         n = temperature.shape[0]
         dev = params.device
         rho = torch.empty((n,), dtype=torch.float64, device=dev)
@@ -283,7 +280,8 @@ class _PureRhoTp(torch.autograd.Function):
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
         ch = _chunks_of(params)
         with torch.cuda.device(dev):
-            order = _state_order(params, temperature) if ch is None else None
+            if ch is not None:
+                order = None  # chunked host upload: every chunk is launched on its own rows
 
             def launch(a, b):
                 _lib.timed_call(
@@ -302,7 +300,7 @@ class _PureRhoTp(torch.autograd.Function):
         params, temperature, pressure, rho, failed, pos = ctx.saved_tensors
         n = temperature.shape[0]
         g = g_val.contiguous()
-        need_p, need_t, need_pr = ctx.needs_input_grad
+        need_p, need_t, need_pr = ctx.needs_input_grad[:3]
         grad_params = torch.empty_like(params) if need_p else None
         grad_t = torch.empty_like(temperature) if need_t else None
         grad_pr = torch.empty_like(pressure) if need_pr else None
@@ -319,7 +317,7 @@ class _PureRhoTp(torch.autograd.Function):
                 grad_params._feos_chunks = _Chunks(bounds, events, grad_params._version)
             else:
                 launch(0, n)
-        return grad_params, grad_t, grad_pr
+        return grad_params, grad_t, grad_pr, None
 
 
 def _grad_or_none(g):
@@ -389,20 +387,20 @@ class PcSaftPure:
     def vapor_pressure(self, temperature):
         """(failed mask [N], p_sat [n_ok] in Pa) -- pcsaft_pure.py:201-215."""
         t = _prep(temperature, self._dev)
-        val, failed, _ = _PureVle.apply(self._params, t, 0)
+        val, failed, _ = _PureVle.apply(self._params, t, 0, _state_order(self._params, t, (self._source, temperature)))
         return self._back(failed.bool()), self._back(val)
 
     def equilibrium_liquid_density(self, temperature):
         """(failed mask [N], rho_L^sat [n_ok] in kmol/m^3) -- pcsaft_pure.py:217-233."""
         t = _prep(temperature, self._dev)
-        val, failed, _ = _PureVle.apply(self._params, t, 1)
+        val, failed, _ = _PureVle.apply(self._params, t, 1, _state_order(self._params, t, (self._source, temperature)))
         return self._back(failed.bool()), self._back(val)
 
     def liquid_density(self, temperature, pressure):
         """(failed mask [N], rho_L(T, p) [n_ok] in kmol/m^3) -- pcsaft_pure.py:184-199."""
         t = _prep(temperature, self._dev)
         p = _prep(pressure, self._dev)
-        val, failed, _ = _PureRhoTp.apply(self._params, t, p)
+        val, failed, _ = _PureRhoTp.apply(self._params, t, p, _state_order(self._params, t, (self._source, temperature)))
         return self._back(failed.bool()), self._back(val)
 
     # ---- state functions at given (T, rho), differentiable (SURVEY section 8(f) rank 1) ---------------
