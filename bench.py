@@ -134,8 +134,8 @@ class C2:
     io_bytes_per_state = 64 + 8 + 16 + 8 + 1
     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the dominant kernel at 1 M
     # states, per state (profiles/README.md)
-    traffic_per_state = 80.5
-    traffic_source = "profiles/r1_final_pure_vle_queue_raw.csv"
+    traffic_per_state = 125.1  # dram__bytes_read.sum + dram__bytes_write.sum per launch / 1 M states (gathered rows)
+    traffic_source = "profiles/r1d_pure_vle_fwd_raw.csv"
     h2d_per_state = 64 + 8 + 8
     d2h_per_state = 64 + 2 * 8 + 2
     default_n = 1_000_000
@@ -265,8 +265,8 @@ class C4:
     kernel = "mix_point_fwd_kernel(+retry)"
     flops_per_eval = 3485.0  # binary non-associating hyper-dual evaluation, SURVEY.md section 8(d)
     io_bytes_per_state = 128 + 16 + 8 + 8 + 32 + 8 + 1
-    traffic_per_state = 196.0
-    traffic_source = "profiles/r1_final_mix_point_fwd_raw.csv"
+    traffic_per_state = 248.6
+    traffic_source = "profiles/r1d_mix_point_fwd_raw.csv"
     h2d_per_state = 8 + 8
     d2h_per_state = 2
     default_n = 1_000_000
@@ -335,8 +335,8 @@ class C5:
     kernel = "gc_point_fwd_kernel(+retry)"
     flops_per_eval = 4687.0  # GC compact hyper-dual evaluation, SURVEY.md section 8(d)
     io_bytes_per_state = 4 + 16 + 8 + 8 + 32 + 8 + 1
-    traffic_per_state = 51.0
-    traffic_source = "profiles/r1_final_gc_point_fwd_raw.csv"
+    traffic_per_state = 57.9
+    traffic_source = "profiles/r1d_gc_point_raw.csv"
     h2d_per_state = 8 + 8
     d2h_per_state = 2
     default_n = 1_000_000

@@ -240,7 +240,9 @@ class GcPcSaftMix:
                                     _lib.ptr(z), n, pair_only, _lib.ptr(o), _stream())
                 return o
             key = (self._pair_index, temperature, molefracs)
-            orders = (_lib.cached_order("gc", key, lambda: compute(0)), _lib.cached_order("gc-pair", key, lambda: compute(1)))
+            dev = self._dev.index
+            orders = (_lib.cached_order(("gc", dev), key, lambda: compute(0)),
+                      _lib.cached_order(("gc-pair", dev), key, lambda: compute(1)))
         val, failed, _ = _GcPoint.apply(self._seg, self._kab, self._phi, t, z, bubble, tables, orders)
         return self._back(val), self._back(failed.bool())
 

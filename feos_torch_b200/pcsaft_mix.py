@@ -134,7 +134,7 @@ class PcSaftMix:
                     _lib.timed_call("feos_dev_mix_point_order", _lib.ptr(self._params), _lib.ptr(t), _lib.ptr(z), n,
                                     _lib.ptr(o), _stream())
                 return o
-            order = _lib.cached_order("mix", (temperature, molefracs), compute)
+            order = _lib.cached_order(("mix", self._dev.index), (temperature, molefracs), compute)
         val, failed, _ = _MixPoint.apply(self._params, self._kij, t, z, bubble, order)
         return self._back(val), self._back(failed.bool())
 

@@ -214,7 +214,7 @@ def _state_order(params, temperature, key):
         _lib.timed_call("feos_dev_pure_order", _lib.ptr(params), _lib.ptr(temperature), n, _lib.ptr(o), _stream())
         return o
     with torch.cuda.device(params.device):
-        return _lib.cached_order("pure", key, compute)
+        return _lib.cached_order(("pure", params.device.index), key, compute)
 
 
 class _PureVle(torch.autograd.Function):
