@@ -214,6 +214,82 @@ FD void pure_extras_grad_pass(const double* prm, double T, double rho, int first
   }
 }
 
+// Association term of a non-polar state: it depends on the nine inputs only through FOUR coefficients
+// (c_eta, delta0, na, nb), so one pass of four dual directions over the term + the hand-written derivatives of
+// the coefficient stage replaces three passes of three directions over coefficient stage and term
+// (C3: pure_vle_bwd_kernel 4.6 -> see profiles/README.md).  Adds to da / dap.
+template <bool NEED_AP>
+FD void pure_assoc_grad_coef(const double* prm, double T, double rho, double (&da)[9], double (&dap)[9]) {
+  const double m = prm[0], sigma = prm[1], eps = prm[2], kappa = prm[4], eps_ab = prm[5];
+  const double ti = 1.0 / T;
+  const double ex = exp(-3.0 * eps * ti);
+  const double f = 1.0 - 0.12 * ex;
+  const double d = sigma * f, d2 = d * d;
+  const double s2 = sigma * sigma, s3 = s2 * sigma;
+  const double E = exp(eps_ab * ti);
+  PureCoef<DN<4>> c;
+  c.dipolar = false;
+  c.assoc = true;
+  c.c_eta = DN<4>((kPi / 6.0) * m * (d2 * d));
+  c.c_eta.e[0] = 1.0;
+  c.delta0 = DN<4>((E - 1.0) * s3 * kappa);
+  c.delta0.e[1] = 1.0;
+  c.na = DN<4>(prm[6]);
+  c.na.e[2] = 1.0;
+  c.nb = DN<4>(prm[7]);
+  c.nb.e[3] = 1.0;
+  double A[4], Ap[4];
+  if (NEED_AP) {
+    typedef D1T<DN<4>> R;
+    R r(DN<4>(rho), DN<4>(1.0));
+    R eta = r * c.c_eta;
+    R e2 = eta * eta;
+    R a = pure_helmholtz_extras<DN<4>, R>(c, r, eta, e2, e2 * eta, e2 * e2, ad_recip(1.0 - eta));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      A[k] = a.re.e[k];
+      Ap[k] = a.d1.e[k];
+    }
+  } else {
+    typedef DN<4> R;
+    R r(rho);
+    R eta = r * c.c_eta;
+    R e2 = eta * eta;
+    R a = pure_helmholtz_extras<DN<4>, R>(c, r, eta, e2, e2 * eta, e2 * e2, ad_recip(1.0 - eta));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      A[k] = a.e[k];
+      Ap[k] = 0.0;
+    }
+  }
+  // coefficient stage (pure_coef): c_eta = pi/6 m d^3, d = sigma (1 - 0.12 exp(-3 eps / T));
+  // delta0 = (exp(eps_ab / T) - 1) sigma^3 kappa
+  const double ce_d = (kPi / 6.0) * m * 3.0 * d2;      // d c_eta / d d
+  const double d_eps = sigma * 0.36 * ex * ti;         // d d / d eps
+  const double d_T = -sigma * 0.36 * ex * eps * ti * ti;
+  const double ce[4] = {(kPi / 6.0) * (d2 * d), ce_d * f, ce_d * d_eps, ce_d * d_T};  // m, sigma, eps, T
+  const double de[4] = {(E - 1.0) * 3.0 * s2 * kappa, (E - 1.0) * s3, E * ti * s3 * kappa,
+                        -E * eps_ab * ti * ti * s3 * kappa};                          // sigma, kappa, eps_ab, T
+  da[0] += A[0] * ce[0];
+  da[1] += A[0] * ce[1] + A[1] * de[0];
+  da[2] += A[0] * ce[2];
+  da[4] += A[1] * de[1];
+  da[5] += A[1] * de[2];
+  da[6] += A[2];
+  da[7] += A[3];
+  da[8] += A[0] * ce[3] + A[1] * de[3];
+  if (NEED_AP) {
+    dap[0] += Ap[0] * ce[0];
+    dap[1] += Ap[0] * ce[1] + Ap[1] * de[0];
+    dap[2] += Ap[0] * ce[2];
+    dap[4] += Ap[1] * de[1];
+    dap[5] += Ap[1] * de[2];
+    dap[6] += Ap[2];
+    dap[7] += Ap[3];
+    dap[8] += Ap[0] * ce[3] + Ap[1] * de[3];
+  }
+}
+
 // d a / d(m, sigma, eps, mu, kappa, eps_ab, na, nb, T) at fixed rho (da[9]) and the same for a' (dap[9])
 template <bool NEED_AP>
 FD void pure_state_grad(const double* prm, double T, double rho, double (&da)[9], double (&dap)[9]) {
@@ -225,7 +301,9 @@ FD void pure_state_grad(const double* prm, double T, double rho, double (&da)[9]
   if (NEED_AP) { dap[0] = bp[0]; dap[1] = bp[1]; dap[2] = bp[2]; dap[8] = bp[3]; }
   bool dipolar = prm[3] != 0.0;
   bool assoc = (prm[6] != 0.0) || (prm[7] != 0.0);  // as pure_coef(..., grad_mode = true)
-  if (dipolar || assoc) {
+  if (assoc && !dipolar) {
+    pure_assoc_grad_coef<NEED_AP>(prm, T, rho, da, dap);
+  } else if (dipolar) {
 #pragma unroll
     for (int f = 0; f < 9; f += 3) {
       double x[3], xp[3];

@@ -149,9 +149,19 @@ def test_closed_form_gradients_equal_dual_number_passes():
     for kw in (dict(gv=gv), dict(gv=gv, gr=gr)):
         a = sim.pure_vle_bwd(P, T, rho, generic=True, **kw)
         b = sim.pure_vle_bwd(P, T, rho, **kw)
-        assert (np.abs(a - b) / np.abs(a).max(axis=1, keepdims=True)).max() < 1e-11
+        err = np.abs(a - b) / np.abs(a).max(axis=1, keepdims=True)
+        assert err[P[:, 6] == 0].max() < 1e-11
+        assert err[P[:, 6] != 0].max() < 5e-9  # association: see the note on the density gradient below
     Pr = np.full(k, 5e6)
     r1, val, st1, _ = sim.pure_rho_tp(P, T, Pr)
     a, gpa = sim.pure_rho_tp_bwd(P, T, Pr, r1, gv, generic=True)
     b, gpb = sim.pure_rho_tp_bwd(P, T, Pr, r1, gv)
-    assert (np.abs(a - b) / np.abs(a).max(axis=1, keepdims=True)).max() < 1e-11
+    err = np.abs(a - b) / np.abs(a).max(axis=1, keepdims=True)
+    plain = P[:, 6] == 0
+    assert err[plain].max() < 1e-11
+    # strongly associating liquids (rho Delta up to 1e6 at the cold end of this grid): in the closed-form site
+    # fractions of pcsaft_pure.py:172-175, sqrt(...) + 1 - dd loses 6 digits and d p / d Delta is the small
+    # remainder of -a_Delta + rho a'_Delta, so the association part of a gradient row carries ~1e-4 relative
+    # noise in EVERY evaluation order (the generic passes, the coefficient-direction pass and torch autograd
+    # of the reference formula disagree with one another at that level); on the scale of the row it is < 1e-8
+    assert err[~plain].max() < 5e-9
