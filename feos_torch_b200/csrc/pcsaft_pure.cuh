@@ -251,7 +251,33 @@ FD PureEval pure_eval(const PureCoef<double>& c, double rho) {
   double a = rho * (f + rho * g);
   double a1 = f + eta * f1 + rho * (2.0 * g + eta * g1);
   double a2 = c.c_eta * (2.0 * f1 + eta * f2) + 2.0 * g + eta * (4.0 * g1 + eta * g2);
-  if (c.dipolar || c.assoc) {
+  if (c.assoc && !c.dipolar) {
+    // association (:163-176) in closed form.  Delta = delta0 g(eta), g = (1 + 1.5 k + 0.5 k^2) s with k = eta s,
+    // s = 1 / (1 - eta) (d k / d eta = d s / d eta = s^2).  With the site fractions at their mass-action solution,
+    //   d a / d rho_S = ln X_S (fixed Delta),  d a / d Delta = - rho_A rho_B X_A X_B,
+    // so a' needs no derivative of X; a'' takes X_A', X_B' from the linearised mass-action equations
+    // (2 x 2 system, determinant X_A + X_B - X_A X_B > 0).
+    const double k = eta * s;
+    const double q = 1.0 + k * (1.5 + 0.5 * k), q1 = (1.5 + k) * s2, q2 = s4 + (1.5 + k) * 2.0 * s3;
+    const double gq = q * s, gq1 = q1 * s + q * s2, gq2 = q2 * s + 2.0 * q1 * s2 + 2.0 * q * s3;
+    const double delta = gq * c.delta0;  // same operations as the generic path: a is bit-identical
+    const double dl1 = c.delta0 * gq1 * c.c_eta, dl2 = c.delta0 * gq2 * c.c_eta * c.c_eta;
+    const double ra = rho * c.na, rb = rho * c.nb;
+    const double dd = (rb - ra) * delta;
+    const double aux = 1.0 - dd;
+    const double sq = sqrt(aux * aux + 4.0 * (rb * delta));
+    const double xa = 2.0 / (sq + 1.0 + dd), xb = 2.0 / (sq + 1.0 - dd);
+    const double la = log(xa), lb = log(xb);
+    a += ra * (la - 0.5 * xa + 0.5) + rb * (lb - 0.5 * xb + 0.5);
+    const double w = ra * rb * xa * xb;
+    a1 += c.na * la + c.nb * lb - w * dl1;
+    // X_A' = u, X_B' = v:  u + X_A^2 rb Delta v = -p1,  X_B^2 ra Delta u + v = -p2
+    const double ca = xa * xa * rb * delta, cb = xb * xb * ra * delta;
+    const double p1 = xa * xa * xb * (c.nb * delta + rb * dl1), p2 = xb * xb * xa * (c.na * delta + ra * dl1);
+    const double idet = 1.0 / (xa + xb - xa * xb);
+    const double u = (ca * p2 - p1) * idet, v = (cb * p1 - p2) * idet;
+    a2 += c.na * u / xa + c.nb * v / xb - (2.0 * c.na * c.nb * rho * xa * xb + ra * rb * (u * xb + xa * v)) * dl1 - w * dl2;
+  } else if (c.dipolar || c.assoc) {
     D2 r(rho, 1.0, 0.0);
     D2 et = r * c.c_eta;
     D2 e2 = et * et;

@@ -216,8 +216,11 @@ pure_vle_retry_kernel(const double* __restrict__ params, const double* __restric
   }
 }
 
+#ifndef FEOS_PURE_BWD_MINB
+#define FEOS_PURE_BWD_MINB 3
+#endif
 template <bool NEED_RLEQ>
-__global__ void __launch_bounds__(kBlock, 3)
+__global__ void __launch_bounds__(kBlock, FEOS_PURE_BWD_MINB)
 pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                     const double* __restrict__ rho, const uint8_t* __restrict__ failed,
                     const int32_t* __restrict__ pos, const double* __restrict__ g_vp,
@@ -279,7 +282,7 @@ pure_rho_tp_fwd_kernel(const double* __restrict__ params, const double* __restri
   if (evals) evals[i] = ne;
 }
 
-__global__ void __launch_bounds__(kBlock, 3)
+__global__ void __launch_bounds__(kBlock, FEOS_PURE_BWD_MINB)
 pure_rho_tp_bwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                        const double* __restrict__ pressure, const double* __restrict__ rho,
                        const uint8_t* __restrict__ failed, const int32_t* __restrict__ pos,

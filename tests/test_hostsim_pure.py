@@ -125,7 +125,11 @@ def test_closed_form_eval_equals_dual_number_eval():
     # both evaluate O(rho)-sized sums with cancellations: compare on the scale of the largest term
     scale = rho * (1 + P[:, 0] * 10)
     assert (np.abs(a1 - a0) / scale).max() < 1e-13
-    assert (np.abs(p1 - p0) / scale).max() < 1e-13
+    # association-only states take the closed-form site-fraction derivatives (pure_eval); in the strong
+    # association limit -a + rho a' is a small remainder, so p carries a few 1e-13 of round-off either way
+    closed = (P[:, 6] > 0) & (P[:, 3] == 0)
+    assert (np.abs(p1 - p0) / scale)[~closed].max() < 1e-13
+    assert (np.abs(p1 - p0) / scale)[closed].max() < 1e-12
     assert (np.abs(d1 - d0) / (1 + np.abs(d0))).max() < 1e-11
 
 
