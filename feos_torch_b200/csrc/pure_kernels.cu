@@ -217,7 +217,7 @@ pure_vle_retry_kernel(const double* __restrict__ params, const double* __restric
 }
 
 #ifndef FEOS_PURE_BWD_MINB
-#define FEOS_PURE_BWD_MINB 3
+#define FEOS_PURE_BWD_MINB 4  // 128 registers: 0.179 -> 0.160 ms (vle), 0.132 -> 0.124 ms (density) per 1 M states; 2 and 5 are slower
 #endif
 template <bool NEED_RLEQ>
 __global__ void __launch_bounds__(kBlock, FEOS_PURE_BWD_MINB)
