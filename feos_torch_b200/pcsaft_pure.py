@@ -10,6 +10,8 @@ Differences that are not observable through returned values: the model object is
 (`reduce`, pcsaft_pure.py:235-243), and tensors may live on the CPU -- they are moved to the
 current CUDA device for the computation and the results are returned on the parameters' device.
 """
+import weakref
+
 import torch
 
 from . import _lib
@@ -367,6 +369,7 @@ class PcSaftPure:
         # host parameters are copied at the first property call, AFTER that call's (small) state tensors: the
         # copy engine works in submission order and the first chunk's kernel needs its temperatures
         self._params_dev = None if (not parameters.is_cuda and parameters.requires_grad) else _prep(parameters, self._dev)
+        self._uploads = {}
 
     @property
     def _params(self):
@@ -383,23 +386,35 @@ class PcSaftPure:
     def _back(self, t):
         return _back(t, self._out_device)
 
+    def _state(self, t):
+        """State tensor (T, p) on the device.  A host tensor that carries no gradient is uploaded once per model
+        object and tensor version: `vapor_pressure(T)` followed by `liquid_density(T, p)` moves T once."""
+        if t.is_cuda or t.requires_grad:
+            return _prep(t, self._dev)
+        hit = self._uploads.get(id(t))
+        if hit is not None and hit[0]() is t and hit[1] == t._version:
+            return hit[2]
+        d = _prep(t, self._dev)
+        self._uploads[id(t)] = (weakref.ref(t), t._version, d)
+        return d
+
     # ---- properties on the phase-equilibrium hot path ------------------------------------------
     def vapor_pressure(self, temperature):
         """(failed mask [N], p_sat [n_ok] in Pa) -- pcsaft_pure.py:201-215."""
-        t = _prep(temperature, self._dev)
+        t = self._state(temperature)
         val, failed, _ = _PureVle.apply(self._params, t, 0, _state_order(self._params, t, (self._source, temperature)))
         return self._back(failed.bool()), self._back(val)
 
     def equilibrium_liquid_density(self, temperature):
         """(failed mask [N], rho_L^sat [n_ok] in kmol/m^3) -- pcsaft_pure.py:217-233."""
-        t = _prep(temperature, self._dev)
+        t = self._state(temperature)
         val, failed, _ = _PureVle.apply(self._params, t, 1, _state_order(self._params, t, (self._source, temperature)))
         return self._back(failed.bool()), self._back(val)
 
     def liquid_density(self, temperature, pressure):
         """(failed mask [N], rho_L(T, p) [n_ok] in kmol/m^3) -- pcsaft_pure.py:184-199."""
-        t = _prep(temperature, self._dev)
-        p = _prep(pressure, self._dev)
+        t = self._state(temperature)
+        p = self._state(pressure)
         val, failed, _ = _PureRhoTp.apply(self._params, t, p, _state_order(self._params, t, (self._source, temperature)))
         return self._back(failed.bool()), self._back(val)
 
