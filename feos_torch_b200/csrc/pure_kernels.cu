@@ -82,7 +82,9 @@ pure_vle_fwd_kernel(const double* __restrict__ params, const double* __restrict_
   double rho_l, u, rle, rve;
   PureEval el, ev;
   int ne = 0;
-  int st = pure_vle_fast(c, rho_max, rho_l, u, el, ev, rle, rve, ne);
+  // associating states call the out-of-line evaluation (instruction cache), the others inline it (pure_solver.cuh)
+  int st = c.assoc ? pure_vle_fast<true>(c, rho_max, rho_l, u, el, ev, rle, rve, ne)
+                   : pure_vle_fast<false>(c, rho_max, rho_l, u, el, ev, rle, rve, ne);
   if (evals) evals[i] = ne;
   if (st == kStatusRetry) {
     int slot = atomicAdd(retry_count, 1);
@@ -273,7 +275,7 @@ pure_rho_tp_fwd_kernel(const double* __restrict__ params, const double* __restri
   double x;
   PureEval e;
   int ne = 0;
-  int st = pure_liquid_density(c, rho_max, p_t, x, e, ne);
+  int st = c.assoc ? pure_liquid_density<true>(c, rho_max, p_t, x, e, ne) : pure_liquid_density<false>(c, rho_max, p_t, x, e, ne);
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   double rn = (st == kStatusOk) ? x - (e.p - p_t) / e.dp : nan;  // pcsaft_pure.py:198
   rho[i] = rn;

@@ -21,6 +21,22 @@
 
 namespace feos {
 
+// Evaluation call of the fast VLE path and the density iteration.  SHARED = true calls ONE out-of-line copy of
+// pure_eval instead of inlining it at each call site: with the association term in it the inlined loop bodies
+// no longer fit the instruction cache (ncu: `no_instruction` 1.9 per issue-active cycle; C3 forward 5.98 -> 5.43 ms
+// per 10 M states), while for the short non-associating evaluation inlining wins (C2 forward 0.42 vs 0.46 ms).
+// The kernels pick per state; in the state order of order.cuh a warp holds one kind.
+#if defined(__CUDACC__)
+static __device__ __noinline__ PureEval pure_eval_shared(const PureCoef<double>& c, double rho) { return pure_eval(c, rho); }
+#endif
+template <bool SHARED>
+FD PureEval pure_eval_sel(const PureCoef<double>& c, double rho) {
+#if defined(__CUDACC__)
+  if (SHARED) return pure_eval_shared(c, rho);
+#endif
+  return pure_eval(c, rho);
+}
+
 // liquid density iterations start at packing fraction 0.45: right of the root for all but the coldest
 // states (from the left Newton overshoots once and then descends monotonically as well); measured on
 // the C2 grid: 12.2 instead of 12.9 evaluations per state, same retry fraction
@@ -32,6 +48,7 @@ FD double clampd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi);
 
 // Coupled Newton iteration.  On return 0: (rho_l, u = ln rho_v) hold the accepted step and
 // (el, ev, rho_l_eval, rho_v_eval) the last evaluation point, one Newton step before it.
+template <bool SHARED = false>
 FD int pure_vle_newton(const PureCoef<double>& c, double& rho_l, double& u, PureEval& el, PureEval& ev,
                        double& rho_l_eval, double& rho_v_eval, int max_iter, int& evals) {
   double prev_l = rho_l, prev_u = u, dl = 0.0, du = 0.0;
@@ -39,8 +56,8 @@ FD int pure_vle_newton(const PureCoef<double>& c, double& rho_l, double& u, Pure
   int halvings = 0;
   for (int it = 0; it < max_iter; ++it) {
     double rho_v = exp(u);
-    el = pure_eval(c, rho_l);
-    ev = pure_eval(c, rho_v);
+    el = pure_eval_sel<SHARED>(c, rho_l);
+    ev = pure_eval_sel<SHARED>(c, rho_v);
     evals += 2;
     bool bad = !(el.dp > 0.0) || !(ev.dp > 0.0) || !(rho_l > rho_v);
     if (bad) {
@@ -73,13 +90,14 @@ FD int pure_vle_newton(const PureCoef<double>& c, double& rho_l, double& u, Pure
   return kStatusRetry;
 }
 
+template <bool SHARED = false>
 FD int pure_vle_fast(const PureCoef<double>& c, double rho_max, double& rho_l, double& u, PureEval& el,
                      PureEval& ev, double& rho_l_eval, double& rho_v_eval, int& evals) {
   rho_l = kLiquidStart * rho_max;
   u = 0.0;
   bool ready = false;
   for (int it = 0; it < 24; ++it) {
-    el = pure_eval(c, rho_l);
+    el = pure_eval_sel<SHARED>(c, rho_l);
     evals += 1;
     if (!(el.dp > 0.0)) return kStatusRetry;
     u = log(rho_l) + el.a1 - el.p / rho_l;  // ideal vapour in equilibrium with this liquid
@@ -92,7 +110,7 @@ FD int pure_vle_fast(const PureCoef<double>& c, double rho_max, double& rho_l, d
     }
   }
   if (!ready || !(u == u)) return kStatusRetry;
-  return pure_vle_newton(c, rho_l, u, el, ev, rho_l_eval, rho_v_eval, 30, evals);
+  return pure_vle_newton<SHARED>(c, rho_l, u, el, ev, rho_l_eval, rho_v_eval, 30, evals);
 }
 
 // The fast path as a resumable state machine: every call of advance() consumes ONE Helmholtz evaluation
@@ -337,11 +355,12 @@ FD int pure_vle_robust(const PureCoef<double>& c, double rho_max, double& rho_l,
 // root is returned instead (Newton from the ideal gas; p(rho) is concave there).
 // On success `rho` is the evaluation point and `e` its evaluation; the caller applies the Newton step
 // (pcsaft_pure.py:196-198).
+template <bool SHARED = false>
 FD int pure_liquid_density(const PureCoef<double>& c, double rho_max, double p_t, double& rho, PureEval& e, int& evals) {
   rho = rho_max;
   bool vapour_side = false;
   for (int it = 0; it < 60; ++it) {
-    e = pure_eval(c, rho);
+    e = pure_eval_sel<SHARED>(c, rho);
     evals += 1;
     if (!(e.dp > 0.0)) {
       if (vapour_side || !(e.p > p_t) || !(p_t > 0.0)) return kStatusFailed;
