@@ -158,7 +158,7 @@ gc_point_retry_kernel(GcArgs g, const double* __restrict__ molefrac, int bubble,
 }
 
 #ifndef FEOS_GC_BWD_MINB
-#define FEOS_GC_BWD_MINB 3  // 168 registers: 1.90 -> 1.83 ms per 1 M states
+#define FEOS_GC_BWD_MINB 4  // registers 255 / 168 / 128: 1.90 / 1.87 / 1.75 ms per 1 M states (converged lanes: occupancy pays)
 #endif
 __global__ void __launch_bounds__(kGcBlock, FEOS_GC_BWD_MINB)
 gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ rho, const uint8_t* __restrict__ failed,
