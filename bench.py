@@ -10,8 +10,12 @@ vapor_pressure fwd+bwd and liquid_density fwd+bwd through the public API.
 
 Prints ONE JSON line (rank 0).  `value` = states (each = one vapor-pressure solve+gradient and one
 liquid-density solve+gradient) per second over all GPUs with inputs resident in HBM; `e2e` = the same
-with pinned HOST inputs, H2D/D2H copies inside the timed region.  `--impl reference` times the
-reference CPU path (oracle port, all host threads) on a bounded sample of the same workload.
+with pinned HOST inputs, H2D/D2H copies inside the timed region.  The default run appends short legs of
+the other BASELINE.json configs under `extras` (c3, c4, c5: own value, e2e, roofline, failed fraction;
+under torchrun the c4 / c5 legs run the NCCL all-reduce of the shared-leaf gradient every step).
+`--impl reference` times the reference CPU path (compiled per-state solver restating feos, OpenMP over
+all host threads, + the reference's Newton-step gradient stage in torch on the CPU) on a bounded sample
+of the same workload.
 """
 import argparse
 import json
@@ -83,46 +87,99 @@ def parse_clocks(path):
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+CPU_CHUNK = 1 << 17  # states per gradient-stage chunk of the CPU arm (bounds the autograd graph: ~1 GB)
+
+
+def cpu_c2_pass(params, T, p):
+    """One pass of the C2 workload on the host the way the reference runs it: solve stage = one compiled
+    per-state solve per state on all cores (oracle/cpu_solver.cpp = what src/pcsaft.rs:82-129 asks of feos, OpenMP
+    for rayon), gradient stage = the reference's Newton-step formulas under torch autograd on the CPU
+    (oracle/eos.py = pcsaft_pure.py:196-199, :210-215).  Returns (grad, seconds in solve stage, in gradient stage)."""
+    from oracle import cpu_solver, eos
+
+    n = T.shape[0]
+    t0 = time.perf_counter()
+    rv, rl, nans = cpu_solver.pure_vle(params, T)
+    t_solve = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    grad = torch.zeros_like(params)
+    psat = torch.zeros(n, dtype=torch.float64)
+    for a in range(0, n, CPU_CHUNK):
+        sl = slice(a, min(a + CPU_CHUNK, n))
+        ok = ~nans[sl]
+        x = params[sl][ok].clone().requires_grad_(True)
+        vp = eos.pure_vapor_pressure_from_densities(x, T[sl][ok], rv[sl][ok], rl[sl][ok])
+        vp.sum().backward()
+        g = torch.zeros((ok.shape[0], 8), dtype=torch.float64)
+        g[ok] = x.grad
+        grad[sl] += g
+        ps = torch.zeros(ok.shape[0], dtype=torch.float64)
+        ps[ok] = vp.detach()
+        psat[sl] = ps
+    t_grad = time.perf_counter() - t0
+    pr = torch.maximum(p, 1.05 * psat)
+    t0 = time.perf_counter()
+    rho, nans2 = cpu_solver.pure_liquid_density(params, T, pr)
+    t_solve += time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for a in range(0, n, CPU_CHUNK):
+        sl = slice(a, min(a + CPU_CHUNK, n))
+        ok = ~nans2[sl]
+        x = params[sl][ok].clone().requires_grad_(True)
+        val = eos.pure_liquid_density_from_density(x, T[sl][ok], pr[sl][ok], rho[sl][ok])
+        val.sum().backward()
+        g = torch.zeros((ok.shape[0], 8), dtype=torch.float64)
+        g[ok] = x.grad
+        grad[sl] += g
+    t_grad += time.perf_counter() - t0
+    return grad, t_solve, t_grad
+
+
 def run_reference(args, rank, world, out):
-    """Reference arm: the reference's CPU implementation of the path (oracle port: CPU solver restating
-    feos + the reference's Newton-step gradient stage under torch autograd), all host threads."""
+    """Reference arm: the reference's CPU implementation of the path (compiled solver restating feos + the
+    reference's Newton-step gradient stage under torch autograd), all host threads."""
     if rank != 0:
         return
-    from oracle import models as om
+    from oracle import cpu_solver
 
     n = args.ref_n
     threads = _use_all_host_threads()
+    cpu_solver.load()
     params, T, p = make_workload(n, 1000, "cpu")
-
-    def step():
-        x = params.clone().requires_grad_(True)
-        model = om.PcSaftPure(x)
-        nans, vp = model.vapor_pressure(T)
-        psat = torch.zeros(n, dtype=torch.float64)
-        psat[~nans] = vp.detach()
-        pr = torch.maximum(p, 1.05 * psat)
-        nans2, rho = model.liquid_density(T, pr)
-        (vp.sum() + rho.sum()).backward()
-        return x.grad
-
     for _ in range(args.warmup):
-        step()
+        cpu_c2_pass(params, T, p)
     t0 = time.perf_counter()
+    ts = tg = 0.0
     for _ in range(args.steps):
-        step()
+        _, a, b = cpu_c2_pass(params, T, p)
+        ts += a
+        tg += b
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = f"{n} states per step of the C2 workload (seed 1000), oracle port on {threads} torch CPU threads"
+    sample = (f"{n} states per step of the C2 workload (seed 1000): compiled per-state solver (g++ -O3 -fopenmp, "
+              f"{cpu_solver.threads()} OpenMP threads) + torch-CPU gradient stage ({threads} threads); "
+              f"solve stage {ts / args.steps:.3f} s, gradient stage {tg / args.steps:.3f} s per step")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: PcSaftPure vapor_pressure + liquid_density fwd+bwd, synthetic non-associating (params,T) pairs",
-                   "states_per_step": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": C2.name, "states_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "solve_stage_states_per_s": n * args.steps / ts, "gradient_stage_states_per_s": n * args.steps / tg},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=out, flush=True)
+
+
+def _bump_version(t):
+    """What an optimizer step does to a leaf, without the update kernel: the tensor's version counter moves, so
+    nothing keyed on (identity, version) of the parameters can be reused across steps for free."""
+    inc = getattr(torch.autograd.graph, "increment_version", None)
+    if inc is not None:
+        inc(t)
+    else:
+        with torch.no_grad():
+            t.add_(0.0)
 
 
 class C2:
@@ -159,6 +216,7 @@ class C2:
 
     def step_device(self):
         self.params.grad = None
+        _bump_version(self.params)  # as if an optimizer had updated the per-state parameters in place
         model = self.PcSaftPure(self.params)
         nans, vp = model.vapor_pressure(self.T)
         nans2, rho = model.liquid_density(self.T, self.p)
@@ -241,6 +299,7 @@ class C3:
 
     def step_device(self):
         self.params.grad = None
+        _bump_version(self.params)
         nans, rho = self.PcSaftPure(self.params).equilibrium_liquid_density(self.T)
         rho.sum().backward()
         return nans
@@ -321,8 +380,8 @@ class C4:
         failed = torch.empty(n, dtype=torch.uint8, device=self.dev)
         P = self.pair.expand(n, 2, 8).contiguous()
         K = self.kij.detach().expand(n, 2).contiguous()
-        _lib.call("feos_dev_mix_point_fwd", _lib.ptr(P), _lib.ptr(K), _lib.ptr(self.T), _lib.ptr(self.z), n, 1, _lib.ptr(rho),
-                  None, _lib.ptr(failed), _lib.ptr(evals), None, torch.cuda.current_stream().cuda_stream)
+        _lib.call("feos_dev_mix_point_fwd", _lib.ptr(P), _lib.ptr(K), _lib.ptr(self.T), _lib.ptr(self.z), None, n, 1, 0,
+                  _lib.ptr(rho), None, _lib.ptr(failed), _lib.ptr(evals), None, torch.cuda.current_stream().cuda_stream)
         return evals.double().mean().item()
 
 
@@ -400,7 +459,7 @@ class C5:
         failed = torch.empty(n, dtype=torch.uint8, device=self.dev)
         _lib.call("feos_dev_gc_point_fwd", _lib.ptr(m._pairs), m._n_pairs, _lib.ptr(m._seg.detach()), m._seg.shape[0],
                   _lib.ptr(m._kab.detach()), m._kab.shape[0], _lib.ptr(m._pair_index), _lib.ptr(m._phi), _lib.ptr(self.T),
-                  _lib.ptr(self.z), n, 1, _lib.ptr(rho), None, _lib.ptr(failed), _lib.ptr(evals), None,
+                  _lib.ptr(self.z), None, n, 1, _lib.ptr(rho), None, _lib.ptr(failed), _lib.ptr(evals), None,
                   torch.cuda.current_stream().cuda_stream)
         return evals.double().mean().item()
 
@@ -425,48 +484,37 @@ def main():
         out.flush()
 
 
-def _main(out):
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (BASELINE.json metric)")
-    ap.add_argument("--n", type=int, default=0, help="states per GPU per step (default: the workload's BASELINE size)")
-    ap.add_argument("--ref-n", type=int, default=50_000, help="states per step of the reference arm (about 7 s per step)")
-    ap.add_argument("--cpu-n", type=int, default=100_000, help="states of the cpu_baseline sample (one pass, about 15 s)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+METRICS = {"c2": METRIC, "c3": "pcsaft_equilibrium_liquid_density_solves_plus_grads_per_s",
+           "c4": "pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s",
+           "c5": "gc_pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s"}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+# Hardware truth beside the algorithmic-flop fraction (profiles/README.md, ncu --set full of the dominant kernel at
+# the bench size): FP64-pipe utilisation, lanes per instruction, and executed FP64 flops (2 DFMA + DADD + DMUL per
+# cycle x cycles / duration) over the measured peak.  The closed-form evaluations execute fewer flops than the
+# algorithmic count of SURVEY.md section 8(d) credits them with, so `frac` is NOT pipe utilisation.
+NCU = {
+    "c2": {"fp64_pipe_pct": 65.8, "lanes_per_inst": 31.7, "executed_flop_frac_of_peak": 0.50, "source": "profiles/r1d_pure_vle_fwd_raw.csv"},
+    "c3": {"fp64_pipe_pct": 62.6, "lanes_per_inst": 31.2, "executed_flop_frac_of_peak": None, "source": "profiles/r1d_pure_c3_raw.csv"},
+    "c4": {"fp64_pipe_pct": 52.0, "lanes_per_inst": 31.1, "executed_flop_frac_of_peak": None, "source": "profiles/r1d_mix_point_fwd_raw.csv"},
+    "c5": {"fp64_pipe_pct": 46.0, "lanes_per_inst": 31.3, "executed_flop_frac_of_peak": None, "source": "profiles/r1d_gc_point_raw.csv"},
+}
 
-    if args.impl == "reference":
-        run_reference(args, rank, world, out)
-        return
 
+def measure(name, n, steps, warmup, rank, world, dev, flush, peak):
+    """Build workload `name` with n states per GPU, time `steps` device-resident and `steps` end-to-end steps
+    (CUDA events, L2 flushed between iterations, max over ranks) and return the fields of the JSON line."""
     import torch.distributed as dist
-
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
     from feos_torch_b200 import _lib
 
-    _lib.load()
-    n = args.n or WORKLOADS[args.workload].default_n
-    wl = WORKLOADS[args.workload](n, rank, dev)
-    flush = torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device=dev)
+    wl = WORKLOADS[name](n, rank, dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, collect):
+    def timed(fn, collect):
         for _ in range(warmup):
             fn()
         barrier()
@@ -488,73 +536,125 @@ def _main(out):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    clk_file = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
-    sampler = clocks_sampler(clk_file, local) if rank == 0 else None
     launches0 = _lib.launch_count()
-    ms_dev = timed(wl.step_device, args.steps, args.warmup, True)
-    launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    ms_dev = timed(wl.step_device, True)
+    launches = (_lib.launch_count() - launches0) * steps // (steps + warmup)
     timings = _lib.TIMINGS
     _lib.TIMINGS = None
-    ms_e2e = timed(wl.step_e2e, args.steps, args.warmup, False)
-    if sampler is not None:
-        sampler.terminate()
-        sampler.wait()
+    ms_e2e = timed(wl.step_e2e, False)
 
     # failed-state accounting + evaluation counts for the roofline (untimed)
     nans = wl.step_device()
     torch.cuda.synchronize()
     failed_frac = nans.double().mean().item()
     mean_evals = wl.mean_evals(_lib)
-
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
-    kern_ms = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in timings.items()}
-    step_ms = ms_dev / args.steps
+    kern_ms = {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in timings.items()}
+    step_ms = ms_dev / steps
     dom = wl.dominant
-    dom_calls = len(timings[dom]) // args.steps
+    dom_calls = len(timings[dom]) // steps
     flops_per_launch = n * mean_evals * wl.flops_per_eval
     dom_ms = kern_ms[dom] / dom_calls
     achieved = flops_per_launch / (dom_ms * 1e-3) / 1e12
-    peak = _lib.measure_fp64_peak()
     spec = 148 * 64 * 2 * 1.965e9 / 1e12
     io_bytes = n * wl.io_bytes_per_state
+    solver_ms = sum(v for k, v in kern_ms.items() if k.startswith("feos_dev_") and not k.endswith("_order"))
     roofline = {
         "bound": "fp64", "kernel": wl.kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak if peak else None,
         "traffic": wl.traffic_per_state * n if wl.traffic_per_state else None, "traffic_source": wl.traffic_source,
         "peak_source": "DFMA-chain microbenchmark in this run (MEASURED_PEAKS.json has no FP64 figure); spec 148 SM x 64 lanes x 2 x 1.965 GHz = %.1f" % spec,
         "flops_per_launch": flops_per_launch, "mean_evals_per_state": mean_evals, "flops_per_eval": wl.flops_per_eval,
-        "kernel_ms": dom_ms, "share_of_step": kern_ms[dom] / step_ms,
+        "kernel_ms": dom_ms, "share_of_step": kern_ms[dom] / step_ms, "solver_kernels_share_of_step": solver_ms / step_ms,
+        "ncu": NCU.get(name),
         "hbm": {"algorithmic_bytes": io_bytes, "achieved_gbs": io_bytes / (dom_ms * 1e-3) / 1e9, "peak_gbs": _peaks().get("hbm_gbs")},
         "kernel_ms_per_step": kern_ms,
     }
-
-    value = n * world * args.steps / (ms_dev * 1e-3)
-    e2e_value = n * world * args.steps / (ms_e2e * 1e-3)
-    cpu = None
-    if not args.no_cpu_baseline and args.workload == "c2":
-        cpu = cpu_baseline(args.cpu_n)
-    line = {
-        "metric": {"c2": METRIC, "c3": "pcsaft_equilibrium_liquid_density_solves_plus_grads_per_s",
-                   "c4": "pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s",
-                   "c5": "gc_pcsaft_binary_bubble_plus_dew_solves_plus_grads_per_s"}[args.workload],
-        "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": wl.name, "states_per_gpu_per_step": n,
-                   "parallelism": f"batch sharded over {world} GPU(s)" + (", one NCCL all-reduce of the shared-leaf gradient per step" if wl.shared else ", no data-path collective"),
-                   "l2": "flushed (256 MiB write) between timed iterations", "failed_fraction": failed_frac},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * wl.h2d_per_state * world,
-                "d2h_bytes_per_step": (n * wl.d2h_per_state + 8) * world, "ms_per_step": ms_e2e / args.steps},
+    par = f"batch sharded over {world} GPU(s)"
+    if wl.shared:
+        par += ", one NCCL all-reduce of the shared-leaf gradient per step" if world > 1 else ", shared-leaf gradient reduced in the backward kernel (all-reduce at N > 1)"
+    else:
+        par += ", no data-path collective"
+    return {
+        "metric": METRICS[name], "value": n * world * steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.name, "states_per_gpu_per_step": n, "parallelism": par,
+                   "l2": "flushed (256 MiB write) between timed iterations", "failed_fraction": failed_frac,
+                   "state_order": "pure: recomputed every %d-th parameter version (parameters' version bumped every step); "
+                                  "binary / GC: keyed on (T, x), computed once per data set" % _lib.ORDER_REFRESH},
+        "e2e": {"value": n * world * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * wl.h2d_per_state * world,
+                "d2h_bytes_per_step": (n * wl.d2h_per_state + 8) * world, "ms_per_step": ms_e2e / steps},
         "gpu_launches": launches,
-        "clocks": parse_clocks(clk_file),
         "roofline": roofline,
-        "cpu_baseline": cpu,
     }
-    print(json.dumps(line), file=out, flush=True)
+
+
+def _main(out):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (BASELINE.json metric)")
+    ap.add_argument("--n", type=int, default=0, help="states per GPU per step (default: the workload's BASELINE size)")
+    ap.add_argument("--ref-n", type=int, default=400_000, help="states per step of the reference arm (about 2 s per step)")
+    ap.add_argument("--cpu-n", type=int, default=1_000_000, help="states of the cpu_baseline sample (3 passes, about 15 s)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", default=None, help="comma-separated workloads measured in short legs under `extras` "
+                    "(default: c3,c4,c5 with the headline workload, none otherwise; 'none' switches them off)")
+    ap.add_argument("--extra-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world, out)
+        return
+
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from feos_torch_b200 import _lib
+
+    _lib.load()
+    flush = torch.empty(L2_FLUSH_BYTES // 8, dtype=torch.float64, device=dev)
+    peak = _lib.measure_fp64_peak()
+
+    clk_file = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
+    sampler = clocks_sampler(clk_file, local) if rank == 0 else None
+    n = args.n or WORKLOADS[args.workload].default_n
+    line = measure(args.workload, n, args.steps, args.warmup, rank, world, dev, flush, peak)
+    if args.extras is None:
+        extras = ["c3", "c4", "c5"] if args.workload == "c2" and not args.n else []
+    else:
+        extras = [e for e in args.extras.split(",") if e and e != "none"]
+    extra_lines = {}
+    for name in extras:
+        torch.cuda.empty_cache()
+        r = measure(name, WORKLOADS[name].default_n, args.extra_steps, 3, rank, world, dev, flush, peak)
+        if r is not None:
+            extra_lines[name] = {k: r[k] for k in ("metric", "value", "unit", "steps", "ms_per_step", "config", "e2e", "gpu_launches", "roofline")}
+    if sampler is not None:
+        sampler.terminate()
+        sampler.wait()
+    if rank == 0:
+        line["clocks"] = parse_clocks(clk_file)
+        line["cpu_baseline"] = None
+        if not args.no_cpu_baseline and args.workload == "c2":
+            line["cpu_baseline"] = cpu_baseline(args.cpu_n)
+        if extra_lines:
+            line["extras"] = extra_lines
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -577,21 +677,28 @@ def _peaks():
 
 
 def cpu_baseline(n):
-    from oracle import models as om
+    """The reference CPU path on this box's host cores (rank 0, N = 1): compiled per-state solver + torch-CPU
+    gradient stage on the first n states of the C2 workload; best of 3 passes after one warm-up pass of n / 4."""
+    from oracle import cpu_solver
 
+    cpu_solver.load()
     params, T, p = make_workload(n, 1000, "cpu")
     threads = _use_all_host_threads()
-    t0 = time.perf_counter()
-    x = params.clone().requires_grad_(True)
-    model = om.PcSaftPure(x)
-    nans, vp = model.vapor_pressure(T)
-    psat = torch.zeros(n, dtype=torch.float64)
-    psat[~nans] = vp.detach()
-    nans2, rho = model.liquid_density(T, torch.maximum(p, 1.05 * psat))
-    (vp.sum() + rho.sum()).backward()
-    dt = time.perf_counter() - t0
+    k = max(1, n // 4)
+    cpu_c2_pass(params[:k], T[:k], p[:k])
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        _, ts, tg = cpu_c2_pass(params, T, p)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, ts, tg)
+    dt, ts, tg = best
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"first {n} states of the C2 workload, one pass, oracle port (torch CPU, {threads} threads), {dt:.1f} s"}
+            "solve_stage_states_per_s": n / ts, "gradient_stage_states_per_s": n / tg,
+            "sample": f"first {n} states of the C2 workload, best of 3 passes: compiled per-state solver restating feos "
+                      f"(oracle/cpu_solver.cpp, g++ -O3 -fopenmp, {cpu_solver.threads()} threads) {ts:.2f} s + the reference's "
+                      f"Newton-step gradient stage under torch autograd on the CPU ({threads} threads) {tg:.2f} s"}
 
 
 if __name__ == "__main__":

@@ -30,12 +30,12 @@ SIGNATURES = {
     "feos_dev_mix_state_bwd": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_state_bwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _i64,
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_mix_point_order": ([_vp, _vp, _vp, _i64, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_order": ([_vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_order": ([_vp, ctypes.c_int32, _vp, _vp, _i64, ctypes.c_int, _vp, _vp], ctypes.c_int),
-    "feos_dev_mix_point_fwd": ([_vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_fwd": ([_vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_state": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_gc_point_fwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _i64,
+    "feos_dev_gc_point_fwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _i64,
                                ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_bwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
@@ -114,24 +114,49 @@ def state_order_enabled(n):
 # references) and their version counters -- storage addresses are not enough: the caching allocator hands the
 # address of a freed temperature tensor to the next one, and a permutation built for other temperatures, while
 # still giving correct results (any permutation does), no longer aligns the iteration counts.
+#
+# "Soft" tensors (the per-state PARAMETERS of the pure path) change in place every optimizer step of a fit; the
+# key of a state (code path, chain-length bin, T / T_c estimate) moves slowly with them, and a slightly stale
+# permutation costs a little lane utilisation, never correctness.  The permutation is therefore kept across their
+# version changes and recomputed every ORDER_REFRESH-th change (FEOS_B200_ORDER_REFRESH, 1 = every change), which
+# amortises the key kernel + radix sort (about 10 % of a C2 step) to under 1 %.
 _ORDER_CACHE = []
 _ORDER_CACHE_SIZE = 8
+ORDER_REFRESH = max(1, int(os.environ.get("FEOS_B200_ORDER_REFRESH", "16")))
 
 
-def cached_order(kind, tensors, compute):
-    """``compute()`` -> int32 order tensor (or None), memoised on (kind, identity + version of ``tensors``)."""
+class _OrderEntry:
+    __slots__ = ("kind", "refs", "versions", "soft_seen", "changes", "order", "n")
+
+
+def cached_order(kind, tensors, compute, n=None, soft=()):
+    """``compute()`` -> int32 order tensor (or None), memoised on (kind, identity + version of ``tensors``,
+    ``n``); ``soft`` tensors only age the entry; an entry whose order does not have ``n`` rows is never returned."""
     import weakref
 
     versions = tuple(t._version for t in tensors)
-    _ORDER_CACHE[:] = [e for e in _ORDER_CACHE if all(r() is not None for r in e[1])]
-    for k, (e_kind, refs, e_versions, order) in enumerate(_ORDER_CACHE):
-        if e_kind == kind and e_versions == versions and len(refs) == len(tensors) and all(r() is t for r, t in zip(refs, tensors)):
+    _ORDER_CACHE[:] = [e for e in _ORDER_CACHE if all(r() is not None for r in e.refs)]
+    for k, e in enumerate(_ORDER_CACHE):
+        if (e.kind == kind and e.versions == versions and e.n == n and len(e.refs) == len(tensors)
+                and all(r() is t for r, t in zip(e.refs, tensors))):
+            # soft tensors: a new version OR a new tensor object (parameters recomputed from other leaves every
+            # iteration) counts as one change
+            if len(soft) != len(e.soft_seen) or any(r() is not t or v != t._version for (r, v), t in zip(e.soft_seen, soft)):
+                e.soft_seen = tuple((weakref.ref(t), t._version) for t in soft)
+                e.changes += 1
+            if e.changes >= ORDER_REFRESH or (e.order is not None and n is not None and e.order.shape[0] != n):
+                del _ORDER_CACHE[k]
+                break
             _ORDER_CACHE.insert(0, _ORDER_CACHE.pop(k))
-            return order
-    order = compute()
-    _ORDER_CACHE.insert(0, (kind, tuple(weakref.ref(t) for t in tensors), versions, order))
+            return e.order
+    e = _OrderEntry()
+    e.kind, e.versions, e.n, e.changes = kind, versions, n, 0
+    e.refs = tuple(weakref.ref(t) for t in tensors)
+    e.soft_seen = tuple((weakref.ref(t), t._version) for t in soft)
+    e.order = compute()
+    _ORDER_CACHE.insert(0, e)
     del _ORDER_CACHE[_ORDER_CACHE_SIZE:]
-    return order
+    return e.order
 
 
 def measure_fp64_peak(iters=20000):

@@ -138,9 +138,10 @@ gc_point_queue_kernel(GcQueueSource src, int n, int bubble, int32_t* __restrict_
 }
 
 __global__ void __launch_bounds__(64)
-gc_point_retry_kernel(GcArgs g, const double* __restrict__ molefrac, int bubble, double* __restrict__ rho,
-                      double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
-                      const int32_t* __restrict__ retry_list, const int32_t* __restrict__ retry_count) {
+gc_point_retry_kernel(GcArgs g, const double* __restrict__ molefrac, const double* __restrict__ start_pressure, int bubble,
+                      double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
+                      int32_t* __restrict__ evals, const int32_t* __restrict__ retry_list,
+                      const int32_t* __restrict__ retry_count) {
   int count = *retry_count;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
     int64_t i = retry_list[k];
@@ -151,7 +152,8 @@ gc_point_retry_kernel(GcArgs g, const double* __restrict__ molefrac, int bubble,
     PointState st, se;
     MixEval es, ei;
     int ne = 0;
-    int rc = point_robust(b, bubble != 0, z0, st, es, ei, se, ne);
+    double p_start = (start_pressure ? start_pressure[i] : kDefaultStartPressure) / (src.T_ * kPaPerRed);
+    int rc = point_robust(b, bubble != 0, z0, p_start, st, es, ei, se, ne);
     if (evals) evals[i] += ne;
     store_gc_point(i, rc, bubble != 0, z0, src.T_, st, se, es, ei, rho, value, failed);
   }
@@ -347,8 +349,9 @@ extern "C" {
 
 int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
-                          const double* temperature, const double* molefracs, int64_t n, int bubble, double* rho,
-                          double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order, void* stream) {
+                          const double* temperature, const double* molefracs, const double* start_pressure, int64_t n,
+                          int bubble, double* rho, double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order,
+                          void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -384,7 +387,7 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   }
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
-  gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, bubble, rho, pressure, failed, evals, ws + 2, ws);
+  gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, start_pressure, bubble, rho, pressure, failed, evals, ws + 2, ws);
   FEOS_LAUNCH_OK();
   FEOS_CUDA(cudaFreeAsync(ws, s));
   return 0;
@@ -443,13 +446,14 @@ int feos_host_gc_point(const feos_gc_pair* pairs, int32_t n_pairs, const double*
   if (n == 0) return 0;
   if (int rc = check_tables(pairs, n_pairs, seg_params, n_seg, n_rec, kab, pair_index)) return rc;
   FEOS_ARG(temperature && molefracs && rho_out && status);
-  (void)pressure;
-  DevBuf dpairs, dseg, dkab, didx, dphi, dt, dz, drho, dfail;
+  DevBuf dpairs, dseg, dkab, didx, dphi, dt, dz, dp0, drho, dfail;
   if (dpairs.alloc(sizeof(GcPair) * n_pairs) || dseg.alloc(64 * (size_t)n_seg) || dkab.alloc(8 * (size_t)n_rec) ||
-      didx.alloc(4 * n) || dphi.alloc(16 * n) || dt.alloc(8 * n) || dz.alloc(8 * n) || drho.alloc(32 * n) || dfail.alloc(n)) {
+      didx.alloc(4 * n) || dphi.alloc(16 * n) || dt.alloc(8 * n) || dz.alloc(8 * n) || drho.alloc(32 * n) || dfail.alloc(n) ||
+      (pressure && dp0.alloc(8 * n))) {
     set_error("cudaMalloc failed for %lld states", (long long)n);
     return -2;
   }
+  if (pressure) FEOS_CUDA(cudaMemcpyAsync(dp0.p, pressure, 8 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dpairs.p, pairs, sizeof(GcPair) * n_pairs, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dseg.p, seg_params, 64 * (size_t)n_seg, cudaMemcpyHostToDevice, 0));
   if (n_rec) FEOS_CUDA(cudaMemcpyAsync(dkab.p, kab, 8 * (size_t)n_rec, cudaMemcpyHostToDevice, 0));
@@ -470,7 +474,8 @@ int feos_host_gc_point(const feos_gc_pair* pairs, int32_t n_pairs, const double*
   }
   int rc = feos_dev_gc_point_fwd(dpairs.as<feos_gc_pair>(), n_pairs, dseg.as<double>(), n_seg, dkab.as<double>(), n_rec,
                                  didx.as<int32_t>(), phi ? dphi.as<double>() : nullptr, dt.as<double>(), dz.as<double>(),
-                                 n, bubble, drho.as<double>(), nullptr, dfail.as<uint8_t>(), nullptr,
+                                 pressure ? dp0.as<double>() : nullptr, n, bubble, drho.as<double>(), nullptr,
+                                 dfail.as<uint8_t>(), nullptr,
                                  ordered ? dorder.as<int32_t>() : nullptr, nullptr);
   if (rc) return rc;
   std::vector<double> rho(4 * (size_t)n);

@@ -32,16 +32,20 @@ __device__ __forceinline__ PcSaftBinary& model_slot(double* smem) {
   return *reinterpret_cast<PcSaftBinary*>(smem + (size_t)kModelStride * threadIdx.x);
 }
 
+// flags of the bubble / dew entry points: the parameter rows / the k_ij row are ONE row shared by all states
+// (a fit of shared parameters: `pair.expand(n, 2, 8)`, `kij.expand(n, 2)` in the reference's API)
+constexpr int kSharedParams = FEOS_SHARED_PARAMS, kSharedKij = FEOS_SHARED_KIJ;
+
 __device__ __forceinline__ void load_mix(const double* __restrict__ params, const double* __restrict__ kij, int64_t i,
-                                         double (&prm)[16], double (&kk)[2]) {
-  const double2* p = reinterpret_cast<const double2*>(params + 16 * i);
+                                         int flags, double (&prm)[16], double (&kk)[2]) {
+  const double2* p = reinterpret_cast<const double2*>(params + ((flags & kSharedParams) ? 0 : 16 * i));
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     double2 t = __ldg(p + k);
     prm[2 * k] = t.x;
     prm[2 * k + 1] = t.y;
   }
-  double2 t = __ldg(reinterpret_cast<const double2*>(kij) + i);
+  double2 t = __ldg(reinterpret_cast<const double2*>(kij) + ((flags & kSharedKij) ? 0 : i));
   kk[0] = t.x;
   kk[1] = t.y;
 }
@@ -76,7 +80,7 @@ __device__ __forceinline__ void store_point(int64_t i, int rc, bool bubble, doub
 __global__ void __launch_bounds__(kMixBlock, FEOS_MIX_FWD_MINB)
 mix_point_fwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
                      const double* __restrict__ temperature, const double* __restrict__ molefrac, int64_t n, int bubble,
-                     double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
+                     int flags, double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
                      int32_t* __restrict__ evals, int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count,
                      const int32_t* __restrict__ order) {
   extern __shared__ double smem[];
@@ -87,7 +91,7 @@ mix_point_fwd_kernel(const double* __restrict__ params, const double* __restrict
   PcSaftBinary& b = model_slot(smem);
   {
     double prm[16], kk[2];
-    load_mix(params, kij, i, prm, kk);
+    load_mix(params, kij, i, flags, prm, kk);
     pcsaft_binary_init(b, prm, kk, T);
   }
   PointState st, se;
@@ -112,6 +116,7 @@ struct MixQueueSource {
   double* rho;
   double* value;
   uint8_t* failed;
+  int flags;
   __device__ __forceinline__ void dummy(PcSaftBinary& b) const {
     const double prm[16] = {1.0, 3.5, 150.0, 0, 0, 0, 0, 0, 1.0, 3.5, 150.0, 0, 0, 0, 0, 0};
     const double kk[2] = {0.0, 0.0};
@@ -121,7 +126,7 @@ struct MixQueueSource {
     T = temperature[i];
     z0 = molefrac[i];
     double prm[16], kk[2];
-    load_mix(params, kij, i, prm, kk);
+    load_mix(params, kij, i, flags, prm, kk);
     pcsaft_binary_init(b, prm, kk, T);
     return z0 > 0.0 && z0 < 1.0;
   }
@@ -142,22 +147,24 @@ mix_point_queue_kernel(MixQueueSource src, int n, int bubble, int32_t* __restric
 
 __global__ void __launch_bounds__(64)
 mix_point_retry_kernel(const double* __restrict__ params, const double* __restrict__ kij,
-                       const double* __restrict__ temperature, const double* __restrict__ molefrac, int bubble,
-                       double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
-                       int32_t* __restrict__ evals, const int32_t* __restrict__ retry_list,
-                       const int32_t* __restrict__ retry_count) {
+                       const double* __restrict__ temperature, const double* __restrict__ molefrac,
+                       const double* __restrict__ start_pressure, int bubble, int flags, double* __restrict__ rho,
+                       double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
+                       const int32_t* __restrict__ retry_list, const int32_t* __restrict__ retry_count) {
   int count = *retry_count;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
     int64_t i = retry_list[k];
     double prm[16], kk[2];
-    load_mix(params, kij, i, prm, kk);
+    load_mix(params, kij, i, flags, prm, kk);
     double T = temperature[i], z0 = molefrac[i];
     PcSaftBinary b;
     pcsaft_binary_init(b, prm, kk, T);
     PointState st, se;
     MixEval es, ei;
     int ne = 0;
-    int rc = point_robust(b, bubble != 0, z0, st, es, ei, se, ne);
+    // the caller's starting pressure (reduced), used where the solver cannot build a start of its own
+    double p_start = (start_pressure ? start_pressure[i] : kDefaultStartPressure) / (T * kPaPerRed);
+    int rc = point_robust(b, bubble != 0, z0, p_start, st, es, ei, se, ne);
     if (evals) evals[i] += ne;
     store_point<PcSaftBinary>(i, rc, bubble != 0, z0, T, st, se, es, ei, rho, value, failed);
   }
@@ -168,81 +175,119 @@ __device__ __noinline__ double mix_value(const MixCoef<double>& c, double r0, do
   return mix_helmholtz<double, double, 2, false>(c, r0, r1);
 }
 
+// Sum of `v` over the block into dst[k] (k < 19 gradient slots in shared memory `acc`): warp shuffle first --
+// shared-memory f64 atomics are compare-and-swap loops -- then one shared atomic per warp.
+__device__ __forceinline__ void warp_sum_to(double v, double* acc_k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(acc_k, v);
+}
+
 #ifndef FEOS_MIX_BWD_MINB
 #define FEOS_MIX_BWD_MINB 3  // 168 registers: 0.57 -> 0.51 ms per 1 M states (lanes are converged; occupancy pays)
 #endif
+// flags & kSharedParams: `params` is one [2,8] row and grad_params [2,8] receives the SUM over the states
+// (block reduction, one atomic per slot and block -- the fit-loss gradient of shared parameters, SURVEY section
+// 2.2 "fused with a per-block gradient reduction where parameters are shared"); likewise kSharedKij / grad_kij [2].
 __global__ void __launch_bounds__(kMixBlock, FEOS_MIX_BWD_MINB)
 mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
                      const double* __restrict__ temperature, const double* __restrict__ rho,
                      const uint8_t* __restrict__ failed, const int32_t* __restrict__ pos, const double* __restrict__ g,
-                     int64_t n, int bubble, double* __restrict__ grad_params, double* __restrict__ grad_kij,
+                     int64_t n, int bubble, int flags, double* __restrict__ grad_params, double* __restrict__ grad_kij,
                      double* __restrict__ grad_t, const int32_t* __restrict__ order) {
+  __shared__ double acc[18];
+  const bool sh_p = (flags & kSharedParams) && grad_params, sh_k = (flags & kSharedKij) && grad_kij;
+  if (sh_p || sh_k) {
+    if (threadIdx.x < 18) acc[threadIdx.x] = 0.0;
+    __syncthreads();
+  }
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (order) i = order[i];
-  if (failed[i]) {
-    if (grad_params) {
+  bool active = i < n;
+  if (active && order) i = order[i];
+  if (active && failed[i]) {
+    if (grad_params && !sh_p) {
       double2* gp = reinterpret_cast<double2*>(grad_params + 16 * i);
 #pragma unroll
       for (int k = 0; k < 8; ++k) gp[k] = make_double2(0.0, 0.0);
     }
-    if (grad_kij) reinterpret_cast<double2*>(grad_kij)[i] = make_double2(0.0, 0.0);
+    if (grad_kij && !sh_k) reinterpret_cast<double2*>(grad_kij)[i] = make_double2(0.0, 0.0);
     if (grad_t) grad_t[i] = 0.0;
-    return;
+    active = false;
   }
-  double prm[16], kk[2];
-  load_mix(params, kij, i, prm, kk);
-  double T = temperature[i];
-  const double2* rp = reinterpret_cast<const double2*>(rho + 4 * i);
-  double2 rv = rp[0], rl = rp[1];
-  double spec[2], inc[2];
-  if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
-  else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
-  PointWeights q;
-  double gi = g[pos ? (int64_t)pos[i] : i];
-  {
-    PcSaftBinary b;
-    pcsaft_binary_init(b, prm, kk, T);
-    MixEval es = b.eval(spec[0], spec[1]);
-    q = point_weights(es, spec, inc);
-    if (b.c.cat == kAssocNone) {
-      // non-associating state: closed-form coefficient adjoints + one reverse sweep through the coefficient stage
-      double p_red = point_pressure(es, mix_value(b.c, inc[0], inc[1]), spec, inc);
-      double o[19];
-      mix_point_grad_closed(prm, kk, T, b.c, spec, inc, q, p_red, gi, o);
-      if (grad_params) {
-        double2* gp = reinterpret_cast<double2*>(grad_params + 16 * i);
+  double o[19];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) gp[k] = make_double2(o[2 * k], o[2 * k + 1]);
+  for (int k = 0; k < 19; ++k) o[k] = 0.0;
+  if (active) {
+    double prm[16], kk[2];
+    load_mix(params, kij, i, flags, prm, kk);
+    double T = temperature[i];
+    const double2* rp = reinterpret_cast<const double2*>(rho + 4 * i);
+    double2 rv = rp[0], rl = rp[1];
+    double spec[2], inc[2];
+    if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
+    else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
+    PointWeights q;
+    double gi = g[pos ? (int64_t)pos[i] : i];
+    bool closed;
+    {
+      PcSaftBinary b;
+      pcsaft_binary_init(b, prm, kk, T);
+      MixEval es = b.eval(spec[0], spec[1]);
+      q = point_weights(es, spec, inc);
+      closed = b.c.cat == kAssocNone;
+      if (closed) {
+        // non-associating state: closed-form coefficient adjoints + one reverse sweep through the coefficient stage
+        double p_red = point_pressure(es, mix_value(b.c, inc[0], inc[1]), spec, inc);
+        mix_point_grad_closed(prm, kk, T, b.c, spec, inc, q, p_red, gi, o);
       }
-      if (grad_kij) reinterpret_cast<double2*>(grad_kij)[i] = make_double2(o[16], o[17]);
-      if (grad_t) grad_t[i] = o[18];
-      return;
     }
-  }
-  // only the directions whose gradient is requested (a k_ij fit needs 1 pass instead of 7)
-  int dirs[24];
-  int nd = 0;
-  if (grad_params)
-    for (int d = 0; d < 16; ++d) dirs[nd++] = d;
-  if (grad_kij) {
-    dirs[nd++] = 16;
-    dirs[nd++] = 17;
-  }
-  if (grad_t) dirs[nd++] = 18;
-  for (int d = 0; d < 3; ++d) dirs[nd + d] = -1;
+    if (!closed) {
+      // only the directions whose gradient is requested (a k_ij fit needs 1 pass instead of 7)
+      int dirs[24];
+      int nd = 0;
+      if (grad_params)
+        for (int d = 0; d < 16; ++d) dirs[nd++] = d;
+      if (grad_kij) {
+        dirs[nd++] = 16;
+        dirs[nd++] = 17;
+      }
+      if (grad_t) dirs[nd++] = 18;
+      for (int d = 0; d < 3; ++d) dirs[nd + d] = -1;
 #pragma unroll 1
-  for (int f = 0; f < nd; f += 3) {
-    double g3[3];
-    mix_point_grad_pass<3>(prm, kk, T, spec, inc, q, dirs + f, gi, g3);
+      for (int f = 0; f < nd; f += 3) {
+        double g3[3];
+        mix_point_grad_pass<3>(prm, kk, T, spec, inc, q, dirs + f, gi, g3);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      int d = dirs[f + k];
-      if (d < 0) break;
-      if (d < 16) grad_params[16 * i + d] = g3[k];
-      else if (d < 18) grad_kij[2 * i + (d - 16)] = g3[k];
-      else grad_t[i] = g3[k];
+        for (int k = 0; k < 3; ++k) {
+          int d = dirs[f + k];
+          if (d < 0) break;
+#pragma unroll
+          for (int j = 0; j < 19; ++j)
+            if (j == d) o[j] = g3[k];
+        }
+      }
     }
+    if (grad_params && !sh_p) {
+      double2* gp = reinterpret_cast<double2*>(grad_params + 16 * i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gp[k] = make_double2(o[2 * k], o[2 * k + 1]);
+    }
+    if (grad_kij && !sh_k) reinterpret_cast<double2*>(grad_kij)[i] = make_double2(o[16], o[17]);
+    if (grad_t) grad_t[i] = o[18];
+  }
+  if (sh_p || sh_k) {
+    if (sh_p) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) warp_sum_to(o[k], acc + k);
+    }
+    if (sh_k) {
+      warp_sum_to(o[16], acc + 16);
+      warp_sum_to(o[17], acc + 17);
+    }
+    __syncthreads();
+    int k = threadIdx.x;
+    if (k < 16 && sh_p && acc[k] != 0.0) atomicAdd(grad_params + k, acc[k]);
+    if (k >= 16 && k < 18 && sh_k && acc[k] != 0.0) atomicAdd(grad_kij + (k - 16), acc[k]);
   }
 }
 
@@ -253,7 +298,7 @@ mix_state_kernel(const double* __restrict__ params, const double* __restrict__ k
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double prm[16], kk[2];
-  load_mix(params, kij, i, prm, kk);
+  load_mix(params, kij, i, 0, prm, kk);
   PcSaftBinary b;
   pcsaft_binary_init(b, prm, kk, temperature[i]);
   double2 r = reinterpret_cast<const double2*>(density)[i];
@@ -286,12 +331,13 @@ int host_point(const double* params, const double* kij, const double* temperatur
   *n_ok = 0;
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && molefracs && rho_out && status);
-  (void)pressure;  // initial pressure of the reference API: the solver builds its own starting point
-  DevBuf dp, dk, dt, dz, drho, dfail;
-  if (dp.alloc(128 * n) || dk.alloc(16 * n) || dt.alloc(8 * n) || dz.alloc(8 * n) || drho.alloc(32 * n) || dfail.alloc(n)) {
+  DevBuf dp, dk, dt, dz, dp0, drho, dfail;
+  if (dp.alloc(128 * n) || dk.alloc(16 * n) || dt.alloc(8 * n) || dz.alloc(8 * n) || drho.alloc(32 * n) || dfail.alloc(n) ||
+      (pressure && dp0.alloc(8 * n))) {
     set_error("cudaMalloc failed for %lld states", (long long)n);
     return -2;
   }
+  if (pressure) FEOS_CUDA(cudaMemcpyAsync(dp0.p, pressure, 8 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 128 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dk.p, kij, 16 * n, cudaMemcpyHostToDevice, 0));
   FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
@@ -303,12 +349,12 @@ int host_point(const double* params, const double* kij, const double* temperatur
       set_error("cudaMalloc failed for %lld states", (long long)n);
       return -2;
     }
-    if (int rc = feos_dev_mix_point_order(dp.as<double>(), dt.as<double>(), dz.as<double>(), n, dorder.as<int32_t>(), nullptr))
+    if (int rc = feos_dev_mix_point_order(dp.as<double>(), dt.as<double>(), dz.as<double>(), n, 0, dorder.as<int32_t>(), nullptr))
       return rc;
   }
-  int rc = feos_dev_mix_point_fwd(dp.as<double>(), dk.as<double>(), dt.as<double>(), dz.as<double>(), n, bubble,
-                                  drho.as<double>(), nullptr, dfail.as<uint8_t>(), nullptr,
-                                  ordered ? dorder.as<int32_t>() : nullptr, nullptr);
+  int rc = feos_dev_mix_point_fwd(dp.as<double>(), dk.as<double>(), dt.as<double>(), dz.as<double>(),
+                                  pressure ? dp0.as<double>() : nullptr, n, bubble, 0, drho.as<double>(), nullptr,
+                                  dfail.as<uint8_t>(), nullptr, ordered ? dorder.as<int32_t>() : nullptr, nullptr);
   if (rc) return rc;
   std::vector<double> rho(4 * (size_t)n);
   FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 32 * n, cudaMemcpyDeviceToHost, 0));
@@ -328,8 +374,9 @@ int host_point(const double* params, const double* kij, const double* temperatur
 extern "C" {
 
 int feos_dev_mix_point_fwd(const double* params, const double* kij, const double* temperature,
-                           const double* molefracs, int64_t n, int bubble, double* rho, double* pressure,
-                           uint8_t* failed, int32_t* evals, const int32_t* order, void* stream) {
+                           const double* molefracs, const double* start_pressure, int64_t n, int bubble, int flags,
+                           double* rho, double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order,
+                           void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -347,8 +394,8 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   // default = one thread per state; FEOS_B200_POINT_KERNEL=queue selects the persistent work-queue kernel
   static const int variant = point_kernel_variant();
   if (variant == 0 || n < 65536) {
-    mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, kMixSmem, s>>>(params, kij, temperature, molefracs, n, bubble,
-                                                                           rho, pressure, failed, evals, ws + 2, ws, order);
+    mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, kMixSmem, s>>>(
+        params, kij, temperature, molefracs, n, bubble, flags, rho, pressure, failed, evals, ws + 2, ws, order);
   } else {
     static int blocks = 0;
     if (!blocks) {
@@ -358,21 +405,21 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
       FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mix_point_queue_kernel, kMixBlock, kMixSmem));
       blocks = sms * (per_sm > 0 ? per_sm : 1);
     }
-    MixQueueSource src{params, kij, temperature, molefracs, rho, pressure, failed};
+    MixQueueSource src{params, kij, temperature, molefracs, rho, pressure, failed, flags};
     int grid = (int)std::min<int64_t>(blocks, (n + kMixBlock - 1) / kMixBlock);
     mix_point_queue_kernel<<<grid, kMixBlock, kMixSmem, s>>>(src, (int)n, bubble, evals, ws + 2, ws, ws + 1);
   }
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
-  mix_point_retry_kernel<<<retry_grid, 64, 0, s>>>(params, kij, temperature, molefracs, bubble, rho, pressure, failed,
-                                                  evals, ws + 2, ws);
+  mix_point_retry_kernel<<<retry_grid, 64, 0, s>>>(params, kij, temperature, molefracs, start_pressure, bubble, flags, rho,
+                                                  pressure, failed, evals, ws + 2, ws);
   FEOS_LAUNCH_OK();
   FEOS_CUDA(cudaFreeAsync(ws, s));
   return 0;
 }
 
 int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
-                           const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble,
+                           const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble, int flags,
                            double* grad_params, double* grad_kij, double* grad_temperature, const int32_t* order,
                            void* stream) {
   clear_error();
@@ -380,7 +427,7 @@ int feos_dev_mix_point_bwd(const double* params, const double* kij, const double
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && rho && failed && g);
   mix_point_bwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, (cudaStream_t)stream>>>(
-      params, kij, temperature, rho, failed, pos, g, n, bubble, grad_params, grad_kij, grad_temperature, order);
+      params, kij, temperature, rho, failed, pos, g, n, bubble, flags, grad_params, grad_kij, grad_temperature, order);
   FEOS_LAUNCH_OK();
   return 0;
 }

@@ -21,6 +21,8 @@
 
 namespace feos {
 
+constexpr double kDefaultStartPressure = 1e5;  // Pa: start pressure when the caller gives none (the value of the reference's tests)
+
 struct PointState {
   double s;       // ln(total density of the specified phase)
   double u[2];    // ln(partial densities of the incipient phase)
@@ -201,12 +203,163 @@ FD int point_fast(const Model& mdl, bool bubble, double z0, PointState& st, MixE
   return point_solve(mdl, bubble, z0, 2, 0.02, 30, 1.0, st, es, ei, st_eval, evals);
 }
 
-// Retry path: fully converged starting states, many successive-substitution rounds, short Newton steps.
+// ---- retry path ------------------------------------------------------------------------------------
+// Stage A: the fast path's algorithm with fully converged starting states, many successive-substitution
+//          rounds and short Newton steps.
+// Stage B (dew points): the starting liquid composition is BRACKETED instead of iterated -- x <- y p / kappa(x)
+//          from x = y fails when no liquid of the vapour's composition exists (light component above its
+//          critical temperature, x_1 << y_1) and oscillates for strongly associating pairs.
+// Stage C: successive substitution on the K-factors with a REAL vapour phase (density iterations of both
+//          phases at the current pressure estimate, the structure of feos' bubble / dew point iteration,
+//          SURVEY.md Appendix B), then Newton -- for states whose vapour is far from ideal (near-critical).
+
+// f(s) = ln(y_1 / y_2) of the ideal vapour over the liquid of composition x_1 = 1 / (1 + e^-s), minus the target
 template <class Model>
-FD int point_robust(const Model& mdl, bool bubble, double z0, PointState& st, MixEval& es, MixEval& ei,
+FD bool dew_residual(const Model& mdl, double s, double s_target, double& f, double& x0, double& rho, double (&u)[2],
+                     int& evals) {
+  x0 = 1.0 / (1.0 + exp(-s));
+  rho = mdl.max_density(x0);
+  if (liquid_start(mdl, x0, rho, u, 40, 1e-8, evals) != kStatusOk) return false;
+  f = (u[0] - u[1]) - s_target;
+  return f == f;
+}
+
+template <class Model>
+FD int dew_start_bracketed(const Model& mdl, double z0, PointState& st, int& evals) {
+  const double s_t = log(z0 / (1.0 - z0));
+  double lo = -25.0, hi = 25.0, f_lo = 0.0, f_hi = 0.0, f, x0, rho, u[2];
+  // the ends: an almost pure liquid of component 2 (s = lo; its vapour holds almost no component 1: f < 0) and of
+  // component 1 (s = hi: f > 0).  An end without a liquid (component above its critical temperature) keeps the
+  // sign it would have; states between it and the root without a liquid are moved to that end's side.
+  bool ok_lo = dew_residual(mdl, lo, s_t, f_lo, x0, rho, u, evals);
+  bool ok_hi = dew_residual(mdl, hi, s_t, f_hi, x0, rho, u, evals);
+  if (!ok_lo && !ok_hi) return kStatusFailed;
+  if ((ok_lo && !(f_lo < 0.0)) || (ok_hi && !(f_hi > 0.0))) return kStatusFailed;
+  bool have = false;
+  for (int it = 0; it < 60; ++it) {
+    double s = 0.5 * (lo + hi);
+    if (ok_lo && ok_hi && (it & 1)) {  // regula falsi on alternate steps once both ends carry values
+      double t = lo - f_lo * (hi - lo) / (f_hi - f_lo);
+      if (t > lo + 0.01 * (hi - lo) && t < hi - 0.01 * (hi - lo)) s = t;
+    }
+    if (dew_residual(mdl, s, s_t, f, x0, rho, u, evals)) {
+      have = true;
+      if (f < 0.0) { lo = s; f_lo = f; ok_lo = true; } else { hi = s; f_hi = f; ok_hi = true; }
+      if (fabs(f) < 1e-6 || hi - lo < 1e-9) break;
+    } else {
+      have = false;
+      if (!ok_lo) lo = s; else if (!ok_hi) hi = s; else return kStatusFailed;
+      if (hi - lo < 1e-9) return kStatusFailed;
+    }
+  }
+  if (!have) return kStatusFailed;
+  double p = exp(u[0]) + exp(u[1]);  // total density of the ideal vapour = its reduced pressure
+  if (!(p > 0.0)) return kStatusFailed;
+  st.s = log(p);
+  st.u[0] = log(rho * x0);
+  st.u[1] = log(rho * (1.0 - x0));
+  return kStatusOk;
+}
+
+// Total density of a phase of composition x at reduced pressure p: Newton along the composition line from `rho`.
+template <class Model>
+FD MixEval density_at_pressure(const Model& mdl, double x0, double p, bool liquid, int iters, double& rho, int& evals) {
+  const double rho_max = mdl.max_density(x0);
+  MixEval e;
+  for (int it = 0;; ++it) {
+    e = mdl.eval(rho * x0, rho * (1.0 - x0));
+    evals += 1;
+    if (it == iters) break;
+    double dp = x0 * e.dp[0] + (1.0 - x0) * e.dp[1];
+    double next;
+    if (liquid) {
+      double step = fmin(fmax((p - e.p) / dp, -0.075 * rho_max), 0.075 * rho_max);
+      next = dp > 0.0 ? rho + step : fmin(1.1 * rho, 1.2 * rho_max);
+    } else {
+      next = dp > 0.0 ? fmax(rho + (p - e.p) / dp, 0.2 * rho) : 0.5 * rho;
+    }
+    if (!(next == next) || !(next > 0.0)) break;
+    if (fabs(next - rho) <= 1e-13 * rho) { rho = next; it = iters - 1; continue; }
+    rho = next;
+  }
+  return e;
+}
+
+template <class Model>
+FD int point_substitution(const Model& mdl, bool bubble, double z0, double p_start, PointState& st, int& evals) {
+  // start: the specified-composition liquid (bubble) / the bracketed liquid (dew) with its ideal vapour
+  double x0, y0, p, rho_l, rho_v;
+  if (bubble) {
+    double u[2];
+    rho_l = mdl.max_density(z0);
+    if (liquid_start(mdl, z0, rho_l, u, 40, 1e-8, evals) != kStatusOk) {
+      // no liquid at its ideal vapour's pressure (near-critical): come from the caller's starting pressure
+      // (the reference hands it to feos as Some(p0), src/pcsaft.rs:170-177), low enough that both density
+      // roots exist, and let the sweeps below climb
+      rho_l = mdl.max_density(z0);
+      MixEval e = density_at_pressure(mdl, z0, p_start, true, 40, rho_l, evals);
+      u[0] = log(rho_l * z0) + e.mu[0];
+      u[1] = log(rho_l * (1.0 - z0)) + e.mu[1];
+      if (!(u[0] == u[0]) || !(u[1] == u[1])) return kStatusFailed;
+    }
+    p = exp(u[0]) + exp(u[1]);
+    x0 = z0;
+    y0 = exp(u[0]) / p;
+  } else {
+    PointState t;
+    if (dew_start_bracketed(mdl, z0, t, evals) != kStatusOk) return kStatusFailed;
+    p = exp(t.s);
+    double r0 = exp(t.u[0]), r1 = exp(t.u[1]);
+    rho_l = r0 + r1;
+    x0 = r0 / rho_l;
+    y0 = z0;
+  }
+  if (!(p > 0.0) || !(p < 1e300)) return kStatusFailed;
+  rho_v = p;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    MixEval el = density_at_pressure(mdl, x0, p, true, 6, rho_l, evals);
+    MixEval ev = density_at_pressure(mdl, y0, p, false, 6, rho_v, evals);
+    // ln K_i = ln phi_i^L - ln phi_i^V,  ln phi_i = mu_i^res - ln(p / rho)
+    double lz = log(p / rho_l) - log(p / rho_v);
+    double k0 = exp(el.mu[0] - ev.mu[0] - lz), k1 = exp(el.mu[1] - ev.mu[1] - lz);
+    double n0, n1, w0;
+    if (bubble) { n0 = x0 * k0; n1 = (1.0 - x0) * k1; w0 = y0; } else { n0 = y0 / k0; n1 = (1.0 - y0) / k1; w0 = x0; }
+    double sum = n0 + n1;
+    if (!(sum > 0.0) || !(sum < 1e300)) return kStatusFailed;
+    // damped (geometric mean of old and new composition): plain substitution oscillates with growing amplitude
+    // for strongly non-ideal pairs
+    double g0 = sqrt(w0 * n0 / sum), g1 = sqrt((1.0 - w0) * n1 / sum);
+    double upd = g0 / (g0 + g1);
+    double change = fabs(upd - w0);
+    double fac = sqrt(fmin(fmax(sum, 0.5), 2.0));
+    if (bubble) { y0 = upd; p *= fac; } else { x0 = upd; p /= fac; }
+    if (change < 1e-7 && fabs(sum - 1.0) < 1e-7) break;
+  }
+  if (!(rho_l > 0.0) || !(rho_v > 0.0)) return kStatusFailed;
+  if (bubble) {
+    st.s = log(rho_l);
+    st.u[0] = log(rho_v * y0);
+    st.u[1] = log(rho_v * (1.0 - y0));
+  } else {
+    st.s = log(rho_v);
+    st.u[0] = log(rho_l * x0);
+    st.u[1] = log(rho_l * (1.0 - x0));
+  }
+  return kStatusOk;
+}
+
+template <class Model>
+FD int point_robust(const Model& mdl, bool bubble, double z0, double p_start, PointState& st, MixEval& es, MixEval& ei,
                     PointState& st_eval, int& evals) {
-  int rc = point_solve(mdl, bubble, z0, 40, 1e-8, 100, 0.3, st, es, ei, st_eval, evals);
-  return rc == kStatusOk ? kStatusOk : kStatusFailed;
+  if (!(z0 > 0.0) || !(z0 < 1.0)) return kStatusFailed;
+  if (point_solve(mdl, bubble, z0, 40, 1e-8, 100, 0.3, st, es, ei, st_eval, evals) == kStatusOk) return kStatusOk;
+  if (!bubble && dew_start_bracketed(mdl, z0, st, evals) == kStatusOk &&
+      point_newton(mdl, bubble, z0, st, es, ei, st_eval, 100, 0.3, evals) == kStatusOk)
+    return kStatusOk;
+  if (point_substitution(mdl, bubble, z0, p_start, st, evals) == kStatusOk &&
+      point_newton(mdl, bubble, z0, st, es, ei, st_eval, 100, 1.0, evals) == kStatusOk)
+    return kStatusOk;
+  return kStatusFailed;
 }
 
 // PC-SAFT binary with k_ij as a Model

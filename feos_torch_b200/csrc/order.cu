@@ -12,12 +12,12 @@ constexpr int kOrderBlock = 256;
 
 __global__ void __launch_bounds__(kOrderBlock)
 mix_order_key_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
-                     const double* __restrict__ molefrac, int64_t n, uint64_t* __restrict__ keys,
+                     const double* __restrict__ molefrac, int64_t n, int flags, uint64_t* __restrict__ keys,
                      int32_t* __restrict__ index) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   double prm[16];
-  const double2* p = reinterpret_cast<const double2*>(params + 16 * i);
+  const double2* p = reinterpret_cast<const double2*>(params + ((flags & FEOS_SHARED_PARAMS) ? 0 : 16 * i));
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     double2 t = __ldg(p + k);
@@ -108,7 +108,7 @@ int feos_dev_pure_order(const double* params, const double* temperature, int64_t
 }
 
 int feos_dev_mix_point_order(const double* params, const double* temperature, const double* molefracs, int64_t n,
-                             int32_t* order, void* stream) {
+                             int flags, int32_t* order, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -116,8 +116,8 @@ int feos_dev_mix_point_order(const double* params, const double* temperature, co
   cudaStream_t s = (cudaStream_t)stream;
   OrderScratch w;
   if (int rc = order_scratch(w, n, 0, kMixOrderBits, s)) return rc;
-  mix_order_key_kernel<<<grid_for(n, kOrderBlock), kOrderBlock, 0, s>>>(params, temperature, molefracs, n, w.keys_in,
-                                                                       w.index);
+  mix_order_key_kernel<<<grid_for(n, kOrderBlock), kOrderBlock, 0, s>>>(params, temperature, molefracs, n, flags,
+                                                                       w.keys_in, w.index);
   FEOS_LAUNCH_OK();
   return order_sort(w, n, 0, kMixOrderBits, order, s);
 }

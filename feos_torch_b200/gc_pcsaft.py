@@ -106,7 +106,7 @@ def _check_association(pairs, seg_params):
 
 class _GcPoint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, seg_params, kab, phi, temperature, molefracs, bubble, tables, orders):
+    def forward(ctx, seg_params, kab, phi, temperature, molefracs, pressure, bubble, tables, orders):
         pairs_dev, pair_index, n_pairs = tables
         order, order_bwd = orders
         n = temperature.shape[0]
@@ -118,7 +118,7 @@ class _GcPoint(torch.autograd.Function):
             _lib.timed_call(
                 "feos_dev_gc_point_fwd", _lib.ptr(pairs_dev), n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                 _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
-                _lib.ptr(molefracs), n, int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None,
+                _lib.ptr(molefracs), _lib.ptr(pressure), n, int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None,
                 _lib.ptr(order), _stream(),
             )
             out, pos = compact(failed, val)
@@ -146,7 +146,7 @@ class _GcPoint(torch.autograd.Function):
             )
         if need_kab and g_kab is None:
             g_kab = torch.zeros_like(kab)
-        return g_seg, g_kab, g_phi, g_t, None, None, None, None
+        return g_seg, g_kab, g_phi, g_t, None, None, None, None, None
 
 
 class _GcState(torch.autograd.Function):
@@ -223,9 +223,14 @@ class GcPcSaftMix:
     def _back(self, t):
         return _back(t, self._out_device)
 
-    def _point(self, temperature, molefracs, bubble):
+    def _point(self, temperature, molefracs, pressure, bubble):
+        for name, x in (("temperature", temperature), ("molefracs", molefracs), ("pressure", pressure)):
+            if x is not None and (x.dim() != 1 or x.shape[0] != self._n):
+                raise ValueError(f"{name} must have shape [{self._n}] (one entry per state of the constructor lists; the model "
+                                 f"is not reduced after failed states, unlike the reference's `reduce`), got {tuple(x.shape)}")
         t = _prep(temperature, self._dev)
         z = _prep(molefracs.detach(), self._dev)
+        p0 = None if pressure is None else _prep(pressure.detach(), self._dev)
         tables = (self._pairs, self._pair_index, self._n_pairs)
         orders = (None, None)
         n = t.shape[0]
@@ -241,22 +246,25 @@ class GcPcSaftMix:
                 return o
             key = (self._pair_index, temperature, molefracs)
             dev = self._dev.index
-            orders = (_lib.cached_order(("gc", dev), key, lambda: compute(0)),
-                      _lib.cached_order(("gc-pair", dev), key, lambda: compute(1)))
-        val, failed, _ = _GcPoint.apply(self._seg, self._kab, self._phi, t, z, bubble, tables, orders)
+            orders = (_lib.cached_order(("gc", dev), key, lambda: compute(0), n=n),
+                      _lib.cached_order(("gc-pair", dev), key, lambda: compute(1), n=n))
+        val, failed, _ = _GcPoint.apply(self._seg, self._kab, self._phi, t, z, p0, bubble, tables, orders)
         return self._back(val), self._back(failed.bool())
 
     def bubble_point(self, temperature, liquid_molefracs, pressure):
-        """(p_bubble [n_ok] in Pa, failed mask [N]) -- gc_pcsaft.py:470-490."""
-        return self._point(temperature, liquid_molefracs, True)
+        """(p_bubble [n_ok] in Pa, failed mask [N]) -- gc_pcsaft.py:470-490.  `pressure`: the reference's starting
+        value (src/gc_pcsaft.rs:125-132), used by the retry path where it cannot build a start of its own."""
+        return self._point(temperature, liquid_molefracs, pressure, True)
 
     def dew_point(self, temperature, vapor_molefracs, pressure):
         """(p_dew [n_ok] in Pa, failed mask [N]) -- gc_pcsaft.py:492-512."""
-        return self._point(temperature, vapor_molefracs, False)
+        return self._point(temperature, vapor_molefracs, pressure, False)
 
     def derivatives(self, temperature, density):
         """(a [N], p/kT [N], mu_i [N,2], v_i [N,2]) at (T, rho [N,2]) -- gc_pcsaft.py:443-468; carries gradients
         w.r.t. the segment parameters, k_ab, phi, T and rho."""
+        if temperature.shape[0] != self._n or density.shape != (self._n, 2):
+            raise ValueError(f"temperature / density must have shapes [{self._n}] / [{self._n}, 2]")
         t = _prep(temperature, self._dev)
         r = _prep(density, self._dev)
         tables = (self._pairs, self._pair_index, self._n_pairs)
@@ -264,7 +272,8 @@ class GcPcSaftMix:
         return self._back(a), self._back(p), self._back(mu), self._back(v)
 
     def helmholtz_energy_density(self, temperature, density, kab=None):
-        """a = A/(V kT) [N,1] -- gc_pcsaft.py:116-253."""
+        """a = A/(V kT) [N,1] -- gc_pcsaft.py:116-253.  `kab` is part of the reference's signature (gc_pcsaft.py:116)
+        but never read there (the dispersion term uses `self.kab`, gc_pcsaft.py:188): it has no effect here either."""
         return self.derivatives(temperature, density)[0][:, None]
 
 

@@ -8,12 +8,33 @@ and ``temperature``; mole fractions and the starting pressure carry none (pcsaft
 import torch
 
 from . import _lib
-from .pcsaft_pure import _back, _cuda_device, _prep, _stream, compact
+from .pcsaft_pure import _back, _check_rows, _cuda_device, _prep, _stream, compact
+
+
+SHARED_PARAMS, SHARED_KIJ = 1, 2  # include/feos_b200.h: FEOS_SHARED_PARAMS, FEOS_SHARED_KIJ
+
+
+def _shared_row(t, inner):
+    """If ``t`` [N, *inner] is ONE row expanded along the batch axis (``row.expand(N, *inner)`` -- how a fit of shared
+    parameters is written in the reference's API, BASELINE config C4), return that row as a tensor of shape ``inner``
+    that is part of the autograd graph of ``t`` (its view base), else None.  The kernels then read the one row and the
+    backward kernel reduces its gradient over the states itself, instead of N materialised rows and an [N, *inner]
+    gradient summed afterwards by torch."""
+    base = t._base
+    if (base is None or t.dim() != len(inner) + 1 or t.shape[0] < 2 or t.stride(0) != 0
+            or tuple(t.shape[1:]) != tuple(inner) or t.dtype != torch.float64 or base.dtype != torch.float64):
+        return None
+    if tuple(base.shape) != tuple(inner) or not base.is_contiguous() or base.data_ptr() != t.data_ptr():
+        return None
+    want = tuple(base.stride())
+    if tuple(t.stride()[1:]) != want:
+        return None
+    return base
 
 
 class _MixPoint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, params, kij, temperature, molefracs, bubble, order):
+    def forward(ctx, params, kij, temperature, molefracs, pressure, bubble, order, flags):
         n = temperature.shape[0]
         dev = params.device
         rho = torch.empty((n, 4), dtype=torch.float64, device=dev)
@@ -21,14 +42,15 @@ class _MixPoint(torch.autograd.Function):
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.timed_call(
-                "feos_dev_mix_point_fwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(molefracs), n,
-                int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None, _lib.ptr(order), _stream(),
+                "feos_dev_mix_point_fwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(molefracs),
+                _lib.ptr(pressure), n, int(bubble), flags, _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None,
+                _lib.ptr(order), _stream(),
             )
             out, pos = compact(failed, val)
         # the backward kernel runs no iteration: the order only pays where code paths are mixed, and costs
         # scattered gradient writes otherwise -- it keeps the input order
         ctx.save_for_backward(params, kij, temperature, rho, failed, pos, None)
-        ctx.bubble = int(bubble)
+        ctx.bubble, ctx.flags = int(bubble), flags
         ctx.mark_non_differentiable(rho, failed)
         return out, failed, rho
 
@@ -38,16 +60,17 @@ class _MixPoint(torch.autograd.Function):
         n = temperature.shape[0]
         g = g_val.contiguous()
         need_p, need_k, need_t = ctx.needs_input_grad[:3]
-        gp = torch.empty_like(params) if need_p else None
-        gk = torch.empty_like(kij) if need_k else None
+        # shared rows: the kernel accumulates the sum over the states (zero first); per-state rows are written
+        gp = (torch.zeros_like(params) if ctx.flags & SHARED_PARAMS else torch.empty_like(params)) if need_p else None
+        gk = (torch.zeros_like(kij) if ctx.flags & SHARED_KIJ else torch.empty_like(kij)) if need_k else None
         gt = torch.empty_like(temperature) if need_t else None
         with torch.cuda.device(params.device):
             _lib.timed_call(
                 "feos_dev_mix_point_bwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(rho),
-                _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, ctx.bubble, _lib.ptr(gp), _lib.ptr(gk), _lib.ptr(gt),
-                _lib.ptr(order), _stream(),
+                _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, ctx.bubble, ctx.flags, _lib.ptr(gp), _lib.ptr(gk),
+                _lib.ptr(gt), _lib.ptr(order), _stream(),
             )
-        return gp, gk, gt, None, None, None
+        return gp, gk, gt, None, None, None, None, None
 
 
 class _MixState(torch.autograd.Function):
@@ -83,31 +106,69 @@ class _MixState(torch.autograd.Function):
 
 
 class PcSaftMix:
-    """parameters [N, 2, 8] (rows as in PcSaftPure), kij [N, 2] = (k_ij, epsilon_k_aibj; 0 = combining rule)."""
+    """parameters [N, 2, 8] (rows as in PcSaftPure), kij [N, 2] = (k_ij, epsilon_k_aibj; 0 = combining rule).
+    Non-associating mixtures of n > 2 components ([N, n, 8], n <= 4; the reference's Helmholtz energy is general in
+    n for them, pcsaft_mix.py:73-90) support `derivatives` / `helmholtz_energy_density`; bubble / dew points are
+    binary like the reference's native layer (src/pcsaft.rs:173, :206).
+
+    Shared parameters: `row.expand(N, 2, 8)` / `kij_row.expand(N, 2)` are recognised (stride 0 along the batch) and
+    handled as ONE row -- nothing is materialised per state and the gradient sum over the states is reduced inside
+    the backward kernel."""
 
     def __init__(self, parameters, kij=None):
-        if parameters.dim() != 3 or parameters.shape[1] != 2 or parameters.shape[2] != 8:
-            raise ValueError("parameters must have shape [N, 2, 8] (binary mixtures)")
+        if parameters.dim() != 3 or parameters.shape[2] != 8 or not 2 <= parameters.shape[1] <= 4:
+            raise ValueError("parameters must have shape [N, n, 8] with n = 2 (n = 3, 4: non-associating state functions only)")
         _lib.load()
+        self._n = parameters.shape[0]
+        self._nc = parameters.shape[1]
         self._out_device = parameters.device
         self._dev = _cuda_device(parameters)
-        self._params = _prep(parameters, self._dev)
         if kij is None:
             # the reference accepts kij=None in the signature but needs it (pcsaft_mix.py:141); zero
             # k_ij / combining-rule eps_AiBj is what "no kij" means physically
             kij = torch.zeros((parameters.shape[0], 2), dtype=torch.float64, device=parameters.device)
         if kij.shape != (parameters.shape[0], 2):
             raise ValueError("kij must have shape [N, 2]")
-        self._kij = _prep(kij, self._dev)
-        self._check_association(parameters)
         self._source = (parameters, kij)
+        self._flags = 0
+        self._params_row = _shared_row(parameters, (2, 8)) if self._nc == 2 else None
+        self._kij_row = _shared_row(kij, (2,)) if self._nc == 2 else None
+        self._params_full = self._kij_full = None
+        if self._params_row is not None:
+            self._flags |= SHARED_PARAMS
+            self._params_row = _prep(self._params_row, self._dev)
+        else:
+            self._params_full = _prep(parameters, self._dev)
+        if self._kij_row is not None:
+            self._flags |= SHARED_KIJ
+            self._kij_row = _prep(self._kij_row, self._dev)
+        else:
+            self._kij_full = _prep(kij, self._dev)
+        self._check_association(parameters if self._params_row is None else self._params_row[None])
 
-    @staticmethod
-    def _check_association(parameters):
+    # per-state [N, n, 8] / [N, 2] device tensors for the consumers that want them (state functions)
+    @property
+    def _params(self):
+        if self._params_full is None:
+            self._params_full = _prep(self._source[0], self._dev)
+        return self._params_full
+
+    @property
+    def _kij(self):
+        if self._kij_full is None:
+            self._kij_full = _prep(self._source[1], self._dev)
+        return self._kij_full
+
+    def _check_association(self, parameters):
         na, nb = parameters[:, :, 6].detach(), parameters[:, :, 7].detach()
-        # pcsaft_mix.py:120-121 (can never trigger for two components; kept for API parity)
-        if bool((torch.count_nonzero(na + nb, dim=1) > 2).any()):
+        count = torch.count_nonzero(na + nb, dim=1)
+        # pcsaft_mix.py:120-121
+        if bool((count > 2).any()):
             raise Exception("Only up to two associating components are allowed!")
+        if self._nc > 2 and bool((count > 0).any() or (parameters[:, :, 3].detach() != 0).any()):
+            raise NotImplementedError(
+                "mixtures of more than two components are supported for non-associating, non-polar components only "
+                "(the reference evaluates association and k_ij for binaries, pcsaft_mix.py:118-152)")
 
     @property
     def parameters(self):
@@ -120,9 +181,15 @@ class PcSaftMix:
     def _back(self, t):
         return _back(t, self._out_device)
 
-    def _point(self, temperature, molefracs, bubble):
+    def _point(self, temperature, molefracs, pressure, bubble):
+        if self._nc != 2:
+            raise NotImplementedError("bubble / dew points are binary (as the reference's native layer, src/pcsaft.rs:173)")
+        _check_rows(self._n, temperature=temperature, molefracs=molefracs, pressure=pressure)
         t = _prep(temperature, self._dev)
         z = _prep(molefracs.detach(), self._dev)
+        p0 = None if pressure is None else _prep(pressure.detach(), self._dev)
+        params = self._params_row if self._params_row is not None else self._params_full
+        kij = self._kij_row if self._kij_row is not None else self._kij_full
         order = None
         n = t.shape[0]
         if _lib.state_order_enabled(n):
@@ -131,25 +198,29 @@ class PcSaftMix:
             def compute():
                 o = torch.empty((n,), dtype=torch.int32, device=self._dev)
                 with torch.cuda.device(self._dev):
-                    _lib.timed_call("feos_dev_mix_point_order", _lib.ptr(self._params), _lib.ptr(t), _lib.ptr(z), n,
-                                    _lib.ptr(o), _stream())
+                    _lib.timed_call("feos_dev_mix_point_order", _lib.ptr(params), _lib.ptr(t), _lib.ptr(z), n,
+                                    self._flags & SHARED_PARAMS, _lib.ptr(o), _stream())
                 return o
-            order = _lib.cached_order(("mix", self._dev.index), (temperature, molefracs), compute)
-        val, failed, _ = _MixPoint.apply(self._params, self._kij, t, z, bubble, order)
+            order = _lib.cached_order(("mix", self._dev.index), (temperature, molefracs), compute, n=n)
+        val, failed, _ = _MixPoint.apply(params, kij, t, z, p0, bubble, order, self._flags)
         return self._back(val), self._back(failed.bool())
 
     def bubble_point(self, temperature, liquid_molefracs, pressure):
-        """(p_bubble [n_ok] in Pa, failed mask [N]) -- pcsaft_mix.py:422-444.  `pressure` is the
-        reference's starting value for its CPU solver; the kernels build their own starting point."""
-        return self._point(temperature, liquid_molefracs, True)
+        """(p_bubble [n_ok] in Pa, failed mask [N]) -- pcsaft_mix.py:422-444.  `pressure` is the starting value the
+        reference hands to its CPU solver (src/pcsaft.rs:170-177); here the fast path builds its own start and the
+        retry path starts its successive substitution from it where no start of its own exists (near-critical)."""
+        return self._point(temperature, liquid_molefracs, pressure, True)
 
     def dew_point(self, temperature, vapor_molefracs, pressure):
-        """(p_dew [n_ok] in Pa, failed mask [N]) -- pcsaft_mix.py:446-468."""
-        return self._point(temperature, vapor_molefracs, False)
+        """(p_dew [n_ok] in Pa, failed mask [N]) -- pcsaft_mix.py:446-468.  `pressure`: see bubble_point."""
+        return self._point(temperature, vapor_molefracs, pressure, False)
 
     def derivatives(self, temperature, density):
         """(a [N], p/kT [N], mu_i^res/kT [N,2], v_i [N,2]) at (T, rho [N,2]) -- pcsaft_mix.py:395-420; carries
         gradients w.r.t. parameters, kij, T and rho like the reference's hyper-dual evaluation under autograd."""
+        _check_rows(self._n, temperature=temperature, density=density)
+        if density.dim() != 2 or density.shape[1] != self._nc:
+            raise ValueError(f"density must have shape [N, {self._nc}]")
         t = _prep(temperature, self._dev)
         r = _prep(density, self._dev)
         a, p, mu, v = _MixState.apply(self._params, self._kij, t, r)

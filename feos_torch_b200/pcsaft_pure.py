@@ -186,6 +186,21 @@ def _back(t, out_device):
     return t.to(out_device)
 
 
+def _check_rows(n, **tensors):
+    """Every per-state tensor must have one row per state of the model.  The reference's native layer panics on any
+    length mismatch (ndarray Zip, src/pcsaft.rs:86-88, :157-162); the C ABI only sees raw pointers, so the check lives here.
+    Unlike the reference (`reduce`, pcsaft_pure.py:235-243, pcsaft_mix.py:470-479) the model object is NOT reduced after a call with failed
+    states: follow-up calls take full-length [N] tensors again."""
+    for name, t in tensors.items():
+        if t is None:
+            continue
+        if t.dim() < 1 or t.shape[0] != n:
+            raise ValueError(
+                f"{name} must have one row per state of the model ({n}), got shape {tuple(t.shape)}. "
+                "This model is not reduced after a call with failed states (the reference mutates it, `reduce`): "
+                "pass full-length tensors, or build a new model from the surviving parameter rows.")
+
+
 def compact(failed, values, out_cols=None):
     """Rows of ``values`` [n] or [n, c] whose state converged, in input order, plus the row map
     ``pos`` [n] (int32, -1 = failed).  One host synchronisation (the output length)."""
@@ -215,8 +230,10 @@ def _state_order(params, temperature, key):
         o = torch.empty((n,), dtype=torch.int32, device=params.device)
         _lib.timed_call("feos_dev_pure_order", _lib.ptr(params), _lib.ptr(temperature), n, _lib.ptr(o), _stream())
         return o
+    # key = (parameter tensor, temperature tensor) of the caller: the temperatures identify the data set (hard), the
+    # parameters are "soft" -- an optimizer updates them in place every step, see _lib.cached_order
     with torch.cuda.device(params.device):
-        return _lib.cached_order(("pure", params.device.index), key, compute)
+        return _lib.cached_order(("pure", params.device.index), key[1:], compute, n=n, soft=key[:1])
 
 
 class _PureVle(torch.autograd.Function):
@@ -363,6 +380,7 @@ class PcSaftPure:
         if parameters.dim() != 2 or parameters.shape[1] != 8:
             raise ValueError("parameters must have shape [N, 8]")
         _lib.load()  # fail loudly before any work if the CUDA extension is missing
+        self._n = parameters.shape[0]
         self._out_device = parameters.device
         self._dev = _cuda_device(parameters)
         self._source = parameters
@@ -395,24 +413,29 @@ class PcSaftPure:
         if hit is not None and hit[0]() is t and hit[1] == t._version:
             return hit[2]
         d = _prep(t, self._dev)
+        for k in [k for k, v in self._uploads.items() if v[0]() is None]:
+            del self._uploads[k]  # tensors that are gone (their id may be reused)
         self._uploads[id(t)] = (weakref.ref(t), t._version, d)
         return d
 
     # ---- properties on the phase-equilibrium hot path ------------------------------------------
     def vapor_pressure(self, temperature):
         """(failed mask [N], p_sat [n_ok] in Pa) -- pcsaft_pure.py:201-215."""
+        _check_rows(self._n, temperature=temperature)
         t = self._state(temperature)
         val, failed, _ = _PureVle.apply(self._params, t, 0, _state_order(self._params, t, (self._source, temperature)))
         return self._back(failed.bool()), self._back(val)
 
     def equilibrium_liquid_density(self, temperature):
         """(failed mask [N], rho_L^sat [n_ok] in kmol/m^3) -- pcsaft_pure.py:217-233."""
+        _check_rows(self._n, temperature=temperature)
         t = self._state(temperature)
         val, failed, _ = _PureVle.apply(self._params, t, 1, _state_order(self._params, t, (self._source, temperature)))
         return self._back(failed.bool()), self._back(val)
 
     def liquid_density(self, temperature, pressure):
         """(failed mask [N], rho_L(T, p) [n_ok] in kmol/m^3) -- pcsaft_pure.py:184-199."""
+        _check_rows(self._n, temperature=temperature, pressure=pressure)
         t = self._state(temperature)
         p = self._state(pressure)
         val, failed, _ = _PureRhoTp.apply(self._params, t, p, _state_order(self._params, t, (self._source, temperature)))
@@ -422,6 +445,7 @@ class PcSaftPure:
     def derivatives(self, temperature, density):
         """(a, p/kT, d(p/kT)/drho) at (T, rho [1/A^3]) -- pcsaft_pure.py:180-182; carries gradients with
         respect to the parameters, T and rho like the reference's Dual3 evaluation under torch autograd."""
+        _check_rows(self._n, temperature=temperature, density=density)
         t = _prep(temperature, self._dev)
         r = _prep(density, self._dev)
         a, p, dp = _PureState.apply(_wait_chunks(self._params), t, r)

@@ -129,11 +129,14 @@ int feos_host_pcsaft_liquid_density(const double* params, const double* temperat
 /* binary mixture with k_ij: PcSaft.bubble_point / PcSaft.dew_point                            */
 /* ------------------------------------------------------------------------------------------ */
 
+#define FEOS_SHARED_PARAMS 1
+#define FEOS_SHARED_KIJ 2
+
 /* State order of the bubble / dew kernels (see feos_dev_pure_order), keyed on (code path, T / eps_bar bin, x).
- *   params [n,2,8], temperature [n], molefracs [n]      in
+ *   params [n,2,8] (or one [2,8] row with FEOS_SHARED_PARAMS in `flags`), temperature [n], molefracs [n]      in
  *   order [n]   permutation of 0 .. n-1                  out */
 int feos_dev_mix_point_order(const double* params, const double* temperature, const double* molefracs, int64_t n,
-                             int32_t* order, void* stream);
+                             int flags, int32_t* order, void* stream);
 /*   pair_index [n] (state -> molecule pair, 0 <= pair_index < n_pairs), temperature [n], molefracs [n];
  *   pair_only != 0: grouped by molecule pair, input order inside a pair (for the backward kernel, which runs
  *   no iteration: only the code path matters and neighbouring states keep its memory accesses local) */
@@ -146,15 +149,25 @@ int feos_dev_gc_point_order(const int32_t* pair_index, int32_t n_pairs, const do
  * (feos_torch/pcsaft_mix.py:422-468).
  *   params [n,2,8], kij [n,2] = (k_ij, eps_AiBj; 0 = combining rule), temperature [n], molefracs [n]
  *   rho [n,4] = (rho_V1, rho_V2, rho_L1, rho_L2) in 1/A^3 (filter_binary order, src/pcsaft.rs:225-228)
+ *   start_pressure [n] in Pa (may be NULL = 1e5 Pa): the `pressure` argument of the reference's bubble_point /
+ *     dew_point, handed to feos as Some(p0) (src/pcsaft.rs:170-177, :203-210).  The fast path builds its own start
+ *     (zero-pressure liquid + ideal vapour); the retry path starts its successive substitution from p0 where no such
+ *     start exists (near-critical states), as the reference's solver starts from it.
+ *   flags: FEOS_SHARED_PARAMS = `params` is ONE [2,8] row shared by all states, FEOS_SHARED_KIJ = `kij` is one [2]
+ *     row (fit of shared parameters, BASELINE config C4: the reference expands them to [n,2,8] / [n,2])
  *   pressure [n] in Pa (may be NULL), failed [n], evals [n] (may be NULL), order [n] (may be NULL, see above) */
 int feos_dev_mix_point_fwd(const double* params, const double* kij, const double* temperature,
-                           const double* molefracs, int64_t n, int bubble, double* rho, double* pressure,
-                           uint8_t* failed, int32_t* evals, const int32_t* order, void* stream);
+                           const double* molefracs, const double* start_pressure, int64_t n, int bubble, int flags,
+                           double* rho, double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order,
+                           void* stream);
 
 /* Gradient of sum_i g[i] * pressure[i] w.r.t. params [n,2,8], kij [n,2] and T [n] (any may be NULL);
- * replaces torch autograd through pcsaft_mix.py:435-444 / :459-468.  `pos` as for the pure path. */
+ * replaces torch autograd through pcsaft_mix.py:435-444 / :459-468.  `pos` as for the pure path.
+ * With FEOS_SHARED_PARAMS / FEOS_SHARED_KIJ in `flags`, grad_params is [2,8] / grad_kij is [2] and receives the SUM
+ * over the states, ACCUMULATED into (zero first): the reduction torch would run over an expanded [n,2,8] gradient
+ * is fused into the kernel (warp shuffle -> shared memory -> one atomic per slot and block). */
 int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
-                           const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble,
+                           const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble, int flags,
                            double* grad_params, double* grad_kij, double* grad_temperature, const int32_t* order,
                            void* stream);
 
@@ -171,8 +184,8 @@ int feos_dev_mix_state_bwd(const double* params, const double* kij, const double
                            void* stream);
 
 /* PcSaft.bubble_point / dew_point(parameters f64[n,2,8], kij f64[n,2], temperature, molefracs, pressure)
- * -> (f64[n_ok,4], bool[n]) with host buffers (src/pcsaft.rs:44-79).  `pressure` (the reference's
- * starting value) is accepted and ignored. */
+ * -> (f64[n_ok,4], bool[n]) with host buffers (src/pcsaft.rs:44-79).  `pressure` = the reference's starting
+ * value (may be NULL), see `start_pressure` of feos_dev_mix_point_fwd. */
 int feos_host_pcsaft_bubble_point(const double* params, const double* kij, const double* temperature,
                                   const double* liquid_molefracs, const double* pressure, int64_t n, double* rho_out,
                                   uint8_t* status, int64_t* n_ok);
@@ -204,12 +217,14 @@ typedef struct feos_gc_pair {
  *   the binary segment records, pair_index [n] (state -> pair), phi [n,2] (may be NULL = 1),
  *   temperature [n].  Device pointers for feos_dev_*, host pointers for feos_host_*.
  *   order [n] (may be NULL): state order from feos_dev_gc_point_order, see feos_dev_mix_point_order.
+ *   start_pressure [n] (may be NULL): as for feos_dev_mix_point_fwd (src/gc_pcsaft.rs:125-132, :160-167).
  * Replaces PyGcPcSaft::bubble_point / dew_point -> bubble_point_ / dew_point_ (src/gc_pcsaft.rs:71-99,
  * :103-171) fused with GcPcSaftMix.bubble_point / dew_point (feos_torch/gc_pcsaft.py:470-512). */
 int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
-                          const double* temperature, const double* molefracs, int64_t n, int bubble, double* rho,
-                          double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order, void* stream);
+                          const double* temperature, const double* molefracs, const double* start_pressure, int64_t n,
+                          int bubble, double* rho, double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order,
+                          void* stream);
 
 /* Gradient of sum_i g[i] * pressure[i].  grad_seg_params [n_seg,8] and grad_kab [n_rec] are shared by
  * all states and are ACCUMULATED into (zero them first); grad_phi [n,2] and grad_temperature [n] are

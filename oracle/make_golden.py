@@ -142,7 +142,9 @@ def _point_entry(make_model, leaves, T, z, p0, bubble):
     return e
 
 
-def mix_golden(ref):
+def mix_golden(ref, subset=None):
+    """``subset``: indices into the category grid (reproducibility test: a slice of the grid through the same code);
+    the random grid is skipped then."""
     out = {}
     P = torch.tensor(cases.MIX_PARAMS, dtype=F64)
     K = torch.tensor(cases.MIX_KIJ, dtype=F64)
@@ -165,6 +167,8 @@ def mix_golden(ref):
                 rows.append(i)
                 temps.append(t)
                 zs.append(z)
+    if subset is not None:
+        rows, temps, zs = ([v[i] for i in subset] for v in (rows, temps, zs))
     idx = torch.tensor(rows)
     Pg, Kg = P[idx], K[idx]
     Tt = torch.tensor(temps, dtype=F64)
@@ -176,6 +180,30 @@ def mix_golden(ref):
         k = Kg.clone().requires_grad_(True)
         entry["bubble" if bubble else "dew"] = _point_entry(lambda: ref.PcSaftMix(x, k), {"params": x, "kij": k}, Tt, zt, p0, bubble)
     out["category_grid"] = entry
+
+    # seeded random (category, T, z) states: masks, values and gradients away from the test grid's nodes.  The
+    # liquid / vapour density ratio of the oracle's solution is stored beside the mask: converged-or-failed is
+    # implementation-defined next to a critical point, the tests exempt ratio < 1.5.
+    g = torch.Generator().manual_seed(5)
+    m = 10 * n if subset is None else 0
+    cat = torch.arange(m) % n
+    Tr = 150.0 + 140.0 * torch.rand(m, generator=g, dtype=F64)
+    zr = 0.02 + 0.96 * torch.rand(m, generator=g, dtype=F64)
+    p0 = torch.full_like(Tr, 1e5)
+    Pr, Kr = P[cat], K[cat]
+    entry = {"params": tl(Pr), "kij": tl(Kr), "T": tl(Tr), "z": tl(zr), "p0": tl(p0), "category": tl(cat)}
+    from oracle import eos as oeos, solver as osolver
+    for bubble in (True, False) if m else ():
+        x = Pr.clone().requires_grad_(True)
+        k = Kr.clone().requires_grad_(True)
+        e = _point_entry(lambda: ref.PcSaftMix(x, k), {"params": x, "kij": k}, Tr, zr, p0, bubble)
+        rho, failed = osolver.binary_bubble_dew(lambda T_, r_: oeos.mix_helmholtz(Pr, Kr, T_, r_), osolver.mix_max_density(Pr),
+                                                Tr, zr, p0, bubble)
+        assert failed.tolist() == e["failed"]
+        e["rho_ratio"] = tl(rho[:, 2:4].sum(dim=1) / rho[:, 0:2].sum(dim=1))
+        entry["bubble" if bubble else "dew"] = e
+    if m:
+        out["random_grid"] = entry
 
     # the reference's own bubble / dew test configurations (tests/test_pcsaft_mix.py:127-251)
     for name, cfg, bubble in (("test_bubble_point", cases.MIX_BUBBLE, True), ("test_dew_point", cases.MIX_DEW, False)):
@@ -190,7 +218,7 @@ def mix_golden(ref):
     return out
 
 
-def gc_golden(ref, table):
+def gc_golden(ref, table, subset=None):
     out = {"segments": table}
     n = len(cases.GC_SEGMENTS)
     T = torch.full((n,), 300.0, dtype=F64)
@@ -211,6 +239,8 @@ def gc_golden(ref, table):
                 rows.append(i)
                 temps.append(t)
                 zs.append(z)
+    if subset is not None:
+        rows, temps, zs = ([v[i] for i in subset] for v in (rows, temps, zs))
     segs = [cases.GC_SEGMENTS[i] for i in rows]
     bonds = [cases.GC_BONDS[i] for i in rows]
     Tt = torch.tensor(temps, dtype=F64)

@@ -13,8 +13,18 @@ from . import eos, solver
 
 
 class PcSaftPure:
-    def __init__(self, parameters):
+    """``compiled=True``: the solve stage runs in the compiled per-state solver (oracle/cpu_solver.cpp, OpenMP over
+    states like the reference's rayon map, src/pcsaft.rs:86-92) instead of the batch-vectorised torch one; the two are
+    the same algorithm and are checked against each other in tests/test_oracle.py."""
+
+    def __init__(self, parameters, compiled=False):
         self.parameters = parameters
+        if compiled:
+            from . import cpu_solver
+
+            self._solver = cpu_solver
+        else:
+            self._solver = solver
 
     def helmholtz_energy(self, temperature, density):
         return eos.pure_helmholtz(self.parameters, temperature, density)
@@ -23,17 +33,17 @@ class PcSaftPure:
         return eos.pure_derivatives(self.parameters, temperature, density)
 
     def vapor_pressure(self, temperature):
-        rv, rl, nans = solver.pure_vle(self.parameters, temperature)
+        rv, rl, nans = self._solver.pure_vle(self.parameters, temperature)
         ok = ~nans
         return nans, eos.pure_vapor_pressure_from_densities(self.parameters[ok], temperature[ok], rv[ok], rl[ok])
 
     def liquid_density(self, temperature, pressure):
-        rho, nans = solver.pure_liquid_density(self.parameters, temperature, pressure)
+        rho, nans = self._solver.pure_liquid_density(self.parameters, temperature, pressure)
         ok = ~nans
         return nans, eos.pure_liquid_density_from_density(self.parameters[ok], temperature[ok], pressure[ok], rho[ok])
 
     def equilibrium_liquid_density(self, temperature):
-        rv, rl, nans = solver.pure_vle(self.parameters, temperature)
+        rv, rl, nans = self._solver.pure_vle(self.parameters, temperature)
         ok = ~nans
         return nans, eos.pure_equilibrium_liquid_density_from_densities(self.parameters[ok], temperature[ok], rv[ok], rl[ok])
 

@@ -253,7 +253,11 @@ def _density_at_p(helm, T, x, p_t, rho0, rho_max, liquid, n_iter=40):
             new = torch.where(dp > 0, rho + step, torch.minimum(1.1 * rho, 1.2 * rho_max))
         else:
             new = torch.where(dp > 0, (rho + step).clamp(min=0.2 * rho), 0.5 * rho)
-        rho = torch.where(torch.isfinite(new), new, rho)
+        new = torch.where(torch.isfinite(new), new, rho)
+        done = bool(((new - rho).abs() <= 1e-14 * rho).all())
+        rho = new
+        if done:
+            break
     return rho
 
 
@@ -286,18 +290,41 @@ def binary_bubble_dew(helm, max_density_fn, temperature, molefrac1, pressure_pa,
         w = part / part.sum(dim=1, keepdim=True)
     else:
         # find x with y(x) = y for an ideal vapour over a liquid near zero pressure
+        # i.e. the root in s = ln(x_1 / x_2) of  f(s) = s + mu_1(x) - mu_2(x) - ln(y_1 / y_2).  The fixed-point
+        # form s <- s_t - (mu_1 - mu_2), even damped, oscillates without end for strongly associating pairs
+        # (four-site components), so the root is bracketed and bisected (f grows with s for a stable liquid).
         s_t = torch.log(z[:, 0] / z[:, 1])
-        s = s_t.clone()
-        for _ in range(40):
+
+        def f_of(s):
             x1 = torch.sigmoid(s)
             x = torch.stack([x1, 1.0 - x1], dim=1)
             rl = _density_at_p(helm, T, x, torch.zeros_like(p), rmax(x), rmax(x), True, n_iter=12)
             _, g, _, _, _ = _mix_props(helm, T, rl[:, None] * x)
-            s_new = 0.5 * s + 0.5 * (s_t - (g[:, 0] - g[:, 1]))  # damped: strongly non-ideal pairs oscillate otherwise
-            done = bool(((s_new - s).abs() < 1e-9).all())
-            s = s_new
-            if done:
+            return s + (g[:, 0] - g[:, 1]) - s_t
+
+        lo = torch.full_like(s_t, -30.0)
+        hi = torch.full_like(s_t, 30.0)
+        f_lo = torch.full_like(s_t, float("nan"))  # residuals at the bracket ends, once an iterate has landed there
+        f_hi = torch.full_like(s_t, float("nan"))
+        side = torch.zeros_like(s_t)  # Illinois: which end was replaced last
+        for it in range(60):
+            mid = 0.5 * (lo + hi)
+            if it >= 8:
+                # regula falsi (Illinois variant) where both end residuals are known; bisection otherwise
+                sec = (lo * f_hi - hi * f_lo) / (f_hi - f_lo)
+                use = torch.isfinite(sec) & (sec > lo) & (sec < hi)
+                mid = torch.where(use, sec, mid)
+            f = f_of(mid)
+            neg = f < 0
+            # the retained end's residual is halved when the same end is replaced twice in a row
+            f_hi = torch.where(neg & (side < 0), 0.5 * f_hi, f_hi)
+            f_lo = torch.where(~neg & (side > 0), 0.5 * f_lo, f_lo)
+            lo, f_lo = torch.where(neg, mid, lo), torch.where(neg, f, f_lo)
+            hi, f_hi = torch.where(neg, hi, mid), torch.where(neg, f_hi, f)
+            side = torch.where(neg, -torch.ones_like(side), torch.ones_like(side))
+            if bool((((hi - lo) < 1e-9) | (f.abs() < 1e-11)).all()):
                 break
+        s = torch.where(f.abs() < 1e-11, mid, 0.5 * (lo + hi))
         x1 = torch.sigmoid(s)
         w = torch.stack([x1, 1.0 - x1], dim=1)
         rl = _density_at_p(helm, T, w, torch.zeros_like(p), rmax(w), rmax(w), True, n_iter=12)
@@ -310,86 +337,99 @@ def binary_bubble_dew(helm, max_density_fn, temperature, molefrac1, pressure_pa,
     rho_l = _density_at_p(helm, T, x_l, p, rmax(x_l), rmax(x_l), True)
     rho_v = p.clone()
 
-    # successive substitution sweeps (moderate count; Newton polish follows)
-    for _ in range(40):
-        rho_l = _density_at_p(helm, T, x_l, p, rho_l, rmax(x_l), True, n_iter=6)
-        rho_v = _density_at_p(helm, T, y_v, p, rho_v, rmax(y_v), False, n_iter=6)
-        _, g_l, _, _, _ = _mix_props(helm, T, rho_l[:, None] * x_l)
-        _, g_v, _, _, _ = _mix_props(helm, T, rho_v[:, None] * y_v)
-        lnk = (g_l - torch.log(p / rho_l)[:, None]) - (g_v - torch.log(p / rho_v)[:, None])  # ln phi_L - ln phi_V
-        # damped successive substitution (geometric mean of old and new): plain substitution oscillates
-        # with growing amplitude for strongly non-ideal (cross-associating) pairs
+    def pack(rho_l, rho_v, x_l, y_v):
         if bubble:
-            new = x_l * torch.exp(lnk)
-            s = new.sum(dim=1)
-            upd = torch.sqrt(y_v * new / s[:, None])
-            upd = upd / upd.sum(dim=1, keepdim=True)
-            change = (upd - y_v).abs().max()
-            y_v = upd
-            p = p * torch.sqrt(s.clamp(0.5, 2.0))
-        else:
-            new = y_v * torch.exp(-lnk)
-            s = new.sum(dim=1)
-            upd = torch.sqrt(x_l * new / s[:, None])
-            upd = upd / upd.sum(dim=1, keepdim=True)
-            change = (upd - x_l).abs().max()
-            x_l = upd
-            p = p / torch.sqrt(s.clamp(0.5, 2.0))
-        if bool(change < 1e-7) and bool(((s - 1.0).abs() < 1e-7).all()):
-            break  # the Newton polish below takes it from here
+            return torch.stack([torch.log(rho_l), torch.log(rho_v * y_v[:, 0]), torch.log(rho_v * y_v[:, 1])], dim=1)
+        return torch.stack([torch.log(rho_v), torch.log(rho_l * x_l[:, 0]), torch.log(rho_l * x_l[:, 1])], dim=1)
 
-    # Newton polish on (mu_1, mu_2, p) equalities
-    if bubble:
-        u = torch.stack([torch.log(rho_l), torch.log(rho_v * y_v[:, 0]), torch.log(rho_v * y_v[:, 1])], dim=1)
-    else:
-        u = torch.stack([torch.log(rho_v), torch.log(rho_l * x_l[:, 0]), torch.log(rho_l * x_l[:, 1])], dim=1)
-    conv = torch.zeros(N, dtype=torch.bool)
-    for _ in range(60):
-        spec_rho = torch.exp(u[:, 0])[:, None] * z  # specified phase
+    def sweeps(p, rho_l, rho_v, x_l, y_v):
+        # successive substitution sweeps (moderate count; Newton polish follows)
+        for _ in range(40):
+            rho_l = _density_at_p(helm, T, x_l, p, rho_l, rmax(x_l), True, n_iter=6)
+            rho_v = _density_at_p(helm, T, y_v, p, rho_v, rmax(y_v), False, n_iter=6)
+            _, g_l, _, _, _ = _mix_props(helm, T, rho_l[:, None] * x_l)
+            _, g_v, _, _, _ = _mix_props(helm, T, rho_v[:, None] * y_v)
+            lnk = (g_l - torch.log(p / rho_l)[:, None]) - (g_v - torch.log(p / rho_v)[:, None])  # ln phi_L - ln phi_V
+            # damped successive substitution (geometric mean of old and new): plain substitution oscillates
+            # with growing amplitude for strongly non-ideal (cross-associating) pairs
+            if bubble:
+                new = x_l * torch.exp(lnk)
+                s = new.sum(dim=1)
+                upd = torch.sqrt(y_v * new / s[:, None])
+                upd = upd / upd.sum(dim=1, keepdim=True)
+                change = (upd - y_v).abs().max()
+                y_v = upd
+                p = p * torch.sqrt(s.clamp(0.5, 2.0))
+            else:
+                new = y_v * torch.exp(-lnk)
+                s = new.sum(dim=1)
+                upd = torch.sqrt(x_l * new / s[:, None])
+                upd = upd / upd.sum(dim=1, keepdim=True)
+                change = (upd - x_l).abs().max()
+                x_l = upd
+                p = p / torch.sqrt(s.clamp(0.5, 2.0))
+            if bool(change < 1e-7) and bool(((s - 1.0).abs() < 1e-7).all()):
+                break  # the Newton polish below takes it from here
+        return pack(rho_l, rho_v, x_l, y_v)
+
+    def newton(u):
+        conv = torch.zeros(N, dtype=torch.bool)
+        for _ in range(60):
+            spec_rho = torch.exp(u[:, 0])[:, None] * z  # specified phase
+            inc_rho = torch.exp(u[:, 1:3])
+            a_s, g_s, h_s, p_s, dp_s = _mix_props(helm, T, spec_rho)
+            a_i, g_i, h_i, p_i, dp_i = _mix_props(helm, T, inc_rho)
+            F = torch.stack(
+                [
+                    g_s[:, 0] + torch.log(spec_rho[:, 0]) - g_i[:, 0] - torch.log(inc_rho[:, 0]),
+                    g_s[:, 1] + torch.log(spec_rho[:, 1]) - g_i[:, 1] - torch.log(inc_rho[:, 1]),
+                    p_s - p_i,
+                ],
+                dim=1,
+            )
+            J = torch.zeros((N, 3, 3), dtype=torch.float64)
+            # d/d ln(rho_spec): rho_spec_j d/drho_j
+            J[:, 0, 0] = (h_s[:, 0, :] * spec_rho).sum(dim=1) + 1.0
+            J[:, 1, 0] = (h_s[:, 1, :] * spec_rho).sum(dim=1) + 1.0
+            J[:, 2, 0] = (dp_s * spec_rho).sum(dim=1)
+            for k in range(2):
+                J[:, 0, 1 + k] = -(h_i[:, 0, k] * inc_rho[:, k]) - (1.0 if k == 0 else 0.0)
+                J[:, 1, 1 + k] = -(h_i[:, 1, k] * inc_rho[:, k]) - (1.0 if k == 1 else 0.0)
+                J[:, 2, 1 + k] = -dp_i[:, k] * inc_rho[:, k]
+            good = torch.isfinite(J).all(dim=(1, 2)) & torch.isfinite(F).all(dim=1)
+            Jg = torch.where(good[:, None, None], J, torch.eye(3, dtype=torch.float64).expand(N, 3, 3))
+            Fg = torch.where(good[:, None], F, torch.zeros_like(F))
+            try:
+                du = torch.linalg.solve(Jg, -Fg[:, :, None])[:, :, 0]
+            except RuntimeError:
+                du = -torch.linalg.pinv(Jg) @ Fg[:, :, None]
+                du = du[:, :, 0]
+            scale = (1.0 / du.abs().max(dim=1).values.clamp(min=1e-300)).clamp(max=1.0)  # |du| <= 1
+            du = du * scale[:, None]
+            conv = good & (du.abs().max(dim=1).values < 1e-11)  # the accepted step squares this
+            u = torch.where(conv[:, None] | ~good[:, None], u, u + du)
+            if bool((conv | ~good).all()):
+                break
+        spec_rho = torch.exp(u[:, 0])[:, None] * z
         inc_rho = torch.exp(u[:, 1:3])
-        a_s, g_s, h_s, p_s, dp_s = _mix_props(helm, T, spec_rho)
-        a_i, g_i, h_i, p_i, dp_i = _mix_props(helm, T, inc_rho)
-        F = torch.stack(
-            [
-                g_s[:, 0] + torch.log(spec_rho[:, 0]) - g_i[:, 0] - torch.log(inc_rho[:, 0]),
-                g_s[:, 1] + torch.log(spec_rho[:, 1]) - g_i[:, 1] - torch.log(inc_rho[:, 1]),
-                p_s - p_i,
-            ],
-            dim=1,
-        )
-        J = torch.zeros((N, 3, 3), dtype=torch.float64)
-        # d/d ln(rho_spec): rho_spec_j d/drho_j
-        J[:, 0, 0] = (h_s[:, 0, :] * spec_rho).sum(dim=1) + 1.0
-        J[:, 1, 0] = (h_s[:, 1, :] * spec_rho).sum(dim=1) + 1.0
-        J[:, 2, 0] = (dp_s * spec_rho).sum(dim=1)
-        for k in range(2):
-            J[:, 0, 1 + k] = -(h_i[:, 0, k] * inc_rho[:, k]) - (1.0 if k == 0 else 0.0)
-            J[:, 1, 1 + k] = -(h_i[:, 1, k] * inc_rho[:, k]) - (1.0 if k == 1 else 0.0)
-            J[:, 2, 1 + k] = -dp_i[:, k] * inc_rho[:, k]
-        good = torch.isfinite(J).all(dim=(1, 2)) & torch.isfinite(F).all(dim=1)
-        Jg = torch.where(good[:, None, None], J, torch.eye(3, dtype=torch.float64).expand(N, 3, 3))
-        Fg = torch.where(good[:, None], F, torch.zeros_like(F))
-        try:
-            du = torch.linalg.solve(Jg, -Fg[:, :, None])[:, :, 0]
-        except RuntimeError:
-            du = -torch.linalg.pinv(Jg) @ Fg[:, :, None]
-            du = du[:, :, 0]
-        scale = (1.0 / du.abs().max(dim=1).values.clamp(min=1e-300)).clamp(max=1.0)  # |du| <= 1
-        du = du * scale[:, None]
-        conv = good & (du.abs().max(dim=1).values < 1e-11)  # the accepted step squares this
-        u = torch.where(conv[:, None] | ~good[:, None], u, u + du)
-        if bool((conv | ~good).all()):
-            break
-    spec_rho = torch.exp(u[:, 0])[:, None] * z
-    inc_rho = torch.exp(u[:, 1:3])
-    if bubble:
-        rho = torch.cat([inc_rho, spec_rho], dim=1)
-    else:
-        rho = torch.cat([spec_rho, inc_rho], dim=1)
-    tot_v = rho[:, 0:2].sum(dim=1)
-    tot_l = rho[:, 2:4].sum(dim=1)
-    trivial = ((tot_l / tot_v - 1.0).abs() < 1e-5) & ((rho[:, 0] / tot_v - rho[:, 2] / tot_l).abs() < 1e-5)
-    failed = ~conv | trivial | ~(tot_l > tot_v) | ~torch.isfinite(rho).all(dim=1)
+        if bubble:
+            rho = torch.cat([inc_rho, spec_rho], dim=1)
+        else:
+            rho = torch.cat([spec_rho, inc_rho], dim=1)
+        tot_v = rho[:, 0:2].sum(dim=1)
+        tot_l = rho[:, 2:4].sum(dim=1)
+        trivial = ((tot_l / tot_v - 1.0).abs() < 1e-5) & ((rho[:, 0] / tot_v - rho[:, 2] / tot_l).abs() < 1e-5)
+        failed = ~conv | trivial | ~(tot_l > tot_v) | ~torch.isfinite(rho).all(dim=1)
+        return rho, failed
+
+    # stage 1: Newton straight from the ideal-vapour start (at low pressure it is already within the
+    # convergence radius, and successive substitution can throw strongly non-ideal pairs off);
+    # stage 2, for what stage 1 did not converge: successive substitution sweeps, then Newton
+    rho, failed = newton(pack(rho_l, rho_v, x_l, y_v))
+    if bool(failed.any()):
+        rho2, failed2 = newton(sweeps(p, rho_l, rho_v, x_l, y_v))
+        rho = torch.where(failed[:, None], rho2, rho)
+        failed = failed & failed2
     return rho, failed
 
 

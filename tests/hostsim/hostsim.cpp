@@ -210,7 +210,7 @@ void sim_mix_point(const double* params, const double* kij, const double* T, con
     int ne = 0;
     int rc = g_use_machine ? point_fast_machine(b, bubble != 0, z[i], st, es, ei, se, ne)
                            : point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
-    if (rc == kStatusRetry && use_robust) rc = point_robust(b, bubble != 0, z[i], st, es, ei, se, ne);
+    if (rc == kStatusRetry && use_robust) rc = point_robust(b, bubble != 0, z[i], kDefaultStartPressure / (T[i] * kPaPerRed), st, es, ei, se, ne);
     status[i] = (uint8_t)rc;
     evals[i] = ne;
     if (rc == kStatusOk) {
@@ -303,7 +303,7 @@ void sim_gc_point(const GcPair* pairs, const double* seg, const double* kab, con
     int ne = 0;
     int rc = g_use_machine ? point_fast_machine(b, bubble != 0, z[i], st, es, ei, se, ne)
                            : point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
-    if (rc == kStatusRetry) rc = point_robust(b, bubble != 0, z[i], st, es, ei, se, ne);
+    if (rc == kStatusRetry) rc = point_robust(b, bubble != 0, z[i], kDefaultStartPressure / (T[i] * kPaPerRed), st, es, ei, se, ne);
     status[i] = (uint8_t)rc;
     evals[i] = ne;
     if (rc == kStatusOk) {

@@ -53,10 +53,10 @@ def test_argument_errors_do_not_cross_abi(built):
         built.call("feos_dev_pure_state", None, None, None, 5, None, None, None, None)
     # the state-order entry points: empty batch = success without a launch, missing buffers / bad sizes = -1
     assert lib.feos_dev_pure_order(None, None, 0, None, None) == 0
-    assert lib.feos_dev_mix_point_order(None, None, None, 0, None, None) == 0
+    assert lib.feos_dev_mix_point_order(None, None, None, 0, 0, None, None) == 0
     assert lib.feos_dev_gc_point_order(None, 1, None, None, 0, 0, None, None) == 0
     assert lib.feos_dev_pure_order(None, None, 8, None, None) == -1
-    assert lib.feos_dev_mix_point_order(None, None, None, -3, None, None) == -1
+    assert lib.feos_dev_mix_point_order(None, None, None, -3, 0, None, None) == -1
     assert lib.feos_dev_gc_point_order(None, 0, None, None, 8, 0, None, None) == -1
     assert b"invalid argument" in lib.feos_b200_last_error()
 

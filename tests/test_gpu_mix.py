@@ -7,8 +7,7 @@ import cases
 
 pytestmark = pytest.mark.gpu
 F64 = torch.float64
-NEAR_CRITICAL = {50}      # see tests/test_hostsim_mix.py
-STRONG = (11, 12, 13)
+NEAR_CRITICAL_RATIO = 1.5  # random grid only: liquid / vapour density ratio below which the mask is implementation-defined
 
 
 @pytest.fixture(scope="module")
@@ -36,12 +35,10 @@ def test_state_functions(ft, golden_mix):
     assert ft.PcSaftMix(P, K).helmholtz_energy_density(T, rho).shape == (len(e["a"]), 1)
 
 
-@pytest.mark.parametrize("key,bubble", [("bubble", True), ("dew", False)])
-def test_category_grid(ft, golden_mix, key, bubble):
-    e = golden_mix["category_grid"]
+def _check_point_grid(ft, e, key, bubble, exempt=None):
+    """bubble / dew of one golden grid through the public API: identical mask, values 1e-10, gradients 1e-8."""
     ge = e[key]
     n = len(e["T"])
-    cat = np.array(e["category"])
     x = torch.tensor(e["params"], dtype=F64, device="cuda", requires_grad=True)
     k = torch.tensor(e["kij"], dtype=F64, device="cuda", requires_grad=True)
     t = torch.tensor(e["T"], dtype=F64, device="cuda", requires_grad=True)
@@ -51,8 +48,8 @@ def test_category_grid(ft, golden_mix, key, bubble):
     val, nans = (model.bubble_point if bubble else model.dew_point)(t, z, p0)
     failed = nans.cpu().numpy()
     gf = np.array(ge["failed"])
-    strict = np.array([i not in NEAR_CRITICAL and (bubble or cat[i] not in STRONG) for i in range(n)])
-    assert (failed == gf)[strict].all()
+    strict = np.ones(n, dtype=bool) if exempt is None else ~exempt(model, t, z, p0, failed, gf)
+    assert failed[strict].tolist() == gf[strict].tolist()
     full = np.full(n, np.nan)
     full[~failed] = val.detach().cpu().numpy()
     gv = np.full(n, np.nan)
@@ -70,6 +67,83 @@ def test_category_grid(ft, golden_mix, key, bubble):
     assert (np.abs(k.grad.cpu().numpy()[both] - gk) / (np.abs(gk).max(axis=1, keepdims=True) + 1e-300)).max() < 1e-8
     gT = np.array(ge["grad_T"])[both]
     assert (np.abs(t.grad.cpu().numpy()[both] - gT) / np.abs(gT)).max() < 1e-8
+    return int(strict.sum())
+
+
+@pytest.mark.parametrize("key,bubble", [("bubble", True), ("dew", False)])
+def test_category_grid(ft, golden_mix, key, bubble):
+    """All 14 association / dipole categories of tests/test_pcsaft_mix.py:17-36 on a 3 x 3 (T, z) grid: the
+    converged / failed mask is IDENTICAL to the reference's (oracle solver) on all 126 states, no exemptions."""
+    assert _check_point_grid(ft, golden_mix["category_grid"], key, bubble) == 126
+
+
+@pytest.mark.parametrize("key,bubble", [("bubble", True), ("dew", False)])
+def test_random_grid(ft, golden_mix, key, bubble):
+    """140 seeded random (category, T, z) states.  Identical mask wherever the solution (the oracle's, or the kernels'
+    where only they converge) has a liquid / vapour density ratio of at least 1.5; next to a critical point whether a
+    solver still separates the phases is implementation-defined."""
+    e = golden_mix["random_grid"]
+    ratio = np.array([r if r is not None else np.nan for r in e[key]["rho_ratio"]], dtype=float)
+
+    def exempt(model, t, z, p0, failed, gf):
+        from feos_torch_b200 import PcSaft
+
+        rho, st = (PcSaft.bubble_point if bubble else PcSaft.dew_point)(
+            model.parameters, model.kij_np, t.detach().cpu().numpy(), z.cpu().numpy(), p0.cpu().numpy())
+        mine = np.full(len(failed), np.nan)
+        mine[~st] = rho[:, 2:4].sum(axis=1) / rho[:, 0:2].sum(axis=1)
+        assert st.tolist() == failed.tolist()  # the native numpy API agrees with the torch API
+        near_oracle = ~gf & (ratio < NEAR_CRITICAL_RATIO)
+        near_mine = ~failed & (mine < NEAR_CRITICAL_RATIO)
+        return (failed != gf) & (near_oracle | near_mine)
+
+    assert _check_point_grid(ft, e, key, bubble, exempt) >= 130
+
+
+def test_shared_rows_match_per_state_rows(ft):
+    """`pair.expand(n, 2, 8)` / `kij.expand(n, 2)` (BASELINE config C4) are handled as ONE row: same pressures and
+    masks bit for bit as materialised per-state rows, and the gradient the backward kernel reduces over the states
+    equals the sum of the per-state gradient rows."""
+    n = 40_000
+    g = torch.Generator().manual_seed(8)
+    pa, pb = cases.MIX_BUBBLE["params"]  # cross-associating pair: dual passes; MIX_DEW: closed-form adjoints
+    for rows, kv in (([pa, pb], [-0.15, 1000.0]), (cases.MIX_DEW["params"], [-0.1, 0.0])):
+        pair = torch.tensor(rows, dtype=F64, device="cuda", requires_grad=True)
+        kij = torch.tensor(kv, dtype=F64, device="cuda", requires_grad=True)
+        T = (120.0 + 40.0 * torch.rand(n, generator=g, dtype=F64)).cuda()
+        z = (0.05 + 0.9 * torch.rand(n, generator=g, dtype=F64)).cuda()
+        p0 = torch.full((n,), 1e5, dtype=F64, device="cuda")
+        w = torch.rand(n, generator=g, dtype=F64).cuda()
+        for bubble in (True, False):
+            pair.grad = kij.grad = None
+            m = ft.PcSaftMix(pair.expand(n, 2, 8), kij.expand(n, 2))
+            assert m._flags == 3
+            p, nans = (m.bubble_point if bubble else m.dew_point)(T, z, p0)
+            (p * w[~nans]).sum().backward()
+            P2 = pair.detach().expand(n, 2, 8).contiguous().requires_grad_(True)
+            K2 = kij.detach().expand(n, 2).contiguous().requires_grad_(True)
+            m2 = ft.PcSaftMix(P2, K2)
+            assert m2._flags == 0
+            q, nans2 = (m2.bubble_point if bubble else m2.dew_point)(T, z, p0)
+            (q * w[~nans2]).sum().backward()
+            assert torch.equal(nans, nans2) and torch.equal(p, q) and (~nans).sum().item() > n // 2
+            ref_p, ref_k = P2.grad.sum(dim=0), K2.grad.sum(dim=0)
+            assert ((pair.grad - ref_p).abs() / ref_p.abs().max()).max().item() < 1e-12
+            assert ((kij.grad - ref_k).abs() / ref_k.abs().max()).max().item() < 1e-12
+
+
+def test_shape_checks(ft):
+    pa, pb = cases.MIX_DEW["params"]
+    P = torch.tensor([[pa, pb]] * 4, dtype=F64, device="cuda")
+    K = torch.zeros((4, 2), dtype=F64, device="cuda")
+    m = ft.PcSaftMix(P, K)
+    T = torch.full((3,), 150.0, dtype=F64, device="cuda")
+    with pytest.raises(ValueError, match="one row per state"):
+        m.bubble_point(T, T, T)
+    with pytest.raises(ValueError):
+        m.derivatives(torch.full((4,), 150.0, dtype=F64, device="cuda"), torch.zeros((4, 3), dtype=F64, device="cuda"))
+    with pytest.raises(ValueError):
+        ft.PcSaftMix(P, K[:3])
 
 
 def test_reference_configs(ft, golden_mix):
@@ -199,7 +273,7 @@ def test_state_order_is_a_permutation_and_changes_no_result(ft, monkeypatch):
     p0 = torch.full((n,), 1e5, dtype=F64, device="cuda")
 
     order = torch.empty(n, dtype=torch.int32, device="cuda")
-    _lib.call("feos_dev_mix_point_order", _lib.ptr(P.detach()), _lib.ptr(T), _lib.ptr(z), n, _lib.ptr(order),
+    _lib.call("feos_dev_mix_point_order", _lib.ptr(P.detach()), _lib.ptr(T), _lib.ptr(z), n, 0, _lib.ptr(order),
               torch.cuda.current_stream().cuda_stream)
     assert torch.equal(torch.sort(order.long()).values, torch.arange(n, device="cuda"))
     # grouped by code path: dipolar / associating flags are constant over long runs of the order

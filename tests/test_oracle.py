@@ -218,3 +218,51 @@ def test_gc_points_match_reference(golden_gc):
         return models.GcPcSaftMix(ident, par, [segs[i] for i in sel], [bonds[i] for i in sel], recs, lv["phi"])
 
     _check_points(model, e, leaves, per_state=("phi",))
+
+
+# ---- the compiled per-state CPU solver (oracle/cpu_solver.cpp): bench.py's CPU baseline ---------------------
+def test_compiled_solver_helmholtz_matches_reference(golden_pure):
+    """Its Helmholtz energy (second-order duals in rho) against the reference Python's a, p, dp/drho."""
+    from oracle import cpu_solver
+
+    for key in ("test_grid", "readme"):
+        e = golden_pure[key]
+        rho = np.asarray(e["rho"])
+        a, a1, a2 = cpu_solver.pure_helmholtz(np.asarray(e["params"]), np.asarray(e["T"]), rho)
+        close(a, e["a"], 1e-13, 1e-16)
+        close(rho - a + rho * a1, e["p_red"], 1e-13, 1e-16)
+        close(1.0 + rho * a2, e["dp_red"], 1e-12, 1e-15)
+
+
+def test_compiled_solver_matches_torch_solver(golden_pure):
+    """Same algorithm as oracle/solver.py, one state at a time: identical masks, densities to 1e-12 -- on the golden
+    grids (associating, dipolar and super-critical rows) and on a seeded C2-shaped grid."""
+    from oracle import cpu_solver, solver
+
+    sets = [(torch.tensor(golden_pure[k]["params"], dtype=F64), torch.tensor(golden_pure[k]["T"], dtype=F64))
+            for k in ("test_grid", "readme", "seeded_grid")]
+    g = torch.Generator().manual_seed(77)
+    n = 400
+    P = torch.zeros((n, 8), dtype=F64)
+    P[:, 0] = 1.0 + 3.0 * torch.rand(n, generator=g, dtype=F64)
+    P[:, 1] = 3.0 + torch.rand(n, generator=g, dtype=F64)
+    P[:, 2] = 150.0 + 200.0 * torch.rand(n, generator=g, dtype=F64)
+    tc = P[:, 2] * (0.6380 + 0.7070 * P[:, 0] - 0.06418 * P[:, 0] ** 2)
+    sets.append((P, (0.5 + 0.7 * torch.rand(n, generator=g, dtype=F64)) * tc))  # tau up to 1.2: failed states too
+    for P, T in sets:
+        rv, rl, failed = cpu_solver.pure_vle(P, T)
+        rv2, rl2, failed2 = solver.pure_vle(P, T)
+        assert failed.tolist() == failed2.tolist()
+        ok = ~failed
+        close(rv[ok], rv2[ok], 1e-12)
+        close(rl[ok], rl2[ok], 1e-12)
+        pr = torch.full_like(T, 2e6)
+        r, f = cpu_solver.pure_liquid_density(P, T, pr)
+        r2, f2 = solver.pure_liquid_density(P, T, pr)
+        assert f.tolist() == f2.tolist()
+        close(r[~f], r2[~f], 1e-12)
+    # README known answer through the compiled solver
+    params = torch.tensor(cases.README_PARAMS, dtype=F64, requires_grad=True)
+    nans, vp = models.PcSaftPure(params.repeat(5, 1), compiled=True).vapor_pressure(torch.tensor(cases.README_T, dtype=F64))
+    for got, want in zip(vp.tolist(), cases.README_VP):
+        assert f"{got:.4f}" == f"{want:.4f}"
