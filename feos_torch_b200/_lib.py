@@ -22,9 +22,9 @@ SIGNATURES = {
     "feos_dev_compact": ([_vp, _i64, _vp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp], ctypes.c_int),
     "feos_dev_pure_order": ([_vp, _vp, _i64, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_vle_fwd": ([_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_pure_vle_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_vle_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _i64, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_rho_tp_fwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_pure_rho_tp_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_pure_rho_tp_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_state": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_pure_state_bwd": ([_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_state_bwd": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
@@ -33,12 +33,12 @@ SIGNATURES = {
     "feos_dev_mix_point_order": ([_vp, _vp, _vp, _i64, ctypes.c_int, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_order": ([_vp, ctypes.c_int32, _vp, _vp, _i64, ctypes.c_int, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_point_fwd": ([_vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
-    "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+    "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_state": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_fwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _i64,
                                ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_bwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp,
-                               _vp, _vp, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+                               _vp, _vp, ctypes.c_int, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_state": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _i64,
                            _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_host_gc_point": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp,

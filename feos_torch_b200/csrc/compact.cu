@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(int32_t* __restrict_
     if (threadIdx.x == 1023) carry_s = carry + incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *n_ok = carry_s;
+  if (threadIdx.x == 0) {
+    *n_ok = carry_s;  // may live in mapped pinned host memory: the host polls it
+    __threadfence_system();
+  }
 }
 
 __global__ void __launch_bounds__(256)

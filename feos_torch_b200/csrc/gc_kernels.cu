@@ -164,7 +164,8 @@ gc_point_retry_kernel(GcArgs g, const double* __restrict__ molefrac, const doubl
 #endif
 __global__ void __launch_bounds__(kGcBlock, FEOS_GC_BWD_MINB)
 gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ rho, const uint8_t* __restrict__ failed,
-                    const int32_t* __restrict__ pos, const double* __restrict__ gout, int64_t n, int bubble,
+                    const int32_t* __restrict__ pos, const double* __restrict__ gout, int g_broadcast, int64_t n,
+                    int bubble,
                     double* __restrict__ grad_seg, double* __restrict__ grad_kab, double* __restrict__ grad_phi,
                     double* __restrict__ grad_t, const int32_t* __restrict__ order) {
   extern __shared__ double acc[];  // [8 n_seg + n_rec] block-level sums of the shared-parameter gradients
@@ -212,7 +213,7 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
       // the model only) for pairs that have those terms
       gc_coef_adjoints(b.c, spec, inc, q, w.cd, w.seed, cbar);
       // B. inputs of the coefficient stage
-      double gi = gout[pos ? (int64_t)pos[i] : i];
+      double gi = gout[g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i)];
       double scale = gi * src.T_ * kPaPerRed;
       // base group (z, m, cd, q1, q2): one reverse-mode sweep; gradients in units of p_red
       for (int k = 0; k < 8 * pr.nseg; ++k) gseg[k] = 0.0;
@@ -306,6 +307,78 @@ gc_point_bwd_kernel(GcArgs g, int n_seg, int n_rec, const double* __restrict__ r
   }
 }
 
+// Gradient with respect to the k_ab of the binary segment records ONLY (a k_ab fit: segment parameters, phi and T
+// carry no gradient).  k_ab enters through the cross dispersion coefficients q1[01], q2[01] alone
+// (gc_pcsaft.py:177-194), so their two closed-form adjoints and one pass over the (a, b) segment pairs that have
+// a record replace the reverse sweep through the whole coefficient stage -- and the per-thread scratch of the
+// general kernel (dense segment / k_ab gradient arrays, dual coefficient copy) is not needed at all.
+__global__ void __launch_bounds__(kGcBlock, 3)
+gc_point_bwd_kab_kernel(GcArgs g, int n_rec, const double* __restrict__ rho, const uint8_t* __restrict__ failed,
+                        const int32_t* __restrict__ pos, const double* __restrict__ gout, int g_broadcast, int64_t n,
+                        int bubble, double* __restrict__ grad_kab, const int32_t* __restrict__ order) {
+  extern __shared__ double acc[];  // [n_rec]
+  for (int k = threadIdx.x; k < n_rec; k += blockDim.x) acc[k] = 0.0;
+  __syncthreads();
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t i = t < n ? (order ? (int64_t)order[t] : t) : -1;
+  const bool valid = i >= 0 && !failed[i];
+  const GcPair* my_pair = nullptr;
+  GcSource src;
+  double cb1 = 0.0, cb2 = 0.0, scale = 0.0;  // adjoints of q1[01], q2[01]; g * T * kB / A^3
+  if (valid) {
+    src = make_source(g, i);
+    my_pair = src.pair;
+    struct {
+      GcBinary b;
+      double cbar[kGcMaxCoef];
+    } w;  // one stack object: see the compiler note in gc_pcsaft.cuh
+    gc_binary_init(w.b, src);
+    const double2* rp = reinterpret_cast<const double2*>(rho + 4 * i);
+    double2 rv = rp[0], rl = rp[1];
+    double spec[2], inc[2];
+    if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
+    else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
+    MixEval es = w.b.eval(spec[0], spec[1]);
+    PointWeights q = point_weights(es, spec, inc);
+    mix_base_coef_adjoint<kGcMaxBond, true>(w.b.c, spec, inc, q, w.cbar);
+    cb1 = w.cbar[11];
+    cb2 = w.cbar[14];
+    scale = gout[g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i)] * src.T_ * kPaPerRed;
+  }
+  const unsigned vm = __ballot_sync(full, valid);
+  if (vm) {
+    const unsigned long long mine = (unsigned long long)my_pair;
+    const unsigned long long lead = __shfl_sync(full, mine, __ffs(vm) - 1);
+    if (__all_sync(full, !valid || mine == lead)) {
+      // one molecule pair per warp (state order): sum over the lanes with shuffles, one shared atomic per record
+      const GcPair& pr = *reinterpret_cast<const GcPair*>(lead);
+      for (int a = 0; a < pr.nseg; ++a)
+        for (int b = 0; b < pr.nseg; ++b) {
+          const int r = pr.krec[a][b];
+          if (r < 0 || pr.cnt[0][a] * pr.cnt[1][b] == 0.0) continue;  // uniform over the warp
+          double v = valid ? gc_kab_term(src, pr, a, b, cb1, cb2) * scale : 0.0;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(full, v, o);
+          if (lane == 0 && v != 0.0) atomicAdd(&acc[r], v);
+        }
+    } else if (valid) {
+      const GcPair& pr = *my_pair;
+      for (int a = 0; a < pr.nseg; ++a)
+        for (int b = 0; b < pr.nseg; ++b) {
+          const int r = pr.krec[a][b];
+          if (r < 0 || pr.cnt[0][a] * pr.cnt[1][b] == 0.0) continue;
+          double v = gc_kab_term(src, pr, a, b, cb1, cb2) * scale;
+          if (v != 0.0) atomicAdd(&acc[r], v);
+        }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < n_rec; k += blockDim.x)
+    if (acc[k] != 0.0) atomicAdd(grad_kab + k, acc[k]);
+}
+
 __global__ void __launch_bounds__(kGcBlock)
 gc_state_kernel(GcArgs g, const double* __restrict__ density, int64_t n, double* __restrict__ a, double* __restrict__ p,
                 double* __restrict__ mu, double* __restrict__ v) {
@@ -396,7 +469,8 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
 int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* rho, const uint8_t* failed, const int32_t* pos,
-                          const double* g, int64_t n, int bubble, double* grad_seg_params, double* grad_kab,
+                          const double* g, int g_broadcast, int64_t n, int bubble, double* grad_seg_params,
+                          double* grad_kab,
                           double* grad_phi, double* grad_temperature, const int32_t* order, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
@@ -415,8 +489,16 @@ int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
     return v;
   }();
   shmem += (size_t)pad;
+  if (!grad_seg_params && !grad_phi && !grad_temperature) {
+    if (!grad_kab || n_rec == 0) return 0;
+    gc_point_bwd_kab_kernel<<<grid_for(n, kGcBlock), kGcBlock, sizeof(double) * (size_t)n_rec, (cudaStream_t)stream>>>(
+        a, n_rec, rho, failed, pos, g, g_broadcast, n, bubble, grad_kab, order);
+    FEOS_LAUNCH_OK();
+    return 0;
+  }
   gc_point_bwd_kernel<<<grid_for(n, kGcBlock), kGcBlock, shmem, (cudaStream_t)stream>>>(
-      a, n_seg, n_rec, rho, failed, pos, g, n, bubble, grad_seg_params, grad_kab, grad_phi, grad_temperature, order);
+      a, n_seg, n_rec, rho, failed, pos, g, g_broadcast, n, bubble, grad_seg_params, grad_kab, grad_phi, grad_temperature,
+      order);
   FEOS_LAUNCH_OK();
   return 0;
 }

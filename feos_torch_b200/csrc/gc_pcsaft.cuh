@@ -564,6 +564,18 @@ FD_NOINLINE void gc_base_adjoint(const GcSource& src, const GcCoef& c, const dou
   (void)c;
 }
 
+// d p_red / d k_ab of the record of the segment pair (a in molecule 0, b in molecule 1) from the adjoints cb1, cb2 of
+// the cross dispersion coefficients q1[01], q2[01] -- the k == 1 branch of gc_base_adjoint on its own, for the
+// k_ab-only backward kernel:  t = n_0a n_1b m_a m_b sigma_ab^3 e_ab,  e_ab = sqrt(eps_a eps_b phi_0 phi_1) / T (1 - k_ab)
+FD double gc_kab_term(const GcSource& src, const GcPair& pr, int a, int b, double cb1, double cb2) {
+  double nn = pr.cnt[0][a] * pr.cnt[1][b];
+  double sab = 0.5 * (src.seg(a, 1) + src.seg(b, 1));
+  double kab = src.kab_of(a, b);
+  double eab = sqrt(src.seg(a, 2)) * sqrt(src.seg(b, 2)) * (sqrt(src.phi(0) * src.phi(1)) / src.T()) * (1.0 - kab);
+  double t = nn * (src.seg(a, 0) * src.seg(b, 0) * (sab * sab * sab)) * eab;
+  return -((cb1 + 2.0 * cb2 * eab) * t) / (1.0 - kab);
+}
+
 // Step B, dipole group: reverse-mode sweep through the molecule-level dipole parameters (gc_coef, :146-168)
 // and dipole_coef (pcsaft_mix.cuh).  cb = adjoints of the 26 dipole coefficients in the flat order
 // (mu2t[2]; pw1, pw2, pe, ps per pair; tw1, tw2, ts per triplet); ADDS to gseg (m, sigma, eps, mu) and gT.

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kMixBlock, FEOS_MIX_BWD_MINB)
 mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
                      const double* __restrict__ temperature, const double* __restrict__ rho,
                      const uint8_t* __restrict__ failed, const int32_t* __restrict__ pos, const double* __restrict__ g,
-                     int64_t n, int bubble, int flags, double* __restrict__ grad_params, double* __restrict__ grad_kij,
+                     int g_broadcast, int64_t n, int bubble, int flags, double* __restrict__ grad_params, double* __restrict__ grad_kij,
                      double* __restrict__ grad_t, const int32_t* __restrict__ order) {
   __shared__ double acc[18];
   const bool sh_p = (flags & kSharedParams) && grad_params, sh_k = (flags & kSharedKij) && grad_kij;
@@ -227,7 +227,7 @@ mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict
     if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
     else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
     PointWeights q;
-    double gi = g[pos ? (int64_t)pos[i] : i];
+    double gi = g[g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i)];
     bool closed;
     {
       PcSaftBinary b;
@@ -419,15 +419,16 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
 }
 
 int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
-                           const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble, int flags,
-                           double* grad_params, double* grad_kij, double* grad_temperature, const int32_t* order,
+                           const uint8_t* failed, const int32_t* pos, const double* g, int g_broadcast, int64_t n,
+                           int bubble, int flags, double* grad_params, double* grad_kij, double* grad_temperature, const int32_t* order,
                            void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && rho && failed && g);
   mix_point_bwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, (cudaStream_t)stream>>>(
-      params, kij, temperature, rho, failed, pos, g, n, bubble, flags, grad_params, grad_kij, grad_temperature, order);
+      params, kij, temperature, rho, failed, pos, g, g_broadcast, n, bubble, flags, grad_params, grad_kij, grad_temperature,
+      order);
   FEOS_LAUNCH_OK();
   return 0;
 }

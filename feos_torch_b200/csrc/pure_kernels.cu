@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kBlock, FEOS_PURE_BWD_MINB)
 pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                     const double* __restrict__ rho, const uint8_t* __restrict__ failed,
                     const int32_t* __restrict__ pos, const double* __restrict__ g_vp,
-                    const double* __restrict__ g_rho, int64_t n, double* __restrict__ grad_params,
+                    const double* __restrict__ g_rho, int g_broadcast, int64_t n, double* __restrict__ grad_params,
                     double* __restrict__ grad_t) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -240,7 +240,7 @@ pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict_
   PureRow r = load_row(params, i);
   double T = temperature[i];
   double2 rr = reinterpret_cast<const double2*>(rho)[i];
-  int64_t gi_idx = pos ? (int64_t)pos[i] : i;
+  int64_t gi_idx = g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i);
   double gv = g_vp ? g_vp[gi_idx] : 0.0;
   double gr = 0.0, dpl = 1.0;
   if (NEED_RLEQ) {
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kBlock, FEOS_PURE_BWD_MINB)
 pure_rho_tp_bwd_kernel(const double* __restrict__ params, const double* __restrict__ temperature,
                        const double* __restrict__ pressure, const double* __restrict__ rho,
                        const uint8_t* __restrict__ failed, const int32_t* __restrict__ pos,
-                       const double* __restrict__ g, int64_t n, double* __restrict__ grad_params,
+                       const double* __restrict__ g, int g_broadcast, int64_t n, double* __restrict__ grad_params,
                        double* __restrict__ grad_t, double* __restrict__ grad_p) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -310,7 +310,7 @@ pure_rho_tp_bwd_kernel(const double* __restrict__ params, const double* __restri
   double x = rho[i];
   double dp = pure_eval(c, x).dp;
   double p_t = pressure[i] / (T * kPaPerRed);
-  double gi = g[pos ? (int64_t)pos[i] : i];
+  double gi = g[g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i)];
   if (grad_p) grad_p[i] = gi / dp / (T * kPaPerRed) * kKmolM3PerRed;
   if (!grad_params && !grad_t) return;
   double out[9];
@@ -413,7 +413,7 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
 
 int feos_dev_pure_vle_bwd(const double* params, const double* temperature, const double* rho,
                           const uint8_t* failed, const int32_t* pos, const double* g_vp, const double* g_rho,
-                          int64_t n, double* grad_params, double* grad_temperature, void* stream) {
+                          int g_broadcast, int64_t n, double* grad_params, double* grad_temperature, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -421,11 +421,11 @@ int feos_dev_pure_vle_bwd(const double* params, const double* temperature, const
   FEOS_ARG(g_vp || g_rho);
   cudaStream_t s = (cudaStream_t)stream;
   if (g_rho)
-    pure_vle_bwd_kernel<true><<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, rho, failed, pos, g_vp, g_rho, n,
-                                                                   grad_params, grad_temperature);
+    pure_vle_bwd_kernel<true><<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, rho, failed, pos, g_vp, g_rho,
+                                                                   g_broadcast, n, grad_params, grad_temperature);
   else
-    pure_vle_bwd_kernel<false><<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, rho, failed, pos, g_vp, g_rho, n,
-                                                                    grad_params, grad_temperature);
+    pure_vle_bwd_kernel<false><<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, rho, failed, pos, g_vp, g_rho,
+                                                                    g_broadcast, n, grad_params, grad_temperature);
   FEOS_LAUNCH_OK();
   return 0;
 }
@@ -444,15 +444,15 @@ int feos_dev_pure_rho_tp_fwd(const double* params, const double* temperature, co
 }
 
 int feos_dev_pure_rho_tp_bwd(const double* params, const double* temperature, const double* pressure,
-                             const double* rho, const uint8_t* failed, const int32_t* pos, const double* g, int64_t n,
-                             double* grad_params, double* grad_temperature, double* grad_pressure,
-                             void* stream) {
+                             const double* rho, const uint8_t* failed, const int32_t* pos, const double* g,
+                             int g_broadcast, int64_t n, double* grad_params, double* grad_temperature,
+                             double* grad_pressure, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
   FEOS_ARG(params && temperature && pressure && rho && failed && g);
   pure_rho_tp_bwd_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
-      params, temperature, pressure, rho, failed, pos, g, n, grad_params, grad_temperature, grad_pressure);
+      params, temperature, pressure, rho, failed, pos, g, g_broadcast, n, grad_params, grad_temperature, grad_pressure);
   FEOS_LAUNCH_OK();
   return 0;
 }

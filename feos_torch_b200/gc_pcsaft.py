@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .pcsaft_pure import _back, _cuda_device, _prep, _stream, compact
+from .pcsaft_pure import _back, _cuda_device, _prep, _stream, _upstream, compact
 
 MAX_SEG = 12
 MAX_BOND = 16
@@ -125,13 +125,16 @@ class _GcPoint(torch.autograd.Function):
         ctx.save_for_backward(seg_params, kab, phi, temperature, rho, failed, pos, pairs_dev, pair_index, order_bwd)
         ctx.bubble, ctx.n_pairs = int(bubble), n_pairs
         ctx.mark_non_differentiable(rho, failed)
+        ctx.set_materialize_grads(False)  # no zero-filled gradients for the mask / density outputs
         return out, failed, rho
 
     @staticmethod
     def backward(ctx, g_val, _g_failed, _g_rho):
         seg_params, kab, phi, temperature, rho, failed, pos, pairs_dev, pair_index, order = ctx.saved_tensors
         n = temperature.shape[0]
-        g = g_val.contiguous()
+        if g_val is None:  # only the mask / density outputs were used downstream
+            return (None,) * 9
+        g, bc = _upstream(g_val)
         need_seg, need_kab, need_phi, need_t = ctx.needs_input_grad[:4]
         g_seg = torch.zeros_like(seg_params) if need_seg else None
         g_kab = torch.zeros_like(kab) if need_kab and kab.shape[0] else None
@@ -141,7 +144,7 @@ class _GcPoint(torch.autograd.Function):
             _lib.timed_call(
                 "feos_dev_gc_point_bwd", _lib.ptr(pairs_dev), ctx.n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                 _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature), _lib.ptr(rho),
-                _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, ctx.bubble, _lib.ptr(g_seg), _lib.ptr(g_kab),
+                _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), bc, n, ctx.bubble, _lib.ptr(g_seg), _lib.ptr(g_kab),
                 _lib.ptr(g_phi), _lib.ptr(g_t), _lib.ptr(order), _stream(),
             )
         if need_kab and g_kab is None:
@@ -249,7 +252,7 @@ class GcPcSaftMix:
             orders = (_lib.cached_order(("gc", dev), key, lambda: compute(0), n=n),
                       _lib.cached_order(("gc-pair", dev), key, lambda: compute(1), n=n))
         val, failed, _ = _GcPoint.apply(self._seg, self._kab, self._phi, t, z, p0, bubble, tables, orders)
-        return self._back(val), self._back(failed.bool())
+        return self._back(val), self._back(failed.view(torch.bool))
 
     def bubble_point(self, temperature, liquid_molefracs, pressure):
         """(p_bubble [n_ok] in Pa, failed mask [N]) -- gc_pcsaft.py:470-490.  `pressure`: the reference's starting

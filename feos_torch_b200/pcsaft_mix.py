@@ -8,7 +8,7 @@ and ``temperature``; mole fractions and the starting pressure carry none (pcsaft
 import torch
 
 from . import _lib
-from .pcsaft_pure import _back, _check_rows, _cuda_device, _prep, _stream, compact
+from .pcsaft_pure import _back, _check_rows, _cuda_device, _prep, _stream, _upstream, compact
 
 
 SHARED_PARAMS, SHARED_KIJ = 1, 2  # include/feos_b200.h: FEOS_SHARED_PARAMS, FEOS_SHARED_KIJ
@@ -52,13 +52,16 @@ class _MixPoint(torch.autograd.Function):
         ctx.save_for_backward(params, kij, temperature, rho, failed, pos, None)
         ctx.bubble, ctx.flags = int(bubble), flags
         ctx.mark_non_differentiable(rho, failed)
+        ctx.set_materialize_grads(False)  # no zero-filled gradients for the mask / density outputs
         return out, failed, rho
 
     @staticmethod
     def backward(ctx, g_val, _g_failed, _g_rho):
         params, kij, temperature, rho, failed, pos, order = ctx.saved_tensors
         n = temperature.shape[0]
-        g = g_val.contiguous()
+        if g_val is None:  # only the mask / density outputs were used downstream
+            return (None,) * 8
+        g, bc = _upstream(g_val)
         need_p, need_k, need_t = ctx.needs_input_grad[:3]
         # shared rows: the kernel accumulates the sum over the states (zero first); per-state rows are written
         gp = (torch.zeros_like(params) if ctx.flags & SHARED_PARAMS else torch.empty_like(params)) if need_p else None
@@ -67,7 +70,7 @@ class _MixPoint(torch.autograd.Function):
         with torch.cuda.device(params.device):
             _lib.timed_call(
                 "feos_dev_mix_point_bwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(rho),
-                _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), n, ctx.bubble, ctx.flags, _lib.ptr(gp), _lib.ptr(gk),
+                _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), bc, n, ctx.bubble, ctx.flags, _lib.ptr(gp), _lib.ptr(gk),
                 _lib.ptr(gt), _lib.ptr(order), _stream(),
             )
         return gp, gk, gt, None, None, None, None, None
@@ -203,7 +206,7 @@ class PcSaftMix:
                 return o
             order = _lib.cached_order(("mix", self._dev.index), (temperature, molefracs), compute, n=n)
         val, failed, _ = _MixPoint.apply(params, kij, t, z, p0, bubble, order, self._flags)
-        return self._back(val), self._back(failed.bool())
+        return self._back(val), self._back(failed.view(torch.bool))
 
     def bubble_point(self, temperature, liquid_molefracs, pressure):
         """(p_bubble [n_ok] in Pa, failed mask [N]) -- pcsaft_mix.py:422-444.  `pressure` is the starting value the

@@ -201,20 +201,58 @@ def _check_rows(n, **tensors):
                 "pass full-length tensors, or build a new model from the surviving parameter rows.")
 
 
+# The number of converged states is the one value the host needs before a property call can return (it is the
+# length of the returned tensor).  The compaction's scan kernel writes it straight into pinned host memory and the
+# host polls that word: no device->host memcpy, no stream synchronisation, and the scatter kernel that follows runs
+# while Python is already preparing the next call.
+_COUNT_SLOTS = 64
+_count_state = {}
+
+
+def _count_slot(dev):
+    st = _count_state.get(dev.index)
+    if st is None:
+        buf = torch.empty((_COUNT_SLOTS,), dtype=torch.int64).pin_memory()
+        st = _count_state[dev.index] = [buf, buf.numpy(), 0]
+    st[2] = (st[2] + 1) % _COUNT_SLOTS
+    return st[0], st[1], st[2]
+
+
+def _wait_count(arr, k, dev):
+    for _ in range(2_000_000):  # ~0.1 s of polling, far beyond any kernel of this library
+        v = arr[k]
+        if v >= 0:
+            return int(v)
+    torch.cuda.current_stream(dev).synchronize()
+    if arr[k] < 0:
+        raise _lib.FeosB200Error("compaction count did not arrive")
+    return int(arr[k])
+
+
 def compact(failed, values, out_cols=None):
     """Rows of ``values`` [n] or [n, c] whose state converged, in input order, plus the row map
-    ``pos`` [n] (int32, -1 = failed).  One host synchronisation (the output length)."""
+    ``pos`` [n] (int32, -1 = failed).  One host wait (the output length)."""
     n = failed.shape[0]
     dev = failed.device
     in_cols = 1 if values.dim() == 1 else values.shape[1]
     out_cols = in_cols if out_cols is None else out_cols
     pos = torch.empty((n,), dtype=torch.int32, device=dev)
-    n_ok = torch.empty((1,), dtype=torch.int64, device=dev)
     out = torch.empty((n, out_cols) if values.dim() == 2 else (n,), dtype=torch.float64, device=dev)
-    _lib.call("feos_dev_compact", _lib.ptr(failed), n, _lib.ptr(pos), _lib.ptr(n_ok), _lib.ptr(values), in_cols,
+    if n == 0:
+        return out, pos
+    buf, arr, k = _count_slot(dev)
+    arr[k] = -1
+    _lib.call("feos_dev_compact", _lib.ptr(failed), n, _lib.ptr(pos), _lib.ptr_at(buf, 8 * k), _lib.ptr(values), in_cols,
               _lib.ptr(out), out_cols, _stream())
-    k = int(n_ok.item())
-    return out[:k], pos
+    return out[:_wait_count(arr, k, dev)], pos
+
+
+def _upstream(g):
+    """Upstream gradient for the backward kernels: (contiguous tensor, broadcast flag).  The gradient of
+    `values.sum()` arrives as ONE value expanded with stride 0; the kernels read it in place (g_broadcast)."""
+    if g.numel() > 1 and all(st == 0 for st in g.stride()):
+        return g.as_strided((1,), (1,), g.storage_offset()), 1
+    return g.contiguous(), 0
 
 
 def _state_order(params, temperature, key):
@@ -264,20 +302,23 @@ class _PureVle(torch.autograd.Function):
         ctx.which = which
         ctx.to_host = ch is not None  # parameters came from the host: their gradient goes back there
         ctx.mark_non_differentiable(rho, failed)
+        ctx.set_materialize_grads(False)  # no zero-filled gradients for the mask / density outputs
         return out, failed, rho
 
     @staticmethod
     def backward(ctx, g_val, _g_failed, _g_rho):
         params, temperature, rho, failed, pos = ctx.saved_tensors
         n = temperature.shape[0]
-        g = g_val.contiguous()
+        if g_val is None:  # only the mask / density outputs were used downstream
+            return (None,) * 4
+        g, bc = _upstream(g_val)
         grad_params = torch.empty_like(params)
         grad_t = torch.empty_like(temperature) if ctx.needs_input_grad[1] else None
         with torch.cuda.device(params.device):
             def launch(a, b):
                 _lib.timed_call(
                     "feos_dev_pure_vle_bwd", _off(params, a), _off(temperature, a), _off(rho, a), _off(failed, a),
-                    _off(pos, a), _lib.ptr(g) if ctx.which == 0 else None, _lib.ptr(g) if ctx.which == 1 else None, b - a,
+                    _off(pos, a), _lib.ptr(g) if ctx.which == 0 else None, _lib.ptr(g) if ctx.which == 1 else None, bc, b - a,
                     _off(grad_params, a), _off(grad_t, a), _stream(),
                 )
             if ctx.to_host and n >= 2 * _CHUNK_MIN:
@@ -312,13 +353,16 @@ class _PureRhoTp(torch.autograd.Function):
         ctx.save_for_backward(params, temperature, pressure, rho, failed, pos)
         ctx.to_host = ch is not None
         ctx.mark_non_differentiable(rho, failed)
+        ctx.set_materialize_grads(False)  # no zero-filled gradients for the mask / density outputs
         return out, failed, rho
 
     @staticmethod
     def backward(ctx, g_val, _g_failed, _g_rho):
         params, temperature, pressure, rho, failed, pos = ctx.saved_tensors
         n = temperature.shape[0]
-        g = g_val.contiguous()
+        if g_val is None:  # only the mask / density outputs were used downstream
+            return (None,) * 4
+        g, bc = _upstream(g_val)
         need_p, need_t, need_pr = ctx.needs_input_grad[:3]
         grad_params = torch.empty_like(params) if need_p else None
         grad_t = torch.empty_like(temperature) if need_t else None
@@ -327,7 +371,7 @@ class _PureRhoTp(torch.autograd.Function):
             def launch(a, b):
                 _lib.timed_call(
                     "feos_dev_pure_rho_tp_bwd", _off(params, a), _off(temperature, a), _off(pressure, a),
-                    _off(rho, a), _off(failed, a), _off(pos, a), _lib.ptr(g), b - a, _off(grad_params, a),
+                    _off(rho, a), _off(failed, a), _off(pos, a), _lib.ptr(g), bc, b - a, _off(grad_params, a),
                     _off(grad_t, a), _off(grad_pr, a), _stream(),
                 )
             if ctx.to_host and need_p and n >= 2 * _CHUNK_MIN:
@@ -424,14 +468,14 @@ class PcSaftPure:
         _check_rows(self._n, temperature=temperature)
         t = self._state(temperature)
         val, failed, _ = _PureVle.apply(self._params, t, 0, _state_order(self._params, t, (self._source, temperature)))
-        return self._back(failed.bool()), self._back(val)
+        return self._back(failed.view(torch.bool)), self._back(val)
 
     def equilibrium_liquid_density(self, temperature):
         """(failed mask [N], rho_L^sat [n_ok] in kmol/m^3) -- pcsaft_pure.py:217-233."""
         _check_rows(self._n, temperature=temperature)
         t = self._state(temperature)
         val, failed, _ = _PureVle.apply(self._params, t, 1, _state_order(self._params, t, (self._source, temperature)))
-        return self._back(failed.bool()), self._back(val)
+        return self._back(failed.view(torch.bool)), self._back(val)
 
     def liquid_density(self, temperature, pressure):
         """(failed mask [N], rho_L(T, p) [n_ok] in kmol/m^3) -- pcsaft_pure.py:184-199."""
@@ -439,7 +483,7 @@ class PcSaftPure:
         t = self._state(temperature)
         p = self._state(pressure)
         val, failed, _ = _PureRhoTp.apply(self._params, t, p, _state_order(self._params, t, (self._source, temperature)))
-        return self._back(failed.bool()), self._back(val)
+        return self._back(failed.view(torch.bool)), self._back(val)
 
     # ---- state functions at given (T, rho), differentiable ---------------
     def derivatives(self, temperature, density):

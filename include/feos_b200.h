@@ -43,7 +43,8 @@ int feos_b200_measure_fp64_peak(int iters, double* tflops);
  * :127-128 and filter_binary :216-231, and of the mask indexing at pcsaft_pure.py:192-194).
  *   failed [n]                                in
  *   pos [n]     row i -> output row, -1 if failed (may be NULL)            out
- *   n_ok        DEVICE scalar: number of converged states                 out
+ *   n_ok        number of converged states: a device scalar, or a word of pinned (mapped) host memory that
+ *               the caller polls instead of synchronising the stream                          out
  *   in [n,in_cols] -> out [n_ok,out_cols], columns >= in_cols are zero (in may be NULL) */
 int feos_dev_compact(const uint8_t* failed, int64_t n, int32_t* pos, int64_t* n_ok, const double* in,
                      int in_cols, double* out, int out_cols, void* stream);
@@ -82,11 +83,13 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
  * parameters and the temperature at the converged densities (implicit-function theorem); replaces
  * torch autograd through pcsaft_pure.py:210-215 / :226-233.  g_vp or g_rho may be NULL (= 0).
  * `pos` (from feos_dev_compact, may be NULL) maps state i to its row in the COMPACTED g arrays;
- * with pos == NULL the g arrays are full length.
+ * with pos == NULL the g arrays are full length.  g_broadcast != 0 (all *_bwd entry points): the g arrays hold ONE
+ * value that applies to every state -- the upstream gradient of `loss = values.sum()`, which torch hands over as
+ * a stride-0 expansion; reading it in place saves materialising it.
  *   grad_params [n,8], grad_temperature [n] (may be NULL)   out; rows of failed states are 0 */
 int feos_dev_pure_vle_bwd(const double* params, const double* temperature, const double* rho,
                           const uint8_t* failed, const int32_t* pos, const double* g_vp, const double* g_rho,
-                          int64_t n, double* grad_params, double* grad_temperature, void* stream);
+                          int g_broadcast, int64_t n, double* grad_params, double* grad_temperature, void* stream);
 
 /* Liquid density at (T, p).  Replaces PyPcSaft::liquid_density -> liquid_density_
  * (src/pcsaft.rs:29-41, :105-129) fused with pcsaft_pure.py:196-199.
@@ -98,9 +101,9 @@ int feos_dev_pure_rho_tp_fwd(const double* params, const double* temperature, co
 /* Gradient of sum_i g[i] * liquid_density[i] w.r.t. parameters, T and p (any output may be NULL);
  * `pos` as above. */
 int feos_dev_pure_rho_tp_bwd(const double* params, const double* temperature, const double* pressure,
-                             const double* rho, const uint8_t* failed, const int32_t* pos, const double* g, int64_t n,
-                             double* grad_params, double* grad_temperature, double* grad_pressure,
-                             void* stream);
+                             const double* rho, const uint8_t* failed, const int32_t* pos, const double* g,
+                             int g_broadcast, int64_t n, double* grad_params, double* grad_temperature,
+                             double* grad_pressure, void* stream);
 
 /* a, p/kT, d(p/kT)/drho at given (T, rho): PcSaftPure.derivatives (pcsaft_pure.py:180-182);
  * any output may be NULL. */
@@ -167,9 +170,9 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
  * over the states, ACCUMULATED into (zero first): the reduction torch would run over an expanded [n,2,8] gradient
  * is fused into the kernel (warp shuffle -> shared memory -> one atomic per slot and block). */
 int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
-                           const uint8_t* failed, const int32_t* pos, const double* g, int64_t n, int bubble, int flags,
-                           double* grad_params, double* grad_kij, double* grad_temperature, const int32_t* order,
-                           void* stream);
+                           const uint8_t* failed, const int32_t* pos, const double* g, int g_broadcast, int64_t n,
+                           int bubble, int flags, double* grad_params, double* grad_kij, double* grad_temperature,
+                           const int32_t* order, void* stream);
 
 /* a, p/kT, mu_i^res/kT [n,2], v_i [n,2] at (T, rho [n,2]): PcSaftMix.derivatives (pcsaft_mix.py:395-420). */
 int feos_dev_mix_state(const double* params, const double* kij, const double* temperature, const double* density,
@@ -232,8 +235,9 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
 int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* rho, const uint8_t* failed, const int32_t* pos,
-                          const double* g, int64_t n, int bubble, double* grad_seg_params, double* grad_kab,
-                          double* grad_phi, double* grad_temperature, const int32_t* order, void* stream);
+                          const double* g, int g_broadcast, int64_t n, int bubble, double* grad_seg_params,
+                          double* grad_kab, double* grad_phi, double* grad_temperature, const int32_t* order,
+                          void* stream);
 
 /* a, p/kT, mu_i, v_i at (T, rho [n,2]): GcPcSaftMix.derivatives (gc_pcsaft.py:443-468). */
 int feos_dev_gc_state(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,

@@ -323,6 +323,34 @@ void sim_gc_point(const GcPair* pairs, const double* seg, const double* kab, con
 }
 
 // grad_seg [n_seg,8] and grad_kab [n_rec] accumulate over states; grad_phi [n,2], grad_t [n]
+// the k_ab-only backward path (gc_point_bwd_kab_kernel)
+void sim_gc_point_bwd_kab(const GcPair* pairs, const double* seg, const double* kab, int n_rec, const int32_t* idx,
+                          const double* phi, const double* T, const double* rho, int64_t n, int bubble, const double* g,
+                          double* grad_kab) {
+  for (int64_t i = 0; i < n; ++i) {
+    GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    const GcPair& pr = *s.pair;
+    GcBinary b;
+    gc_binary_init(b, s);
+    const double* r = rho + 4 * i;
+    double spec[2], inc[2];
+    if (bubble) { spec[0] = r[2]; spec[1] = r[3]; inc[0] = r[0]; inc[1] = r[1]; }
+    else { spec[0] = r[0]; spec[1] = r[1]; inc[0] = r[2]; inc[1] = r[3]; }
+    MixEval es = b.eval(spec[0], spec[1]);
+    PointWeights q = point_weights(es, spec, inc);
+    double cbar[kGcMaxCoef];
+    mix_base_coef_adjoint<kGcMaxBond, true>(b.c, spec, inc, q, cbar);
+    double scale = g[i] * T[i] * kPaPerRed;
+    for (int a = 0; a < pr.nseg; ++a)
+      for (int c2 = 0; c2 < pr.nseg; ++c2) {
+        int rec = pr.krec[a][c2];
+        if (rec < 0 || pr.cnt[0][a] * pr.cnt[1][c2] == 0.0) continue;
+        grad_kab[rec] += gc_kab_term(s, pr, a, c2, cbar[11], cbar[14]) * scale;
+      }
+  }
+  (void)n_rec;
+}
+
 void sim_gc_point_bwd(const GcPair* pairs, const double* seg, int n_seg, const double* kab, int n_rec,
                       const int32_t* idx, const double* phi, const double* T, const double* rho, int64_t n, int bubble,
                       const double* g, double* grad_seg, double* grad_kab, double* grad_phi, double* grad_t,

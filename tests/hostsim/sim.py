@@ -152,6 +152,16 @@ def gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g, generic=False):
     return gs, gk, gp, gt
 
 
+def gc_point_bwd_kab(pairs, seg, kab, idx, phi, T, rho, bubble, g):
+    pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
+    rho, g = c64(rho), c64(g)
+    n = T.shape[0]
+    gk = np.zeros_like(kab)
+    lib().sim_gc_point_bwd_kab(_p(pairs), _p(seg), _p(kab), ctypes.c_int(kab.shape[0]), _p(idx), _p(phi), _p(T), _p(rho),
+                               ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(g), _p(gk))
+    return gk
+
+
 def pure_state_bwd(params, T, rho, ga, gp, gdp):
     params, T, rho, ga, gp, gdp = c64(params), c64(T), c64(rho), c64(ga), c64(gp), c64(gdp)
     n = T.shape[0]

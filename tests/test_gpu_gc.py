@@ -86,6 +86,41 @@ def test_category_grid(ft, golden_gc, key, bubble):
         assert abs(fd.item() - par[2].grad[j].item()) < 1e-6 * abs(fd.item())
 
 
+@pytest.mark.parametrize("key,bubble", [("bubble", True), ("dew", False)])
+def test_kab_only_gradient(ft, golden_gc, key, bubble):
+    """A k_ab fit (only the binary segment records require a gradient) takes the k_ab-only backward kernel
+    (gc_point_bwd_kab_kernel): same k_ab gradient as the reference (golden), per-state weights included."""
+    e = golden_gc["category_grid"]
+    rows = e["category"]
+    ge = e[key]
+    n = len(rows)
+    ident, par = seg_args(golden_gc)
+    kab = [torch.tensor(k[2], dtype=F64, device="cuda", requires_grad=True) for k in cases.GC_KAB]
+    recs = [(k[0], k[1], kv) for k, kv in zip(cases.GC_KAB, kab)]
+    phi = torch.tensor([cases.GC_PHI] * n, dtype=F64, device="cuda")
+    t = torch.tensor(e["T"], dtype=F64, device="cuda")
+    z = torch.tensor(e["z"], dtype=F64, device="cuda")
+    p0 = torch.tensor(e["p0"], dtype=F64, device="cuda")
+    segs, bonds = [cases.GC_SEGMENTS[i] for i in rows], [cases.GC_BONDS[i] for i in rows]
+    model = ft.GcPcSaftMix(ident, par, segs, bonds, recs, phi)
+    val, nans = (model.bubble_point if bubble else model.dew_point)(t, z, p0)
+    val.sum().backward()  # broadcast upstream gradient
+    for j in range(2):
+        assert abs(kab[j].grad.item() - ge["grad_kab%d" % j]) < 1e-8 * abs(ge["grad_kab%d" % j])
+    # per-state weights: against the general kernel (T requires a gradient there)
+    w = torch.linspace(0.5, 1.5, n, dtype=F64, device="cuda")
+    got = []
+    for need_t in (False, True):
+        for k in kab:
+            k.grad = None
+        tt = t.clone().requires_grad_(need_t)
+        val, nans = (model.bubble_point if bubble else model.dew_point)(tt, z, p0)
+        (val * w[~nans]).sum().backward()
+        got.append([k.grad.item() for k in kab])
+    for a, b in zip(*got):
+        assert abs(a - b) <= 1e-12 * abs(b) and b != 0.0
+
+
 def test_reference_configs(ft, golden_gc):
     """tests/test_gc_pcsaft.py:130-222."""
     cfg = cases.GC_POINT

@@ -121,6 +121,9 @@ def test_base_adjoint_equals_dual_passes(golden_gc):
         b = sim.gc_point_bwd(pairs, seg, kab, idx, phi, T, rho, bubble, g)
         for x, y in zip(a, b):
             assert np.abs(x - y).max() <= 1e-10 * np.abs(x).max()
+        # the k_ab-only path (gc_point_bwd_kab_kernel: two closed-form adjoints + the record pairs) gives the same k_ab gradient
+        gk = sim.gc_point_bwd_kab(pairs, seg, kab, idx, phi, T, rho, bubble, g)
+        assert np.abs(gk - b[1]).max() <= 1e-12 * np.abs(b[1]).max() and np.abs(b[1]).min() > 0
 
 
 def test_closed_form_base_eval_equals_hyper_dual(golden_gc):
