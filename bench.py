@@ -605,7 +605,7 @@ def _main(out):
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extras", default=None, help="comma-separated workloads measured in short legs under `extras` "
                     "(default: c3,c4,c5 with the headline workload, none otherwise; 'none' switches them off)")
-    ap.add_argument("--extra-steps", type=int, default=5)
+    ap.add_argument("--extra-steps", type=int, default=10)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
 

@@ -131,14 +131,31 @@ extern "C" int feos_dev_compact(const uint8_t* failed, int64_t n, int32_t* pos, 
   FEOS_ARG(failed);
   FEOS_ARG(!in || (out && in_cols >= 1 && out_cols >= in_cols));
   int tiles = (int)((n + kTile - 1) / kTile);
-  int32_t* ws = nullptr;
-  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)tiles, s)) return rc_;
+  Scratch scratch;
+  if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)tiles, s)) return rc_;
+  int32_t* ws = scratch.as<int32_t>();
   compact_count_kernel<<<tiles, 256, 0, s>>>(failed, n, ws);
   FEOS_LAUNCH_OK();
   compact_scan_kernel<<<1, 1024, 0, s>>>(ws, tiles, n_ok);
   FEOS_LAUNCH_OK();
   compact_scatter_kernel<<<tiles, 256, 0, s>>>(failed, n, ws, pos, in, in_cols, out, out_cols);
   FEOS_LAUNCH_OK();
-  FEOS_CUDA(cudaFreeAsync(ws, s));
+  return 0;
+}
+
+int feos::host_compact_download(HostCall& hc, const uint8_t* d_failed, int64_t n, const double* d_values, int in_cols,
+                                int out_cols, double* h_out, uint8_t* h_status, int64_t* n_ok) {
+  double* d_out = nullptr;
+  int64_t* d_count = nullptr;
+  if (int rc = hc.alloc(&d_out, (size_t)n * out_cols)) return rc;
+  if (int rc = hc.alloc(&d_count, 1)) return rc;
+  if (int rc = feos_dev_compact(d_failed, n, nullptr, d_count, d_values, in_cols, d_out, out_cols, hc.s)) return rc;
+  FEOS_CUDA(cudaMemcpyAsync(h_status, d_failed, n, cudaMemcpyDeviceToHost, hc.s));
+  int64_t k = 0;
+  FEOS_CUDA(cudaMemcpyAsync(&k, d_count, sizeof(k), cudaMemcpyDeviceToHost, hc.s));
+  FEOS_CUDA(cudaStreamSynchronize(hc.s));
+  if (k > 0) FEOS_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * (size_t)k * out_cols, cudaMemcpyDeviceToHost, hc.s));
+  FEOS_CUDA(cudaStreamSynchronize(hc.s));
+  *n_ok = k;
   return 0;
 }

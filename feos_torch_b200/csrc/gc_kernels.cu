@@ -11,7 +11,6 @@
 //   gc_state_kernel          a, p, mu_i, v_i at given (T, rho_1, rho_2)  (GcPcSaftMix.derivatives).
 #include <algorithm>
 #include <cstdlib>
-#include <vector>
 
 #include "../../include/feos_b200.h"
 #include "common.h"
@@ -400,16 +399,6 @@ gc_state_kernel(GcArgs g, const double* __restrict__ density, int64_t n, double*
 using namespace feos;
 
 namespace {
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -2; }
-  template <class T>
-  T* as() { return (T*)p; }
-};
-
 int check_tables(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg, int32_t n_rec,
                  const double* kab, const int32_t* pair_index) {
   FEOS_ARG(pairs && n_pairs > 0 && seg_params && n_seg > 0 && n_rec >= 0 && pair_index);
@@ -432,28 +421,27 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   FEOS_ARG(temperature && molefracs && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
   GcArgs g{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
-  int32_t* ws = nullptr;  // [0] = retry counter, [1] = queue head, [2 ..] = retry list
-  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  Scratch scratch;  // [0] = retry counter, [1] = queue head, [2 ..] = retry list
+  if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  int32_t* ws = scratch.as<int32_t>();
   FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
-  static const int smem_ok = [] {
-    cudaError_t e = cudaFuncSetAttribute(gc_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem);
-    if (e != cudaSuccess) return (int)e;
-    return (int)cudaFuncSetAttribute(gc_point_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem);
-  }();
-  FEOS_ARG(smem_ok == cudaSuccess);
+  static PerDevice cache;  // shared-memory opt-in and persistent grid size, once per DEVICE
+  int blocks = 0;
+  if (int rc_ = cache.get([](int dev, int* v) {
+        FEOS_CUDA(cudaFuncSetAttribute(gc_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem));
+        FEOS_CUDA(cudaFuncSetAttribute(gc_point_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem));
+        int sms = 0, per_sm = 0;
+        FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_point_queue_kernel, kGcFwdBlock, kGcSmem));
+        *v = sms * (per_sm > 0 ? per_sm : 1);
+        return 0;
+      }, &blocks))
+    return rc_;
   static const int variant = point_kernel_variant();
   if (variant == 0 || n < 65536) {
     gc_point_fwd_kernel<<<grid_for(n, kGcFwdBlock), kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure,
                                                                              failed, evals, ws + 2, ws, order);
   } else {
-    static int blocks = 0;
-    if (!blocks) {
-      int dev = 0, sms = 0, per_sm = 0;
-      FEOS_CUDA(cudaGetDevice(&dev));
-      FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gc_point_queue_kernel, kGcFwdBlock, kGcSmem));
-      blocks = sms * (per_sm > 0 ? per_sm : 1);
-    }
     GcQueueSource src{g, molefracs, rho, pressure, failed};
     int grid = (int)std::min<int64_t>(blocks, (n + kGcFwdBlock - 1) / kGcFwdBlock);
     gc_point_queue_kernel<<<grid, kGcFwdBlock, kGcSmem, s>>>(src, (int)n, bubble, evals, ws + 2, ws, ws + 1);
@@ -462,7 +450,6 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
   gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, start_pressure, bubble, rho, pressure, failed, evals, ws + 2, ws);
   FEOS_LAUNCH_OK();
-  FEOS_CUDA(cudaFreeAsync(ws, s));
   return 0;
 }
 
@@ -528,50 +515,31 @@ int feos_host_gc_point(const feos_gc_pair* pairs, int32_t n_pairs, const double*
   if (n == 0) return 0;
   if (int rc = check_tables(pairs, n_pairs, seg_params, n_seg, n_rec, kab, pair_index)) return rc;
   FEOS_ARG(temperature && molefracs && rho_out && status);
-  DevBuf dpairs, dseg, dkab, didx, dphi, dt, dz, dp0, drho, dfail;
-  if (dpairs.alloc(sizeof(GcPair) * n_pairs) || dseg.alloc(64 * (size_t)n_seg) || dkab.alloc(8 * (size_t)n_rec) ||
-      didx.alloc(4 * n) || dphi.alloc(16 * n) || dt.alloc(8 * n) || dz.alloc(8 * n) || drho.alloc(32 * n) || dfail.alloc(n) ||
-      (pressure && dp0.alloc(8 * n))) {
-    set_error("cudaMalloc failed for %lld states", (long long)n);
-    return -2;
+  HostCall hc;
+  feos_gc_pair* dpairs;
+  double *dseg, *dkab = nullptr, *dphi = nullptr, *dt, *dz, *dp0 = nullptr, *drho;
+  int32_t *didx, *dorder = nullptr;
+  uint8_t* dfail;
+  if (int rc = hc.upload(&dpairs, pairs, (size_t)n_pairs)) return rc;
+  if (int rc = hc.upload(&dseg, seg_params, 8 * (size_t)n_seg)) return rc;
+  if (int rc = n_rec ? hc.upload(&dkab, kab, (size_t)n_rec) : hc.alloc(&dkab, 1)) return rc;
+  if (int rc = hc.upload(&didx, pair_index, (size_t)n)) return rc;
+  if (phi)
+    if (int rc = hc.upload(&dphi, phi, 2 * (size_t)n)) return rc;
+  if (int rc = hc.upload(&dt, temperature, (size_t)n)) return rc;
+  if (int rc = hc.upload(&dz, molefracs, (size_t)n)) return rc;
+  if (pressure)
+    if (int rc = hc.upload(&dp0, pressure, (size_t)n)) return rc;
+  if (int rc = hc.alloc(&drho, 4 * (size_t)n)) return rc;
+  if (int rc = hc.alloc(&dfail, (size_t)n)) return rc;
+  if (n >= kOrderMinStates) {
+    if (int rc = hc.alloc(&dorder, (size_t)n)) return rc;
+    if (int rc = feos_dev_gc_point_order(didx, n_pairs, dt, dz, n, 0, dorder, hc.s)) return rc;
   }
-  if (pressure) FEOS_CUDA(cudaMemcpyAsync(dp0.p, pressure, 8 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dpairs.p, pairs, sizeof(GcPair) * n_pairs, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dseg.p, seg_params, 64 * (size_t)n_seg, cudaMemcpyHostToDevice, 0));
-  if (n_rec) FEOS_CUDA(cudaMemcpyAsync(dkab.p, kab, 8 * (size_t)n_rec, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(didx.p, pair_index, 4 * n, cudaMemcpyHostToDevice, 0));
-  if (phi) FEOS_CUDA(cudaMemcpyAsync(dphi.p, phi, 16 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dz.p, molefracs, 8 * n, cudaMemcpyHostToDevice, 0));
-  DevBuf dorder;
-  const bool ordered = n >= kOrderMinStates;
-  if (ordered) {
-    if (dorder.alloc(4 * n)) {
-      set_error("cudaMalloc failed for %lld states", (long long)n);
-      return -2;
-    }
-    if (int rc = feos_dev_gc_point_order(didx.as<int32_t>(), n_pairs, dt.as<double>(), dz.as<double>(), n, 0,
-                                         dorder.as<int32_t>(), nullptr))
-      return rc;
-  }
-  int rc = feos_dev_gc_point_fwd(dpairs.as<feos_gc_pair>(), n_pairs, dseg.as<double>(), n_seg, dkab.as<double>(), n_rec,
-                                 didx.as<int32_t>(), phi ? dphi.as<double>() : nullptr, dt.as<double>(), dz.as<double>(),
-                                 pressure ? dp0.as<double>() : nullptr, n, bubble, drho.as<double>(), nullptr,
-                                 dfail.as<uint8_t>(), nullptr,
-                                 ordered ? dorder.as<int32_t>() : nullptr, nullptr);
-  if (rc) return rc;
-  std::vector<double> rho(4 * (size_t)n);
-  FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 32 * n, cudaMemcpyDeviceToHost, 0));
-  FEOS_CUDA(cudaMemcpyAsync(status, dfail.p, n, cudaMemcpyDeviceToHost, 0));
-  FEOS_CUDA(cudaStreamSynchronize(0));
-  int64_t k = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    if (status[i]) continue;
-    for (int c = 0; c < 4; ++c) rho_out[4 * k + c] = rho[4 * i + c];
-    ++k;
-  }
-  *n_ok = k;
-  return 0;
+  if (int rc = feos_dev_gc_point_fwd(dpairs, n_pairs, dseg, n_seg, dkab, n_rec, didx, dphi, dt, dz, dp0, n, bubble, drho,
+                                     nullptr, dfail, nullptr, dorder, hc.s))
+    return rc;
+  return host_compact_download(hc, dfail, n, drho, 4, 4, rho_out, status, n_ok);
 }
 
 }  // extern "C"

@@ -10,7 +10,6 @@
 //   mix_state_kernel         a, p, mu_i, v_i at given (T, rho_1, rho_2)  (PcSaftMix.derivatives).
 #include <algorithm>
 #include <cstdlib>
-#include <vector>
 
 #include "../../include/feos_b200.h"
 #include "common.h"
@@ -314,16 +313,6 @@ mix_state_kernel(const double* __restrict__ params, const double* __restrict__ k
 using namespace feos;
 
 namespace {
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -2; }
-  template <class T>
-  T* as() { return (T*)p; }
-};
-
 int host_point(const double* params, const double* kij, const double* temperature, const double* molefracs,
                const double* pressure, int64_t n, int bubble, double* rho_out, uint8_t* status, int64_t* n_ok) {
   clear_error();
@@ -331,43 +320,25 @@ int host_point(const double* params, const double* kij, const double* temperatur
   *n_ok = 0;
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && molefracs && rho_out && status);
-  DevBuf dp, dk, dt, dz, dp0, drho, dfail;
-  if (dp.alloc(128 * n) || dk.alloc(16 * n) || dt.alloc(8 * n) || dz.alloc(8 * n) || drho.alloc(32 * n) || dfail.alloc(n) ||
-      (pressure && dp0.alloc(8 * n))) {
-    set_error("cudaMalloc failed for %lld states", (long long)n);
-    return -2;
+  HostCall hc;
+  double *dp, *dk, *dt, *dz, *dp0 = nullptr, *drho;
+  uint8_t* dfail;
+  int32_t* dorder = nullptr;
+  if (int rc = hc.upload(&dp, params, 16 * (size_t)n)) return rc;
+  if (int rc = hc.upload(&dk, kij, 2 * (size_t)n)) return rc;
+  if (int rc = hc.upload(&dt, temperature, (size_t)n)) return rc;
+  if (int rc = hc.upload(&dz, molefracs, (size_t)n)) return rc;
+  if (pressure)
+    if (int rc = hc.upload(&dp0, pressure, (size_t)n)) return rc;
+  if (int rc = hc.alloc(&drho, 4 * (size_t)n)) return rc;
+  if (int rc = hc.alloc(&dfail, (size_t)n)) return rc;
+  if (n >= kOrderMinStates) {
+    if (int rc = hc.alloc(&dorder, (size_t)n)) return rc;
+    if (int rc = feos_dev_mix_point_order(dp, dt, dz, n, 0, dorder, hc.s)) return rc;
   }
-  if (pressure) FEOS_CUDA(cudaMemcpyAsync(dp0.p, pressure, 8 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 128 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dk.p, kij, 16 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dz.p, molefracs, 8 * n, cudaMemcpyHostToDevice, 0));
-  DevBuf dorder;
-  const bool ordered = n >= kOrderMinStates;
-  if (ordered) {
-    if (dorder.alloc(4 * n)) {
-      set_error("cudaMalloc failed for %lld states", (long long)n);
-      return -2;
-    }
-    if (int rc = feos_dev_mix_point_order(dp.as<double>(), dt.as<double>(), dz.as<double>(), n, 0, dorder.as<int32_t>(), nullptr))
-      return rc;
-  }
-  int rc = feos_dev_mix_point_fwd(dp.as<double>(), dk.as<double>(), dt.as<double>(), dz.as<double>(),
-                                  pressure ? dp0.as<double>() : nullptr, n, bubble, 0, drho.as<double>(), nullptr,
-                                  dfail.as<uint8_t>(), nullptr, ordered ? dorder.as<int32_t>() : nullptr, nullptr);
-  if (rc) return rc;
-  std::vector<double> rho(4 * (size_t)n);
-  FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 32 * n, cudaMemcpyDeviceToHost, 0));
-  FEOS_CUDA(cudaMemcpyAsync(status, dfail.p, n, cudaMemcpyDeviceToHost, 0));
-  FEOS_CUDA(cudaStreamSynchronize(0));
-  int64_t k = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    if (status[i]) continue;
-    for (int c = 0; c < 4; ++c) rho_out[4 * k + c] = rho[4 * i + c];  // filter_binary, src/pcsaft.rs:216-231
-    ++k;
-  }
-  *n_ok = k;
-  return 0;
+  if (int rc = feos_dev_mix_point_fwd(dp, dk, dt, dz, dp0, n, bubble, 0, drho, nullptr, dfail, nullptr, dorder, hc.s))
+    return rc;
+  return host_compact_download(hc, dfail, n, drho, 4, 4, rho_out, status, n_ok);  // filter_binary, src/pcsaft.rs:216-231
 }
 }  // namespace
 
@@ -382,29 +353,29 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && molefracs && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
-  int32_t* ws = nullptr;  // [0] = retry counter, [1] = queue head, [2 ..] = retry list
-  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  Scratch scratch;  // [0] = retry counter, [1] = queue head, [2 ..] = retry list
+  if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  int32_t* ws = scratch.as<int32_t>();
   FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
-  static const int smem_ok = [] {
-    cudaError_t e = cudaFuncSetAttribute(mix_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem);
-    if (e != cudaSuccess) return (int)e;
-    return (int)cudaFuncSetAttribute(mix_point_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem);
-  }();
-  FEOS_ARG(smem_ok == cudaSuccess);
+  // opt-in to > 48 KB of dynamic shared memory and the persistent grid size: once per DEVICE
+  static PerDevice cache;
+  int blocks = 0;
+  if (int rc_ = cache.get([](int dev, int* v) {
+        FEOS_CUDA(cudaFuncSetAttribute(mix_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem));
+        FEOS_CUDA(cudaFuncSetAttribute(mix_point_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem));
+        int sms = 0, per_sm = 0;
+        FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mix_point_queue_kernel, kMixBlock, kMixSmem));
+        *v = sms * (per_sm > 0 ? per_sm : 1);
+        return 0;
+      }, &blocks))
+    return rc_;
   // default = one thread per state; FEOS_B200_POINT_KERNEL=queue selects the persistent work-queue kernel
   static const int variant = point_kernel_variant();
   if (variant == 0 || n < 65536) {
     mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, kMixSmem, s>>>(
         params, kij, temperature, molefracs, n, bubble, flags, rho, pressure, failed, evals, ws + 2, ws, order);
   } else {
-    static int blocks = 0;
-    if (!blocks) {
-      int dev = 0, sms = 0, per_sm = 0;
-      FEOS_CUDA(cudaGetDevice(&dev));
-      FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mix_point_queue_kernel, kMixBlock, kMixSmem));
-      blocks = sms * (per_sm > 0 ? per_sm : 1);
-    }
     MixQueueSource src{params, kij, temperature, molefracs, rho, pressure, failed, flags};
     int grid = (int)std::min<int64_t>(blocks, (n + kMixBlock - 1) / kMixBlock);
     mix_point_queue_kernel<<<grid, kMixBlock, kMixSmem, s>>>(src, (int)n, bubble, evals, ws + 2, ws, ws + 1);
@@ -414,7 +385,6 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   mix_point_retry_kernel<<<retry_grid, 64, 0, s>>>(params, kij, temperature, molefracs, start_pressure, bubble, flags, rho,
                                                   pressure, failed, evals, ws + 2, ws);
   FEOS_LAUNCH_OK();
-  FEOS_CUDA(cudaFreeAsync(ws, s));
   return 0;
 }
 

@@ -57,6 +57,7 @@ gc_order_key_kernel(const int32_t* __restrict__ pair_index, const double* __rest
 
 // scratch layout: keys_in [n] u64 | keys_out [n] u64 | index [n] i32 | cub temporary storage
 struct OrderScratch {
+  Scratch mem;
   void* base = nullptr;
   uint64_t* keys_in = nullptr;
   uint64_t* keys_out = nullptr;
@@ -70,7 +71,8 @@ static int order_scratch(OrderScratch& w, int64_t n, int begin_bit, int end_bit,
                                             (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, begin_bit, end_bit, s));
   size_t keys = (sizeof(uint64_t) * (size_t)n + 255) / 256 * 256;
   size_t idx = (sizeof(int32_t) * (size_t)n + 255) / 256 * 256;
-  if (int rc = scratch_alloc(&w.base, 2 * keys + idx + w.temp_bytes, s)) return rc;
+  if (int rc = w.mem.alloc(2 * keys + idx + w.temp_bytes, s)) return rc;
+  w.base = w.mem.p;
   char* p = (char*)w.base;
   w.keys_in = (uint64_t*)p;
   w.keys_out = (uint64_t*)(p + keys);
@@ -84,8 +86,7 @@ static int order_sort(OrderScratch& w, int64_t n, int begin_bit, int end_bit, in
   FEOS_CUDA(cub::DeviceRadixSort::SortPairs(w.temp, w.temp_bytes, (const uint64_t*)w.keys_in, w.keys_out,
                                             (const int32_t*)w.index, order, (int)n, begin_bit, end_bit, s));
   count_launch(4);  // histogram + onesweep passes (accounting only)
-  FEOS_CUDA(cudaFreeAsync(w.base, s));
-  return 0;
+  return 0;  // w.mem gives the scratch back (stream-ordered) when the caller's OrderScratch goes out of scope
 }
 
 }  // namespace feos

@@ -14,7 +14,6 @@
 //   pure_state_kernel        a, p, dp/drho at given (T, rho).
 #include <algorithm>
 #include <cstdlib>
-#include <vector>
 
 #include "../../include/feos_b200.h"
 #include "common.h"
@@ -344,24 +343,12 @@ pure_state_kernel(const double* __restrict__ params, const double* __restrict__ 
 using namespace feos;
 
 namespace {
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() {
-    if (p) cudaFree(p);
-  }
-  int alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? 0 : -2; }
-  template <class T>
-  T* as() { return (T*)p; }
-};
-
-// state order for the host entry points (large batches only; buf stays NULL = input order otherwise)
-int host_order(DevBuf& buf, const double* params, const double* temperature, int64_t n) {
+// state order for the host entry points (large batches only; NULL = input order otherwise)
+int host_order(HostCall& hc, int32_t** order, const double* params, const double* temperature, int64_t n) {
+  *order = nullptr;
   if (n < kOrderMinStates) return 0;
-  if (buf.alloc(4 * n)) {
-    set_error("cudaMalloc failed for %lld states", (long long)n);
-    return -2;
-  }
-  return feos_dev_pure_order(params, temperature, n, buf.as<int32_t>(), nullptr);
+  if (int rc = hc.alloc(order, (size_t)n)) return rc;
+  return feos_dev_pure_order(params, temperature, n, *order, hc.s);
 }
 }  // namespace
 
@@ -375,8 +362,9 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
   if (n == 0) return 0;
   FEOS_ARG(params && temperature && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
-  int32_t* ws = nullptr;  // [0] = retry counter, [1] = queue head, [2..n+1] = retry list
-  if (int rc_ = scratch_alloc((void**)&ws, sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  Scratch scratch;  // [0] = retry counter, [1] = queue head, [2..n+1] = retry list
+  if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  int32_t* ws = scratch.as<int32_t>();
   FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
   // FEOS_B200_PURE_VLE_KERNEL = "loop" (one thread per state) / "queue" (persistent work queue) for A/B runs.
   // Default: states in input order -> queue (1 M C2 states, ncu: 0.566 ms, 22.4 of 32 lanes active per
@@ -390,14 +378,16 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
     pure_vle_fwd_kernel<<<grid_for(n, kBlock), kBlock, 0, s>>>(params, temperature, n, rho, vapor_pressure,
                                                              liquid_density, failed, evals, ws + 2, ws, order);
   } else {
-    static int blocks = 0;
-    if (!blocks) {
-      int dev = 0, sms = 0, per_sm = 0;
-      FEOS_CUDA(cudaGetDevice(&dev));
-      FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pure_vle_queue_kernel, kBlock, 0));
-      blocks = sms * (per_sm > 0 ? per_sm : 1);  // persistent grid: every resident slot of every SM
-    }
+    static PerDevice cache;
+    int blocks = 0;
+    if (int rc_ = cache.get([](int dev, int* v) {
+          int sms = 0, per_sm = 0;
+          FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+          FEOS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pure_vle_queue_kernel, kBlock, 0));
+          *v = sms * (per_sm > 0 ? per_sm : 1);  // persistent grid: every resident slot of every SM
+          return 0;
+        }, &blocks))
+      return rc_;
     int grid = (int)std::min<int64_t>(blocks, (n + kBlock - 1) / kBlock);
     pure_vle_queue_kernel<<<grid, kBlock, 0, s>>>(params, temperature, (int)n, rho, vapor_pressure, liquid_density,
                                                 failed, evals, ws + 2, ws, ws + 1, order);
@@ -407,7 +397,6 @@ int feos_dev_pure_vle_fwd(const double* params, const double* temperature, int64
   pure_vle_retry_kernel<<<retry_grid, 64, 0, s>>>(params, temperature, rho, vapor_pressure, liquid_density, failed,
                                                  evals, ws + 2, ws);
   FEOS_LAUNCH_OK();
-  FEOS_CUDA(cudaFreeAsync(ws, s));
   return 0;
 }
 
@@ -472,40 +461,25 @@ int feos_dev_pure_state(const double* params, const double* temperature, const d
 // host-buffer entry points (reference native signatures)
 // ---------------------------------------------------------------------------------------------
 
-int feos_host_pcsaft_vapor_pressure(const double* params, const double* temperature, int64_t n,
-                                    double* rho_out, uint8_t* status, int64_t* n_ok) {
+int feos_host_pcsaft_vapor_pressure(const double* params, const double* temperature, int64_t n, double* rho_out,
+                                    uint8_t* status, int64_t* n_ok) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31 && n_ok);
   *n_ok = 0;
   if (n == 0) return 0;
   FEOS_ARG(params && temperature && rho_out && status);
-  DevBuf dp, dt, drho, dfail;
-  if (dp.alloc(64 * n) || dt.alloc(8 * n) || drho.alloc(16 * n) || dfail.alloc(n)) {
-    set_error("cudaMalloc failed for %lld states", (long long)n);
-    return -2;
-  }
-  FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 64 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
-  DevBuf dorder;
-  if (int rc = host_order(dorder, dp.as<double>(), dt.as<double>(), n)) return rc;
-  int rc = feos_dev_pure_vle_fwd(dp.as<double>(), dt.as<double>(), n, drho.as<double>(), nullptr, nullptr,
-                                 dfail.as<uint8_t>(), nullptr, dorder.as<int32_t>(), nullptr);
-  if (rc) return rc;
-  std::vector<double> rho(2 * (size_t)n);
-  FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 16 * n, cudaMemcpyDeviceToHost, 0));
-  FEOS_CUDA(cudaMemcpyAsync(status, dfail.p, n, cudaMemcpyDeviceToHost, 0));
-  FEOS_CUDA(cudaStreamSynchronize(0));
-  int64_t k = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    if (status[i]) continue;
-    rho_out[4 * k] = rho[2 * i];
-    rho_out[4 * k + 1] = rho[2 * i + 1];
-    rho_out[4 * k + 2] = 0.0;  // src/pcsaft.rs:95-101 leaves columns 2, 3 at zero
-    rho_out[4 * k + 3] = 0.0;
-    ++k;
-  }
-  *n_ok = k;
-  return 0;
+  HostCall hc;
+  double *dp, *dt, *drho;
+  uint8_t* dfail;
+  int32_t* dorder;
+  if (int rc = hc.upload(&dp, params, 8 * (size_t)n)) return rc;
+  if (int rc = hc.upload(&dt, temperature, (size_t)n)) return rc;
+  if (int rc = hc.alloc(&drho, 2 * (size_t)n)) return rc;
+  if (int rc = hc.alloc(&dfail, (size_t)n)) return rc;
+  if (int rc = host_order(hc, &dorder, dp, dt, n)) return rc;
+  if (int rc = feos_dev_pure_vle_fwd(dp, dt, n, drho, nullptr, nullptr, dfail, nullptr, dorder, hc.s)) return rc;
+  // rows (rho_V, rho_L, 0, 0) of the converged states: src/pcsaft.rs:95-101 leaves columns 2, 3 at zero
+  return host_compact_download(hc, dfail, n, drho, 2, 4, rho_out, status, n_ok);
 }
 
 int feos_host_pcsaft_liquid_density(const double* params, const double* temperature, const double* pressure,
@@ -515,28 +489,18 @@ int feos_host_pcsaft_liquid_density(const double* params, const double* temperat
   *n_ok = 0;
   if (n == 0) return 0;
   FEOS_ARG(params && temperature && pressure && rho_out && status);
-  DevBuf dp, dt, dpr, drho, dfail;
-  if (dp.alloc(64 * n) || dt.alloc(8 * n) || dpr.alloc(8 * n) || drho.alloc(8 * n) || dfail.alloc(n)) {
-    set_error("cudaMalloc failed for %lld states", (long long)n);
-    return -2;
-  }
-  FEOS_CUDA(cudaMemcpyAsync(dp.p, params, 64 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dt.p, temperature, 8 * n, cudaMemcpyHostToDevice, 0));
-  FEOS_CUDA(cudaMemcpyAsync(dpr.p, pressure, 8 * n, cudaMemcpyHostToDevice, 0));
-  DevBuf dorder;
-  if (int rc = host_order(dorder, dp.as<double>(), dt.as<double>(), n)) return rc;
-  int rc = feos_dev_pure_rho_tp_fwd(dp.as<double>(), dt.as<double>(), dpr.as<double>(), n, drho.as<double>(), nullptr,
-                                    dfail.as<uint8_t>(), nullptr, dorder.as<int32_t>(), nullptr);
-  if (rc) return rc;
-  std::vector<double> rho((size_t)n);
-  FEOS_CUDA(cudaMemcpyAsync(rho.data(), drho.p, 8 * n, cudaMemcpyDeviceToHost, 0));
-  FEOS_CUDA(cudaMemcpyAsync(status, dfail.p, n, cudaMemcpyDeviceToHost, 0));
-  FEOS_CUDA(cudaStreamSynchronize(0));
-  int64_t k = 0;
-  for (int64_t i = 0; i < n; ++i)
-    if (!status[i]) rho_out[k++] = rho[i];
-  *n_ok = k;
-  return 0;
+  HostCall hc;
+  double *dp, *dt, *dpr, *drho;
+  uint8_t* dfail;
+  int32_t* dorder;
+  if (int rc = hc.upload(&dp, params, 8 * (size_t)n)) return rc;
+  if (int rc = hc.upload(&dt, temperature, (size_t)n)) return rc;
+  if (int rc = hc.upload(&dpr, pressure, (size_t)n)) return rc;
+  if (int rc = hc.alloc(&drho, (size_t)n)) return rc;
+  if (int rc = hc.alloc(&dfail, (size_t)n)) return rc;
+  if (int rc = host_order(hc, &dorder, dp, dt, n)) return rc;
+  if (int rc = feos_dev_pure_rho_tp_fwd(dp, dt, dpr, n, drho, nullptr, dfail, nullptr, dorder, hc.s)) return rc;
+  return host_compact_download(hc, dfail, n, drho, 1, 1, rho_out, status, n_ok);
 }
 
 }  // extern "C"

@@ -262,12 +262,14 @@ FD int pure_vle_robust(const PureCoef<double>& c, double rho_max, double& rho_l,
   double min_dp = 1e300;
   int i_min = 1;
   double prev_rho = 0.0, prev_dp = 1.0;
+  double dp_before = 1.0, dp_after = -1.0;  // samples next to the smallest one (dp_after < 0: not taken yet)
   for (int i = 1; i <= NG; ++i) {
     double x = (double)i / NG;
     double rho = top * x * (0.3 + 0.7 * x);  // denser sampling at low density
     double dp = pure_eval(c, rho).dp;
     evals += 1;
-    if (dp < min_dp) { min_dp = dp; i_min = i; }
+    if (dp < min_dp) { min_dp = dp; i_min = i; dp_before = prev_dp; dp_after = -1.0; }
+    else if (i == i_min + 1) dp_after = dp;
     if (!(dp > 0.0)) {
       if (a_hi < 0.0) { a_lo = prev_rho; fa_lo = prev_dp; a_hi = rho; fa_hi = dp; }
       b_lo = rho; fb_lo = dp; b_hi = -1.0;
@@ -278,8 +280,21 @@ FD int pure_vle_robust(const PureCoef<double>& c, double rho_max, double& rho_l,
     prev_rho = rho; prev_dp = dp;
   }
   if (a_hi < 0.0) {
-    // no unstable grid point: golden-section search for the minimum of dp around the smallest sample
     auto grid = [&](int i) { double x = (double)i / NG; return top * x * (0.3 + 0.7 * x); };
+    // no unstable grid point.  Clearly super-critical states (half of the retry list of a fit with a
+    // super-critical slice) are recognised from the scan alone: the parabola through the smallest sample and
+    // its two neighbours bounds the minimum of dp/drho (ideal gas: 1) well above zero.
+    if (i_min > 1 && i_min < NG && dp_after > 0.0) {
+      double x0 = grid(i_min - 1), x1 = grid(i_min), x2 = grid(i_min + 1);
+      double d01 = (min_dp - dp_before) / (x1 - x0), d12 = (dp_after - min_dp) / (x2 - x1);
+      double curv = (d12 - d01) / (x2 - x0);
+      if (curv > 0.0) {
+        double xv = 0.5 * (x0 + x1) - 0.5 * d01 / curv;
+        double fv = dp_before + d01 * (xv - x0) + curv * (xv - x0) * (xv - x1);
+        if (fv > 0.05 && min_dp > 0.05) return kStatusFailed;
+      }
+    }
+    // otherwise: golden-section search for the minimum of dp around the smallest sample
     double lo = grid(i_min - 1), hi = grid(i_min < NG ? i_min + 1 : NG);
     if (i_min == 1) lo = 0.05 * grid(1);
     const double gr = 0.6180339887498949;
@@ -315,6 +330,18 @@ FD int pure_vle_robust(const PureCoef<double>& c, double rho_max, double& rho_l,
   double p_sv = pure_eval(c, rho_sv).p, p_sl = pure_eval(c, rho_sl).p;
   evals += 2;
   if (!(p_sv > 0.0) || !(p_sv > p_sl)) return kStatusFailed;
+  // 3a. near the critical point the binodal is the spinodal scaled by sqrt(3) about its mid density (Landau
+  //     expansion): from there the coupled Newton iteration usually converges in a few steps, instead of the
+  //     ~60 evaluations of the bracketed pressure iteration below (which remains the fallback)
+  {
+    double mid = 0.5 * (rho_sv + rho_sl), half = 0.5 * (rho_sl - rho_sv);
+    double rv0 = mid - 1.7320508075688772 * half;
+    if (rv0 > 0.25 * rho_sv) {
+      rho_l = mid + 1.7320508075688772 * half;
+      u = log(rv0);
+      if (pure_vle_newton(c, rho_l, u, el, ev, rho_l_eval, rho_v_eval, 30, evals) == kStatusOk) return kStatusOk;
+    }
+  }
   // 3. bracketed Newton in q = ln p on G(p) = mu_L(p) - mu_V(p), dG/dp = 1/rho_L - 1/rho_V < 0; coarse:
   //    the coupled Newton iteration polishes the result
   double q_hi = log(p_sv);

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .pcsaft_pure import _back, _cuda_device, _prep, _stream, _upstream, compact
+from .pcsaft_pure import _back, _on_device, _cuda_device, _prep, _stream, _upstream, compact
 
 MAX_SEG = 12
 MAX_BOND = 16
@@ -114,7 +114,7 @@ class _GcPoint(torch.autograd.Function):
         rho = torch.empty((n, 4), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.timed_call(
                 "feos_dev_gc_point_fwd", _lib.ptr(pairs_dev), n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                 _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
@@ -140,7 +140,7 @@ class _GcPoint(torch.autograd.Function):
         g_kab = torch.zeros_like(kab) if need_kab and kab.shape[0] else None
         g_phi = torch.empty_like(phi) if need_phi and phi is not None else None
         g_t = torch.empty_like(temperature) if need_t else None
-        with torch.cuda.device(temperature.device):
+        with _on_device(temperature.device):
             _lib.timed_call(
                 "feos_dev_gc_point_bwd", _lib.ptr(pairs_dev), ctx.n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                 _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature), _lib.ptr(rho),
@@ -164,7 +164,7 @@ class _GcState(torch.autograd.Function):
         p = torch.empty((n,), dtype=torch.float64, device=dev)
         mu = torch.empty((n, 2), dtype=torch.float64, device=dev)
         v = torch.empty((n, 2), dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.call("feos_dev_gc_state", _lib.ptr(pairs_dev), n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                       _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
                       _lib.ptr(density), n, _lib.ptr(a), _lib.ptr(p), _lib.ptr(mu), _lib.ptr(v), _stream())
@@ -184,7 +184,7 @@ class _GcState(torch.autograd.Function):
         g_t = torch.empty_like(temperature) if need_t else None
         g_r = torch.empty_like(density) if need_r else None
         if n:
-            with torch.cuda.device(temperature.device):
+            with _on_device(temperature.device):
                 _lib.call("feos_dev_gc_state_bwd", _lib.ptr(pairs_dev), ctx.n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                           _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
                           _lib.ptr(density), n, _lib.ptr(ga), _lib.ptr(gp), _lib.ptr(gmu), _lib.ptr(gv), _lib.ptr(g_seg),
@@ -243,7 +243,7 @@ class GcPcSaftMix:
             # set is recognised by the caller's (T, x) tensor objects in the next iteration of a fit loop.
             def compute(pair_only):
                 o = torch.empty((n,), dtype=torch.int32, device=self._dev)
-                with torch.cuda.device(self._dev):
+                with _on_device(self._dev):
                     _lib.timed_call("feos_dev_gc_point_order", _lib.ptr(self._pair_index), self._n_pairs, _lib.ptr(t),
                                     _lib.ptr(z), n, pair_only, _lib.ptr(o), _stream())
                 return o

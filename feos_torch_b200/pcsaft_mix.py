@@ -8,7 +8,7 @@ and ``temperature``; mole fractions and the starting pressure carry none (pcsaft
 import torch
 
 from . import _lib
-from .pcsaft_pure import _back, _check_rows, _cuda_device, _prep, _stream, _upstream, compact
+from .pcsaft_pure import _back, _on_device, _check_rows, _cuda_device, _prep, _stream, _upstream, compact
 
 
 SHARED_PARAMS, SHARED_KIJ = 1, 2  # include/feos_b200.h: FEOS_SHARED_PARAMS, FEOS_SHARED_KIJ
@@ -40,7 +40,7 @@ class _MixPoint(torch.autograd.Function):
         rho = torch.empty((n, 4), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.timed_call(
                 "feos_dev_mix_point_fwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(molefracs),
                 _lib.ptr(pressure), n, int(bubble), flags, _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None,
@@ -67,7 +67,7 @@ class _MixPoint(torch.autograd.Function):
         gp = (torch.zeros_like(params) if ctx.flags & SHARED_PARAMS else torch.empty_like(params)) if need_p else None
         gk = (torch.zeros_like(kij) if ctx.flags & SHARED_KIJ else torch.empty_like(kij)) if need_k else None
         gt = torch.empty_like(temperature) if need_t else None
-        with torch.cuda.device(params.device):
+        with _on_device(params.device):
             _lib.timed_call(
                 "feos_dev_mix_point_bwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(rho),
                 _lib.ptr(failed), _lib.ptr(pos), _lib.ptr(g), bc, n, ctx.bubble, ctx.flags, _lib.ptr(gp), _lib.ptr(gk),
@@ -87,7 +87,7 @@ class _MixState(torch.autograd.Function):
         p = torch.empty((n,), dtype=torch.float64, device=dev)
         mu = torch.empty((n, 2), dtype=torch.float64, device=dev)
         v = torch.empty((n, 2), dtype=torch.float64, device=dev)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             _lib.call("feos_dev_mix_state", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(density), n,
                       _lib.ptr(a), _lib.ptr(p), _lib.ptr(mu), _lib.ptr(v), _stream())
         ctx.save_for_backward(params, kij, temperature, density)
@@ -101,7 +101,7 @@ class _MixState(torch.autograd.Function):
         need = ctx.needs_input_grad
         out = [torch.empty_like(x) if nd else None for x, nd in zip((params, kij, temperature, density), need)]
         if n:
-            with torch.cuda.device(params.device):
+            with _on_device(params.device):
                 _lib.call("feos_dev_mix_state_bwd", _lib.ptr(params), _lib.ptr(kij), _lib.ptr(temperature), _lib.ptr(density), n,
                           _lib.ptr(ga), _lib.ptr(gp), _lib.ptr(gmu), _lib.ptr(gv), _lib.ptr(out[0]), _lib.ptr(out[1]),
                           _lib.ptr(out[2]), _lib.ptr(out[3]), _stream())
@@ -110,17 +110,22 @@ class _MixState(torch.autograd.Function):
 
 class PcSaftMix:
     """parameters [N, 2, 8] (rows as in PcSaftPure), kij [N, 2] = (k_ij, epsilon_k_aibj; 0 = combining rule).
-    Non-associating mixtures of n > 2 components ([N, n, 8], n <= 4; the reference's Helmholtz energy is general in
-    n for them, pcsaft_mix.py:73-90) support `derivatives` / `helmholtz_energy_density`; bubble / dew points are
-    binary like the reference's native layer (src/pcsaft.rs:173, :206).
+
+    Binary mixtures only, like the reference: its dispersion loop is written for n components (pcsaft_mix.py:73-90),
+    but no call with n != 2 gets through its public API -- with `kij` it raises "kij can only be used for binary
+    mixtures!" (pcsaft_mix.py:74-75), without it `self.kij[cross_associating, 1]` fails on None (pcsaft_mix.py:141),
+    and the native layer is binary (src/pcsaft.rs:173, :206).  tests/test_reference_limits.py pins this.
 
     Shared parameters: `row.expand(N, 2, 8)` / `kij_row.expand(N, 2)` are recognised (stride 0 along the batch) and
     handled as ONE row -- nothing is materialised per state and the gradient sum over the states is reduced inside
     the backward kernel."""
 
     def __init__(self, parameters, kij=None):
-        if parameters.dim() != 3 or parameters.shape[2] != 8 or not 2 <= parameters.shape[1] <= 4:
-            raise ValueError("parameters must have shape [N, n, 8] with n = 2 (n = 3, 4: non-associating state functions only)")
+        if parameters.dim() != 3 or parameters.shape[2] != 8:
+            raise ValueError("parameters must have shape [N, 2, 8]")
+        if parameters.shape[1] != 2:
+            # the reference raises for every n != 2 as well (pcsaft_mix.py:74-75 with kij, :141 without)
+            raise NotImplementedError("binary mixtures only ([N, 2, 8]); the reference's API cannot evaluate n != 2 either")
         _lib.load()
         self._n = parameters.shape[0]
         self._nc = parameters.shape[1]
@@ -168,10 +173,6 @@ class PcSaftMix:
         # pcsaft_mix.py:120-121
         if bool((count > 2).any()):
             raise Exception("Only up to two associating components are allowed!")
-        if self._nc > 2 and bool((count > 0).any() or (parameters[:, :, 3].detach() != 0).any()):
-            raise NotImplementedError(
-                "mixtures of more than two components are supported for non-associating, non-polar components only "
-                "(the reference evaluates association and k_ij for binaries, pcsaft_mix.py:118-152)")
 
     @property
     def parameters(self):
@@ -185,8 +186,6 @@ class PcSaftMix:
         return _back(t, self._out_device)
 
     def _point(self, temperature, molefracs, pressure, bubble):
-        if self._nc != 2:
-            raise NotImplementedError("bubble / dew points are binary (as the reference's native layer, src/pcsaft.rs:173)")
         _check_rows(self._n, temperature=temperature, molefracs=molefracs, pressure=pressure)
         t = _prep(temperature, self._dev)
         z = _prep(molefracs.detach(), self._dev)
@@ -200,7 +199,7 @@ class PcSaftMix:
             # is recognised by the caller's (T, x) tensor objects in the next iteration of a fit loop
             def compute():
                 o = torch.empty((n,), dtype=torch.int32, device=self._dev)
-                with torch.cuda.device(self._dev):
+                with _on_device(self._dev):
                     _lib.timed_call("feos_dev_mix_point_order", _lib.ptr(params), _lib.ptr(t), _lib.ptr(z), n,
                                     self._flags & SHARED_PARAMS, _lib.ptr(o), _stream())
                 return o

@@ -18,7 +18,27 @@ from . import _lib
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current stream of the current device (torch._C call: the Python wrapper objects of
+    torch.cuda.current_stream cost several microseconds per launch)."""
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+
+
+class _on_device:
+    """`with _on_device(dev):` = torch.cuda.device(dev) that costs nothing when `dev` is already current (the usual
+    case: one process per GPU)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
 
 
 def _cuda_device(t):
@@ -257,9 +277,9 @@ def _upstream(g):
 
 def _state_order(params, temperature, key):
     """Permutation that puts states of the same code path and similar (m, T / T_c) into one warp
-    (csrc/order.cuh), for batches large enough to be throughput-bound; ``None`` = input order.  Not used with
-    chunked host uploads (every chunk is launched on its own rows as soon as it has arrived).  ``key``: the
-    caller's own tensor objects, by which the data set is recognised in the next iteration of a fit loop."""
+    (csrc/order.cuh), for batches large enough to be throughput-bound; ``None`` = input order.  With a chunked
+    host upload every chunk gets its own permutation (`_chunk_order`).  ``key``: the caller's own tensor objects,
+    by which the data set is recognised in the next iteration of a fit loop."""
     n = temperature.shape[0]
     if not _lib.state_order_enabled(n) or _chunks_of(params) is not None:
         return None
@@ -270,8 +290,23 @@ def _state_order(params, temperature, key):
         return o
     # key = (parameter tensor, temperature tensor) of the caller: the temperatures identify the data set (hard), the
     # parameters are "soft" -- an optimizer updates them in place every step, see _lib.cached_order
-    with torch.cuda.device(params.device):
+    with _on_device(params.device):
         return _lib.cached_order(("pure", params.device.index), key[1:], compute, n=n, soft=key[:1])
+
+
+def _chunk_order(params, temperature, key, a, b):
+    """State order of rows [a, b) of a chunked host upload (indices relative to a): computed on the chunk once its
+    rows have arrived (the caller has made the stream wait for the chunk's event) and kept like the whole-batch
+    order -- a fit loop uploads the same pinned tensors every iteration."""
+    n = b - a
+    if key is None or not _lib.state_order_enabled(n):
+        return None
+
+    def compute():
+        o = torch.empty((n,), dtype=torch.int32, device=params.device)
+        _lib.timed_call("feos_dev_pure_order", _off(params, a), _off(temperature, a), n, _lib.ptr(o), _stream())
+        return o
+    return _lib.cached_order(("pure-chunk", params.device.index, a, b), key[1:], compute, n=n, soft=key[:1])
 
 
 class _PureVle(torch.autograd.Function):
@@ -279,22 +314,21 @@ class _PureVle(torch.autograd.Function):
     Returns (compacted values [n_ok], failed [n] uint8, rho [n, 2])."""
 
     @staticmethod
-    def forward(ctx, params, temperature, which, order):
+    def forward(ctx, params, temperature, which, order, key):
         n = temperature.shape[0]
         dev = params.device
         rho = torch.empty((n, 2), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
         ch = _chunks_of(params)
-        with torch.cuda.device(dev):
-            if ch is not None:
-                order = None  # chunked host upload: every chunk is launched on its own rows
-
+        with _on_device(dev):
             def launch(a, b):
+                # chunked host upload: every chunk is launched on its own rows, in its own state order
+                o = order if ch is None else _chunk_order(params, temperature, key, a, b)
                 _lib.timed_call(
                     "feos_dev_pure_vle_fwd", _off(params, a), _off(temperature, a), b - a, _off(rho, a),
                     _off(val, a) if which == 0 else None, _off(val, a) if which == 1 else None,
-                    _off(failed, a), None, _lib.ptr(order), _stream(),
+                    _off(failed, a), None, _lib.ptr(o), _stream(),
                 )
             _launch_chunked(params, zip(ch.bounds, ch.events) if ch else [((0, n), None)], launch)
             out, pos = compact(failed, val)
@@ -310,11 +344,11 @@ class _PureVle(torch.autograd.Function):
         params, temperature, rho, failed, pos = ctx.saved_tensors
         n = temperature.shape[0]
         if g_val is None:  # only the mask / density outputs were used downstream
-            return (None,) * 4
+            return (None,) * 5
         g, bc = _upstream(g_val)
         grad_params = torch.empty_like(params)
         grad_t = torch.empty_like(temperature) if ctx.needs_input_grad[1] else None
-        with torch.cuda.device(params.device):
+        with _on_device(params.device):
             def launch(a, b):
                 _lib.timed_call(
                     "feos_dev_pure_vle_bwd", _off(params, a), _off(temperature, a), _off(rho, a), _off(failed, a),
@@ -327,26 +361,24 @@ class _PureVle(torch.autograd.Function):
                 grad_params._feos_chunks = _Chunks(bounds, events, grad_params._version)
             else:
                 launch(0, n)
-        return grad_params, grad_t, None, None
+        return grad_params, grad_t, None, None, None
 
 
 class _PureRhoTp(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, params, temperature, pressure, order):
+    def forward(ctx, params, temperature, pressure, order, key):
         n = temperature.shape[0]
         dev = params.device
         rho = torch.empty((n,), dtype=torch.float64, device=dev)
         val = torch.empty((n,), dtype=torch.float64, device=dev)
         failed = torch.empty((n,), dtype=torch.uint8, device=dev)
         ch = _chunks_of(params)
-        with torch.cuda.device(dev):
-            if ch is not None:
-                order = None  # chunked host upload: every chunk is launched on its own rows
-
+        with _on_device(dev):
             def launch(a, b):
+                o = order if ch is None else _chunk_order(params, temperature, key, a, b)
                 _lib.timed_call(
                     "feos_dev_pure_rho_tp_fwd", _off(params, a), _off(temperature, a), _off(pressure, a), b - a,
-                    _off(rho, a), _off(val, a), _off(failed, a), None, _lib.ptr(order), _stream(),
+                    _off(rho, a), _off(val, a), _off(failed, a), None, _lib.ptr(o), _stream(),
                 )
             _launch_chunked(params, zip(ch.bounds, ch.events) if ch else [((0, n), None)], launch)
             out, pos = compact(failed, val)
@@ -361,13 +393,13 @@ class _PureRhoTp(torch.autograd.Function):
         params, temperature, pressure, rho, failed, pos = ctx.saved_tensors
         n = temperature.shape[0]
         if g_val is None:  # only the mask / density outputs were used downstream
-            return (None,) * 4
+            return (None,) * 5
         g, bc = _upstream(g_val)
         need_p, need_t, need_pr = ctx.needs_input_grad[:3]
         grad_params = torch.empty_like(params) if need_p else None
         grad_t = torch.empty_like(temperature) if need_t else None
         grad_pr = torch.empty_like(pressure) if need_pr else None
-        with torch.cuda.device(params.device):
+        with _on_device(params.device):
             def launch(a, b):
                 _lib.timed_call(
                     "feos_dev_pure_rho_tp_bwd", _off(params, a), _off(temperature, a), _off(pressure, a),
@@ -380,7 +412,7 @@ class _PureRhoTp(torch.autograd.Function):
                 grad_params._feos_chunks = _Chunks(bounds, events, grad_params._version)
             else:
                 launch(0, n)
-        return grad_params, grad_t, grad_pr, None
+        return grad_params, grad_t, grad_pr, None, None
 
 
 def _grad_or_none(g):
@@ -394,7 +426,7 @@ class _PureState(torch.autograd.Function):
     def forward(ctx, params, temperature, density):
         n = temperature.shape[0]
         a, p, dp = (torch.empty((n,), dtype=torch.float64, device=params.device) for _ in range(3))
-        with torch.cuda.device(params.device):
+        with _on_device(params.device):
             _lib.call("feos_dev_pure_state", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(density), n,
                       _lib.ptr(a), _lib.ptr(p), _lib.ptr(dp), _stream())
         ctx.save_for_backward(params, temperature, density)
@@ -410,7 +442,7 @@ class _PureState(torch.autograd.Function):
         grad_t = torch.empty_like(temperature) if need_t else None
         grad_r = torch.empty_like(density) if need_r else None
         if n:
-            with torch.cuda.device(params.device):
+            with _on_device(params.device):
                 _lib.call("feos_dev_pure_state_bwd", _lib.ptr(params), _lib.ptr(temperature), _lib.ptr(density), n,
                           _lib.ptr(ga), _lib.ptr(gp), _lib.ptr(gdp), _lib.ptr(grad_p), _lib.ptr(grad_t), _lib.ptr(grad_r),
                           _stream())
@@ -467,14 +499,16 @@ class PcSaftPure:
         """(failed mask [N], p_sat [n_ok] in Pa) -- pcsaft_pure.py:201-215."""
         _check_rows(self._n, temperature=temperature)
         t = self._state(temperature)
-        val, failed, _ = _PureVle.apply(self._params, t, 0, _state_order(self._params, t, (self._source, temperature)))
+        key = (self._source, temperature)
+        val, failed, _ = _PureVle.apply(self._params, t, 0, _state_order(self._params, t, key), key)
         return self._back(failed.view(torch.bool)), self._back(val)
 
     def equilibrium_liquid_density(self, temperature):
         """(failed mask [N], rho_L^sat [n_ok] in kmol/m^3) -- pcsaft_pure.py:217-233."""
         _check_rows(self._n, temperature=temperature)
         t = self._state(temperature)
-        val, failed, _ = _PureVle.apply(self._params, t, 1, _state_order(self._params, t, (self._source, temperature)))
+        key = (self._source, temperature)
+        val, failed, _ = _PureVle.apply(self._params, t, 1, _state_order(self._params, t, key), key)
         return self._back(failed.view(torch.bool)), self._back(val)
 
     def liquid_density(self, temperature, pressure):
@@ -482,7 +516,8 @@ class PcSaftPure:
         _check_rows(self._n, temperature=temperature, pressure=pressure)
         t = self._state(temperature)
         p = self._state(pressure)
-        val, failed, _ = _PureRhoTp.apply(self._params, t, p, _state_order(self._params, t, (self._source, temperature)))
+        key = (self._source, temperature)
+        val, failed, _ = _PureRhoTp.apply(self._params, t, p, _state_order(self._params, t, key), key)
         return self._back(failed.view(torch.bool)), self._back(val)
 
     # ---- state functions at given (T, rho), differentiable ---------------
