@@ -130,7 +130,7 @@ class _OrderEntry:
 
 
 def cached_order(kind, tensors, compute, n=None, soft=()):
-    """``compute()`` -> int32 order tensor (or None), memoised on (kind, identity + version of ``tensors``,
+    """``compute(out)`` -> int32 order tensor (written into ``out`` if given, else newly allocated; or None), memoised on (kind, identity + version of ``tensors``,
     ``n``); ``soft`` tensors only age the entry; an entry whose order does not have ``n`` rows is never returned."""
     import weakref
 
@@ -144,16 +144,21 @@ def cached_order(kind, tensors, compute, n=None, soft=()):
             if len(soft) != len(e.soft_seen) or any(r() is not t or v != t._version for (r, v), t in zip(e.soft_seen, soft)):
                 e.soft_seen = tuple((weakref.ref(t), t._version) for t in soft)
                 e.changes += 1
-            if e.changes >= ORDER_REFRESH or (e.order is not None and n is not None and e.order.shape[0] != n):
+            if e.order is not None and n is not None and e.order.shape[0] != n:
                 del _ORDER_CACHE[k]
                 break
+            if e.changes >= ORDER_REFRESH:
+                # recomputed INTO the same tensor (stream-ordered after its last use): a refresh allocates nothing, so
+                # the caching allocator's steady state -- and with it the step time -- is not disturbed
+                e.order = compute(e.order)
+                e.changes = 0
             _ORDER_CACHE.insert(0, _ORDER_CACHE.pop(k))
             return e.order
     e = _OrderEntry()
     e.kind, e.versions, e.n, e.changes = kind, versions, n, 0
     e.refs = tuple(weakref.ref(t) for t in tensors)
     e.soft_seen = tuple((weakref.ref(t), t._version) for t in soft)
-    e.order = compute()
+    e.order = compute(None)
     _ORDER_CACHE.insert(0, e)
     del _ORDER_CACHE[_ORDER_CACHE_SIZE:]
     return e.order

@@ -315,6 +315,7 @@ struct GcBinary {
     return e;
   }
   FD double max_density(double x0) const { return kMaxEta / (x0 * msig3[0] + (1.0 - x0) * msig3[1]); }
+  FD double start_density(double x0) const { return one_fluid_start_density(c, msig3, x0, max_density(x0)); }
 };
 
 FD void gc_binary_init(GcBinary& b, const GcSource& src) {

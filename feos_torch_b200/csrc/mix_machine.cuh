@@ -27,7 +27,8 @@ struct PointMachine {
     bubble = bubble_;
     z0 = z0_;
     x0 = z0_;
-    rho = rho_max = mdl.max_density(x0);
+    rho_max = mdl.max_density(x0);
+    rho = mdl.start_density(x0);
     phase = 0;
     it = 0;
     r = 0;
@@ -77,7 +78,7 @@ struct PointMachine {
       double w0 = e.mu[0] - e.v[0] * e.p, w1 = e.mu[1] - e.v[1] * e.p;
       double r0 = rho * x[0], r1 = rho * x[1];
       double delta = (r0 * exp(w0) + r1 * exp(w1) - e.p) / dps;
-      delta = fmax(delta, -0.3 * rho);
+      delta = fmin(fmax(delta, -0.3 * rho), 1.05 * rho_max - rho);
       rho += delta;
       if (!(fabs(delta) < kStartTol * rho)) return it >= kStartIter ? kStatusRetry : kRunning;
       // the density iteration has converged: point_solve() continues

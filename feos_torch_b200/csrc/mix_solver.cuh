@@ -16,6 +16,7 @@
 // Model must provide:  Eval eval(rho0, rho1) (a, mu[2], h00, h01, h11, p, dp[2], v[2]) and
 //                      double max_density(x0) (total density at packing fraction 0.5).
 #pragma once
+#include "liquid_start.cuh"
 #include "mix_eval_fast.cuh"
 #include "pure_solver.cuh"
 
@@ -124,6 +125,22 @@ FD int point_newton(const Model& mdl, bool bubble, double z0, PointState& st, Mi
   return kStatusRetry;
 }
 
+// Liquid start of composition x (liquid_start.cuh) for non-associating, non-polar mixtures: the pure-fluid correlation
+// with one-fluid values  m = sum x_i m_i,  m sigma^3 = sum x_i m_i sigma_i^3  (= 6/pi sum x_i msig3_i)  and
+// eps / T = sum x_i x_j q1_ij / (m^2 sigma^3)  (q1_ij = m_i m_j eps_ij sigma_ij^3 / T: the van der Waals one-fluid
+// rule on the model's own dispersion coefficients, k_ij included).  Falls back to the packing-fraction-0.5 density.
+template <class Coef>
+FD double one_fluid_start_density(const Coef& c, const double (&msig3)[2], double x0, double rho_max) {
+  if (c.cat != kAssocNone || c.dipolar) return rho_max;
+  const double x1 = 1.0 - x0;
+  const double m = x0 * c.m[0] + x1 * c.m[1];
+  const double ms3 = (6.0 / kPi) * (x0 * msig3[0] + x1 * msig3[1]);
+  const double q = x0 * x0 * c.q1[0] + 2.0 * x0 * x1 * c.q1[1] + x1 * x1 * c.q1[2];
+  if (!(q > 0.0)) return rho_max;
+  const double f = liquid_start_fraction(m * ms3 / q, m);
+  return f > 0.0 ? f * rho_max : rho_max;
+}
+
 // Density iteration of a liquid of composition x towards the pressure of the ideal vapour it would be
 // in equilibrium with; returns ln of the ideal-vapour partial densities (Poynting corrected) in u.
 template <class Model>
@@ -146,7 +163,7 @@ FD int liquid_start(const Model& mdl, double x0, double& rho, double (&u)[2], in
     double w0 = e.mu[0] - e.v[0] * e.p, w1 = e.mu[1] - e.v[1] * e.p;
     double r0 = rho * x[0], r1 = rho * x[1];
     double delta = (r0 * exp(w0) + r1 * exp(w1) - e.p) / dps;
-    delta = fmax(delta, -0.3 * rho);
+    delta = fmin(fmax(delta, -0.3 * rho), 1.05 * rho_max - rho);  // (a start left of the root overshoots once)
     rho += delta;
     if (fabs(delta) < tol * rho) {
       u[0] = log(r0) + w0;
@@ -160,11 +177,12 @@ FD int liquid_start(const Model& mdl, double x0, double& rho, double (&u)[2], in
 // rounds = number of successive-substitution rounds on the liquid composition (dew point only)
 template <class Model>
 FD int point_solve(const Model& mdl, bool bubble, double z0, int ss_rounds, double start_tol, int newton_iter,
-                   double max_step, PointState& st, MixEval& es, MixEval& ei, PointState& st_eval, int& evals) {
+                   double max_step, PointState& st, MixEval& es, MixEval& ei, PointState& st_eval, int& evals,
+                   bool correlated_start = false) {
   if (!(z0 > 0.0) || !(z0 < 1.0)) return kStatusFailed;
   double u[2];
   if (bubble) {
-    double rho = mdl.max_density(z0);
+    double rho = correlated_start ? mdl.start_density(z0) : mdl.max_density(z0);
     int rc = liquid_start(mdl, z0, rho, u, 30, start_tol, evals);
     if (rc != kStatusOk) return rc;
     st.s = log(rho);
@@ -172,7 +190,7 @@ FD int point_solve(const Model& mdl, bool bubble, double z0, int ss_rounds, doub
     st.u[1] = u[1];
   } else {
     double x0 = z0;
-    double rho = mdl.max_density(x0);
+    double rho = correlated_start ? mdl.start_density(x0) : mdl.max_density(x0);
     double p = 0.0;
     for (int r = 0; r <= ss_rounds; ++r) {
       int rc = liquid_start(mdl, x0, rho, u, 30, start_tol, evals);
@@ -200,7 +218,7 @@ FD int point_solve(const Model& mdl, bool bubble, double z0, int ss_rounds, doub
 template <class Model>
 FD int point_fast(const Model& mdl, bool bubble, double z0, PointState& st, MixEval& es, MixEval& ei,
                   PointState& st_eval, int& evals) {
-  return point_solve(mdl, bubble, z0, 2, 0.02, 30, 1.0, st, es, ei, st_eval, evals);
+  return point_solve(mdl, bubble, z0, 2, 0.02, 30, 1.0, st, es, ei, st_eval, evals, true);
 }
 
 // ---- retry path ------------------------------------------------------------------------------------
@@ -376,6 +394,7 @@ struct PcSaftBinary {
     return e;
   }
   FD double max_density(double x0) const { return kMaxEta / (x0 * msig3[0] + (1.0 - x0) * msig3[1]); }
+  FD double start_density(double x0) const { return one_fluid_start_density(c, msig3, x0, max_density(x0)); }
 };
 
 FD void pcsaft_binary_init(PcSaftBinary& b, const double (&prm)[16], const double (&kij)[2], double T) {

@@ -45,6 +45,10 @@ __device__ __forceinline__ void make_coef(const PureRow& r, double T, PureCoef<d
   pure_coef<double>(c, r.v[0], r.v[1], r.v[2], r.v[3], r.v[4], r.v[5], r.v[6], r.v[7], T, false);
   rho_max = kMaxEta / (kPi / 6.0 * r.v[0] * r.v[1] * r.v[1] * r.v[1]);
 }
+// liquid start of the forward solves (liquid_start.cuh)
+__device__ __forceinline__ double start_density(const PureRow& r, double T, const PureCoef<double>& c, double rho_max) {
+  return pure_start_density(c, rho_max, T / r.v[2]);
+}
 
 __device__ __forceinline__ void store_vle(int64_t i, int st, double rho_l, double u, const PureEval& el,
                                           const PureEval& ev, double rle, double rve, double T, double* rho,
@@ -83,7 +87,7 @@ pure_vle_fwd_kernel(const double* __restrict__ params, const double* __restrict_
   int ne = 0;
   // associating states call the out-of-line evaluation (instruction cache), the others inline it (pure_solver.cuh)
   int st = c.assoc ? pure_vle_fast<true>(c, rho_max, rho_l, u, el, ev, rle, rve, ne)
-                   : pure_vle_fast<false>(c, rho_max, rho_l, u, el, ev, rle, rve, ne);
+                   : pure_vle_fast<false>(c, rho_max, rho_l, u, el, ev, rle, rve, ne, start_density(r, T, c, rho_max));
   if (evals) evals[i] = ne;
   if (st == kStatusRetry) {
     int slot = atomicAdd(retry_count, 1);
@@ -149,7 +153,7 @@ pure_vle_queue_kernel(const double* __restrict__ params, const double* __restric
             T = temperature[idx];
             double rho_max;
             make_coef(r, T, c, rho_max);
-            m.start(rho_max);
+            m.start(rho_max, start_density(r, T, c, rho_max));
             ne = 0;
             active = true;
           }
@@ -274,7 +278,8 @@ pure_rho_tp_fwd_kernel(const double* __restrict__ params, const double* __restri
   double x;
   PureEval e;
   int ne = 0;
-  int st = c.assoc ? pure_liquid_density<true>(c, rho_max, p_t, x, e, ne) : pure_liquid_density<false>(c, rho_max, p_t, x, e, ne);
+  int st = c.assoc ? pure_liquid_density<true>(c, rho_max, p_t, x, e, ne)
+                   : pure_liquid_density<false>(c, rho_max, p_t, x, e, ne, start_density(r, T, c, rho_max));
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   double rn = (st == kStatusOk) ? x - (e.p - p_t) / e.dp : nan;  // pcsaft_pure.py:198
   rho[i] = rn;

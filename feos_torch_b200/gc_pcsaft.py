@@ -241,16 +241,16 @@ class GcPcSaftMix:
             # forward: states of one molecule pair and neighbouring (T, x) share a warp (csrc/order.cuh); backward
             # (no iteration): grouped by pair only, input order inside a pair keeps its accesses local.  The data
             # set is recognised by the caller's (T, x) tensor objects in the next iteration of a fit loop.
-            def compute(pair_only):
-                o = torch.empty((n,), dtype=torch.int32, device=self._dev)
+            def compute(pair_only, out):
+                o = out if out is not None else torch.empty((n,), dtype=torch.int32, device=self._dev)
                 with _on_device(self._dev):
                     _lib.timed_call("feos_dev_gc_point_order", _lib.ptr(self._pair_index), self._n_pairs, _lib.ptr(t),
                                     _lib.ptr(z), n, pair_only, _lib.ptr(o), _stream())
                 return o
             key = (self._pair_index, temperature, molefracs)
             dev = self._dev.index
-            orders = (_lib.cached_order(("gc", dev), key, lambda: compute(0), n=n),
-                      _lib.cached_order(("gc-pair", dev), key, lambda: compute(1), n=n))
+            orders = (_lib.cached_order(("gc", dev), key, lambda out: compute(0, out), n=n),
+                      _lib.cached_order(("gc-pair", dev), key, lambda out: compute(1, out), n=n))
         val, failed, _ = _GcPoint.apply(self._seg, self._kab, self._phi, t, z, p0, bubble, tables, orders)
         return self._back(val), self._back(failed.view(torch.bool))
 

@@ -197,8 +197,8 @@ class PcSaftMix:
         if _lib.state_order_enabled(n):
             # states with the same code path and neighbouring (T, x) share a warp (csrc/order.cuh); the data set
             # is recognised by the caller's (T, x) tensor objects in the next iteration of a fit loop
-            def compute():
-                o = torch.empty((n,), dtype=torch.int32, device=self._dev)
+            def compute(out):
+                o = out if out is not None else torch.empty((n,), dtype=torch.int32, device=self._dev)
                 with _on_device(self._dev):
                     _lib.timed_call("feos_dev_mix_point_order", _lib.ptr(params), _lib.ptr(t), _lib.ptr(z), n,
                                     self._flags & SHARED_PARAMS, _lib.ptr(o), _stream())

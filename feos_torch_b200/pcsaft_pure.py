@@ -284,8 +284,8 @@ def _state_order(params, temperature, key):
     if not _lib.state_order_enabled(n) or _chunks_of(params) is not None:
         return None
 
-    def compute():
-        o = torch.empty((n,), dtype=torch.int32, device=params.device)
+    def compute(out):
+        o = out if out is not None else torch.empty((n,), dtype=torch.int32, device=params.device)
         _lib.timed_call("feos_dev_pure_order", _lib.ptr(params), _lib.ptr(temperature), n, _lib.ptr(o), _stream())
         return o
     # key = (parameter tensor, temperature tensor) of the caller: the temperatures identify the data set (hard), the
@@ -302,8 +302,8 @@ def _chunk_order(params, temperature, key, a, b):
     if key is None or not _lib.state_order_enabled(n):
         return None
 
-    def compute():
-        o = torch.empty((n,), dtype=torch.int32, device=params.device)
+    def compute(out):
+        o = out if out is not None else torch.empty((n,), dtype=torch.int32, device=params.device)
         _lib.timed_call("feos_dev_pure_order", _off(params, a), _off(temperature, a), n, _lib.ptr(o), _stream())
         return o
     return _lib.cached_order(("pure-chunk", params.device.index, a, b), key[1:], compute, n=n, soft=key[:1])

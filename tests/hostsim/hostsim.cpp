@@ -14,8 +14,14 @@ static void load_coef(const double* p, double T, PureCoef<double>& c, double& rh
   pure_coef<double>(c, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], T, false);
   rho_max = kMaxEta / (kPi / 6.0 * p[0] * p[1] * p[1] * p[1]);
 }
+static int g_start_corr = 1;  // liquid start correlation (liquid_start.cuh) on / off for A/B tests
+static double start_of(const double* p, double T, const PureCoef<double>& c, double rho_max) {
+  return g_start_corr ? pure_start_density(c, rho_max, T / p[2]) : 0.0;
+}
 
 extern "C" {
+
+void sim_set_start_correlation(int on) { g_start_corr = on; }
 
 void sim_pure_vle(const double* params, const double* T, int64_t n, int use_robust, double* rho, double* vp,
                   double* rleq, uint8_t* status, int32_t* evals) {
@@ -26,7 +32,7 @@ void sim_pure_vle(const double* params, const double* T, int64_t n, int use_robu
     double rl, u, rle, rve;
     PureEval el, ev;
     int ne = 0;
-    int st = pure_vle_fast(c, rho_max, rl, u, el, ev, rle, rve, ne);
+    int st = pure_vle_fast(c, rho_max, rl, u, el, ev, rle, rve, ne, start_of(params + 8 * i, T[i], c, rho_max));
     if (st == kStatusRetry && use_robust) st = pure_vle_robust(c, rho_max, rl, u, el, ev, rle, rve, ne);
     status[i] = (uint8_t)st;
     evals[i] = ne;
@@ -48,7 +54,7 @@ void sim_pure_vle_machine(const double* params, const double* T, int64_t n, doub
     double rho_max;
     load_coef(params + 8 * i, T[i], c, rho_max);
     PureVleMachine m;
-    m.start(rho_max);
+    m.start(rho_max, start_of(params + 8 * i, T[i], c, rho_max));
     int ne = 0, st = kRunning;
     while (st == kRunning) {
       PureEval e = pure_eval(c, m.density());
@@ -125,7 +131,7 @@ void sim_pure_rho_tp(const double* params, const double* T, const double* P, int
     double rho;
     PureEval e;
     int ne = 0;
-    int st = pure_liquid_density(c, rho_max, p_t, rho, e, ne);
+    int st = pure_liquid_density(c, rho_max, p_t, rho, e, ne, start_of(params + 8 * i, T[i], c, rho_max));
     status[i] = (uint8_t)st;
     evals[i] = ne;
     double rn = rho - (e.p - p_t) / e.dp;

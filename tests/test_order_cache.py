@@ -14,7 +14,7 @@ def test_hard_key_identity_and_version():
     T = torch.zeros(8)
     calls = []
 
-    def compute():
+    def compute(out=None):
         calls.append(1)
         return torch.arange(8, dtype=torch.int32)
 
@@ -34,8 +34,8 @@ def test_hard_key_identity_and_version():
 def test_row_count_guard():
     _fresh()
     T = torch.zeros(8)
-    o8 = _lib.cached_order("k", (T,), lambda: torch.arange(8, dtype=torch.int32), n=8)
-    o4 = _lib.cached_order("k", (T,), lambda: torch.arange(4, dtype=torch.int32), n=4)
+    o8 = _lib.cached_order("k", (T,), lambda out: torch.arange(8, dtype=torch.int32), n=8)
+    o4 = _lib.cached_order("k", (T,), lambda out: torch.arange(4, dtype=torch.int32), n=4)
     assert o8.shape[0] == 8 and o4.shape[0] == 4
 
 
@@ -46,7 +46,7 @@ def test_soft_tensors_age_the_entry(monkeypatch):
     T, P = torch.zeros(8), torch.zeros(8, 8)
     calls = []
 
-    def compute():
+    def compute(out=None):
         calls.append(1)
         return torch.arange(8, dtype=torch.int32)
 
