@@ -34,8 +34,8 @@ FD void horner7_2(const double (&k)[7], double x, double& v, double& d1, double&
   d2 *= 2.0;
 }
 
-template <int NB, bool GC>
-FD BaseH2 mix_base_eval(const MixCoef<double, NB, GC>& c, double r0, double r1) {
+template <int NB, class Coef>
+FD BaseH2 mix_base_eval_impl(const Coef& c, double r0, double r1) {
   const double z00 = c.z[0][0], z01 = c.z[0][1], z10 = c.z[1][0], z11 = c.z[1][1];
   const double z20 = c.z[2][0], z21 = c.z[2][1], z30 = c.z[3][0], z31 = c.z[3][1];
   const double zt0 = r0 * z00 + r1 * z01, zt1 = r0 * z10 + r1 * z11, zt2 = r0 * z20 + r1 * z21;
@@ -186,6 +186,11 @@ FD BaseH2 mix_base_eval(const MixCoef<double, NB, GC>& c, double r0, double r1) 
   return o;
 }
 
+template <int NB, bool GC>
+FD BaseH2 mix_base_eval(const MixCoef<double, NB, GC>& c, double r0, double r1) {
+  return mix_base_eval_impl<NB>(c, r0, r1);
+}
+
 // Gross-Vrabec dipole term a = phi2^2 / (phi2 - phi3) in closed form (value, gradient, Hessian), added to `o`:
 //   phi2 = -pi sum_k tau_k(rho) ps_k J2_k(eta),  phi3 = -4/3 pi^2 sum_t tautau_t(rho) ts_t J3_t(eta)
 // with tau = (t0^2, t0 t1, t1^2), tautau = (t0^3, t0^2 t1, t1^2 t0, t1^3), t_i = rho_i mu2t_i and the pair /
@@ -295,6 +300,14 @@ FD MixEval mix_eval(const MixCoef<double, NB, GC>& c, double rho0, double rho1) 
     r1.g1 = 1.0;
     a = a + mix_helmholtz<double, H2<double>, NB, GC, 4>(c, r0, r1);
   }
+  return mix_eval_from(a, rho0, rho1);
+}
+
+// plain pairs (MixCoefBase): the base part is the whole evaluation
+FD MixEval mix_eval(const MixCoefBase& c, double rho0, double rho1) {
+  BaseH2 b = mix_base_eval_impl<2>(c, rho0, rho1);
+  H2<double> a;
+  a.re = b.a; a.g0 = b.g0; a.g1 = b.g1; a.h00 = b.h00; a.h01 = b.h01; a.h11 = b.h11;
   return mix_eval_from(a, rho0, rho1);
 }
 

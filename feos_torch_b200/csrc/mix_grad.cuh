@@ -233,6 +233,59 @@ FD_NOINLINE void mix_base_coef_adjoint(const MixCoef<double, NB, GC>& c, const d
   cbar[15] = point_comb(pi.q2 * (i1 * i1), ps.q2 * r11, q);
 }
 
+// ---- k_ij alone --------------------------------------------------------------------------------------------
+// A k_ij fit (BASELINE config C4) asks for d p / d k_ij only.  k_ij enters the Helmholtz energy through the cross
+// dispersion coefficients q1[01], q2[01] alone (pcsaft_mix.py:69-90: eps_ij (1 - k_ij)) -- for EVERY pair, polar and
+// associating ones included -- so the gradient needs the two partials
+//     d a / d Q1 = -2 pi I1(eta, mbar),   d a / d Q2 = -pi mbar C1(eta, mbar) I2(eta, mbar)
+// at the incipient densities (double) and with the density direction of the specified phase (D1), instead of the
+// whole coefficient adjoint + reverse sweep.
+template <class R, class C>
+FD void disp_q_partials(const C& c, const R& rho0, const R& rho1, R& pq1, R& pq2) {
+  R z3 = rho0 * c.z[3][0] + rho1 * c.z[3][1];
+  R mbar = (rho0 * c.m[0] + rho1 * c.m[1]) * ad_recip(rho0 + rho1);
+  R mi = ad_recip(mbar);
+  R w1 = 1.0 - mi;
+  R w2 = w1 * (1.0 - 2.0 * mi);
+  R s0, s1, s2, d0, d1, d2;
+  horner7(cA0, z3, s0, d0);
+  horner7(cA1, z3, s1, d1);
+  horner7(cA2, z3, s2, d2);
+  pq1 = (-2.0 * kPi) * (s0 + w1 * s1 + w2 * s2);
+  horner7(cB0, z3, s0, d0);
+  horner7(cB1, z3, s1, d1);
+  horner7(cB2, z3, s2, d2);
+  R i2 = s0 + w1 * s1 + w2 * s2;
+  R e2 = z3 * z3, e3 = e2 * z3;
+  R omi = ad_recip(1.0 - z3), tmi = ad_recip(2.0 - z3);
+  R omi2 = omi * omi;
+  R X = (8.0 * z3 - 2.0 * e2) * (omi2 * omi2);
+  R Y = (20.0 * z3 - 27.0 * e2 + 12.0 * e3 - 2.0 * (e2 * e2)) * (omi2 * (tmi * tmi));
+  R c1 = ad_recip(1.0 + mbar * X + (1.0 - mbar) * Y);
+  pq2 = (-kPi) * ((c1 * i2) * mbar);
+}
+
+// g * d(p_bubble/dew [Pa]) / d k_ij of any binary; `q` = point_weights of the specified phase's full evaluation
+template <class C>
+FD double mix_point_grad_kij(const double (&prm)[16], double kij0, double T, const C& c, const double (&spec)[2],
+                             const double (&inc)[2], const PointWeights& q, double g) {
+  double iq1, iq2;
+  D1 sq1, sq2;
+  disp_q_partials<double>(c, inc[0], inc[1], iq1, iq2);
+  const D1 s0(spec[0], q.dir[0]), s1(spec[1], q.dir[1]);
+  disp_q_partials<D1>(c, s0, s1, sq1, sq2);
+  const D1 r01 = 2.0 * (s0 * s1);
+  const double i01 = 2.0 * inc[0] * inc[1];
+  const double cb1 = point_comb(iq1 * i01, sq1 * r01, q);  // d p_red / d q1[01]
+  const double cb2 = point_comb(iq2 * i01, sq2 * r01, q);  // d p_red / d q2[01]
+  // q1[01] = m0 m1 sqrt(eps0 eps1)/T (1 - k) s01^3, q2[01] = q1[01] sqrt(eps0 eps1)/T (1 - k)
+  const double ti = 1.0 / T;
+  const double s01 = 0.5 * (prm[1] + prm[9]);
+  const double e = sqrt(prm[2] * prm[10]) * ti;
+  const double base = prm[0] * prm[8] * e * (s01 * s01 * s01);  // - d q1[01] / d k
+  return -(base * (cb1 + cb2 * (2.0 * e * (1.0 - kij0)))) * (g * T * kPaPerRed);
+}
+
 // ---- closed-form coefficient adjoints of the Gross-Vrabec dipole term -------------------------------
 //   a_dip = phi2^2 / (phi2 - phi3),
 //   phi2 = -pi sum_k tt_k J2_k ps_k,            J2_k = PA0 + pw1_k PA1 + pw2_k PA2 + pe_k (PB0 + pw1_k PB1 + pw2_k PB2)

@@ -10,6 +10,7 @@
 //   mix_state_kernel         a, p, mu_i, v_i at given (T, rho_1, rho_2)  (PcSaftMix.derivatives).
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "../../include/feos_b200.h"
 #include "common.h"
@@ -23,13 +24,19 @@ constexpr int kMixBlock = 128;
 // The (parameters, k_ij, T)-only coefficients of a state (~70 doubles) live in SHARED memory, one slot
 // per thread, so that the registers hold only the hyper-dual working set of the evaluation.  The slot
 // stride is an odd number of 8-byte words: thread t touches word (stride * t + field), conflict-free.
-constexpr int kModelWords = (sizeof(PcSaftBinary) + 7) / 8;
-constexpr int kModelStride = kModelWords | 1;
-constexpr size_t kMixSmem = sizeof(double) * kModelStride * kMixBlock;
+template <class Model>
+struct ModelSlot {
+  static constexpr int kWords = (sizeof(Model) + 7) / 8;
+  static constexpr int kStride = kWords | 1;
+  static constexpr size_t kSmem = sizeof(double) * kStride * kMixBlock;
+  static __device__ __forceinline__ Model& get(double* smem) {
+    return *reinterpret_cast<Model*>(smem + (size_t)kStride * threadIdx.x);
+  }
+};
+constexpr size_t kMixSmem = ModelSlot<PcSaftBinary>::kSmem;
+constexpr size_t kMixPlainSmem = ModelSlot<PcSaftBinaryPlain>::kSmem;
 
-__device__ __forceinline__ PcSaftBinary& model_slot(double* smem) {
-  return *reinterpret_cast<PcSaftBinary*>(smem + (size_t)kModelStride * threadIdx.x);
-}
+__device__ __forceinline__ PcSaftBinary& model_slot(double* smem) { return ModelSlot<PcSaftBinary>::get(smem); }
 
 // flags of the bubble / dew entry points: the parameter rows / the k_ij row are ONE row shared by all states
 // (a fit of shared parameters: `pair.expand(n, 2, 8)`, `kij.expand(n, 2)` in the reference's API)
@@ -76,33 +83,52 @@ __device__ __forceinline__ void store_point(int64_t i, int rc, bool bubble, doub
 #ifndef FEOS_MIX_FWD_MINB
 #define FEOS_MIX_FWD_MINB 2
 #endif
-__global__ void __launch_bounds__(kMixBlock, FEOS_MIX_FWD_MINB)
+#ifndef FEOS_MIX_PLAIN_MINB
+#define FEOS_MIX_PLAIN_MINB 3
+#endif
+// Two instantiations share the work by the CLASS of a state's parameter pair (mix_is_plain): PLAIN = hard sphere +
+// hard chain + dispersion only, the other one every pair with a dipole or association term.  Each skips the states
+// of the other class (the state order puts the classes into separate blocks); the plain one raises `other_class`
+// when it meets such a state, and the blocks of the general one leave at once while that flag is down.
+template <bool PLAIN>
+__global__ void __launch_bounds__(kMixBlock, PLAIN ? FEOS_MIX_PLAIN_MINB : FEOS_MIX_FWD_MINB)
 mix_point_fwd_kernel(const double* __restrict__ params, const double* __restrict__ kij,
                      const double* __restrict__ temperature, const double* __restrict__ molefrac, int64_t n, int bubble,
                      int flags, double* __restrict__ rho, double* __restrict__ value, uint8_t* __restrict__ failed,
                      int32_t* __restrict__ evals, int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count,
-                     const int32_t* __restrict__ order) {
+                     const int32_t* __restrict__ order, int32_t* __restrict__ other_class) {
+  using Model = typename std::conditional<PLAIN, PcSaftBinaryPlain, PcSaftBinary>::type;
   extern __shared__ double smem[];
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (order) i = order[i];  // states of similar (T, x) and code path share a warp (order.cuh)
-  double T = temperature[i], z0 = molefrac[i];
-  PcSaftBinary& b = model_slot(smem);
-  {
-    double prm[16], kk[2];
-    load_mix(params, kij, i, flags, prm, kk);
-    pcsaft_binary_init(b, prm, kk, T);
+  if (!PLAIN && *reinterpret_cast<volatile int32_t*>(other_class) == 0) return;
+  Model& b = ModelSlot<Model>::get(smem);
+  // the plain instantiation is launched with one block per tile of kMixBlock states; the general one with a grid of
+  // resident blocks that walk the tiles (so that its launch costs nothing when there is no such state)
+#pragma unroll 1
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = order ? (int64_t)order[t] : t;  // states of similar (T, x) and code path share a warp (order.cuh)
+    double T, z0;
+    {
+      double prm[16], kk[2];
+      load_mix(params, kij, i, flags, prm, kk);
+      if (mix_is_plain(prm) != PLAIN) {
+        if (PLAIN) *other_class = 1;
+        continue;
+      }
+      T = temperature[i];
+      z0 = molefrac[i];
+      pcsaft_binary_init(b, prm, kk, T);
+    }
+    PointState st, se;
+    MixEval es, ei;
+    int ne = 0;
+    int rc = point_fast(b, bubble != 0, z0, st, es, ei, se, ne);
+    if (evals) evals[i] = ne;
+    if (rc == kStatusRetry) {
+      retry_list[atomicAdd(retry_count, 1)] = (int32_t)i;
+      continue;
+    }
+    store_point<Model>(i, rc, bubble != 0, z0, T, st, se, es, ei, rho, value, failed);
   }
-  PointState st, se;
-  MixEval es, ei;
-  int ne = 0;
-  int rc = point_fast(b, bubble != 0, z0, st, es, ei, se, ne);
-  if (evals) evals[i] = ne;
-  if (rc == kStatusRetry) {
-    retry_list[atomicAdd(retry_count, 1)] = (int32_t)i;
-    return;
-  }
-  store_point<PcSaftBinary>(i, rc, bubble != 0, z0, T, st, se, es, ei, rho, value, failed);
 }
 
 // Persistent work-queue variant (point_queue.cuh): same solver as mix_point_fwd_kernel, cut into
@@ -290,6 +316,73 @@ mix_point_bwd_kernel(const double* __restrict__ params, const double* __restrict
   }
 }
 
+// d p / d (k_ij, eps_AiBj) alone (a k_ij fit, BASELINE config C4): closed form for k_ij (mix_point_grad_kij: one
+// evaluation of the specified phase for the weights + the two dispersion partials), a dual pass for eps_AiBj only
+// where it exists (cross-associating pairs with kij[:, 1] != 0).  Same class split as the forward kernel.
+#ifndef FEOS_MIX_BWDK_MINB
+#define FEOS_MIX_BWDK_MINB 3
+#endif
+template <bool PLAIN>
+__global__ void __launch_bounds__(kMixBlock, PLAIN ? FEOS_MIX_BWDK_MINB : 2)
+mix_point_bwd_kij_kernel(const double* __restrict__ params, const double* __restrict__ kij,
+                         const double* __restrict__ temperature, const double* __restrict__ rho,
+                         const uint8_t* __restrict__ failed, const int32_t* __restrict__ pos, const double* __restrict__ g,
+                         int g_broadcast, int64_t n, int bubble, int flags, double* __restrict__ grad_kij,
+                         const int32_t* __restrict__ order, int32_t* __restrict__ other_class) {
+  using Model = typename std::conditional<PLAIN, PcSaftBinaryPlain, PcSaftBinary>::type;
+  __shared__ double acc[2];
+  if (!PLAIN && *reinterpret_cast<volatile int32_t*>(other_class) == 0) return;
+  const bool sh_k = (flags & kSharedKij) != 0;
+  if (sh_k) {
+    if (threadIdx.x < 2) acc[threadIdx.x] = 0.0;
+    __syncthreads();
+  }
+  double s16 = 0.0, s17 = 0.0;  // sums over this thread's states (shared k_ij row)
+  // plain: one block per tile; general: resident blocks walking the tiles (see mix_point_fwd_kernel)
+#pragma unroll 1
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = order ? (int64_t)order[t] : t;
+    double prm[16], kk[2];
+    load_mix(params, kij, i, flags, prm, kk);
+    if (mix_is_plain(prm) != PLAIN) {
+      if (PLAIN) *other_class = 1;
+      continue;
+    }
+    double o16 = 0.0, o17 = 0.0;
+    if (!failed[i]) {
+      double T = temperature[i];
+      const double2* rp = reinterpret_cast<const double2*>(rho + 4 * i);
+      double2 rv = rp[0], rl = rp[1];
+      double spec[2], inc[2];
+      if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
+      else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
+      double gi = g[g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i)];
+      Model b;
+      pcsaft_binary_init(b, prm, kk, T);
+      PointWeights q = point_weights(b.eval(spec[0], spec[1]), spec, inc);
+      o16 = mix_point_grad_kij(prm, kk[0], T, b.c, spec, inc, q, gi);
+      if (!PLAIN && b.c.cat == kAssocCross && kk[1] != 0.0) {
+        const int dirs[1] = {17};
+        double g1[1];
+        mix_point_grad_pass<1>(prm, kk, T, spec, inc, q, dirs, gi, g1);
+        o17 = g1[0];
+      }
+    }
+    if (sh_k) {
+      s16 += o16;
+      s17 += o17;
+    } else {
+      reinterpret_cast<double2*>(grad_kij)[i] = make_double2(o16, o17);
+    }
+  }
+  if (sh_k) {
+    warp_sum_to(s16, acc);
+    if (!PLAIN) warp_sum_to(s17, acc + 1);
+    __syncthreads();
+    if (threadIdx.x < 2 && acc[threadIdx.x] != 0.0) atomicAdd(grad_kij + threadIdx.x, acc[threadIdx.x]);
+  }
+}
+
 __global__ void __launch_bounds__(kMixBlock)
 mix_state_kernel(const double* __restrict__ params, const double* __restrict__ kij,
                  const double* __restrict__ temperature, const double* __restrict__ density, int64_t n,
@@ -313,6 +406,11 @@ mix_state_kernel(const double* __restrict__ params, const double* __restrict__ k
 using namespace feos;
 
 namespace {
+// grid of the general-class instantiations: a few blocks per resident slot, each walking its share of the tiles
+int general_grid(int64_t n, int resident_blocks) {
+  return (int)std::min<int64_t>((n + kMixBlock - 1) / kMixBlock, 4 * (int64_t)std::max(resident_blocks, 1));
+}
+
 int host_point(const double* params, const double* kij, const double* temperature, const double* molefracs,
                const double* pressure, int64_t n, int bubble, double* rho_out, uint8_t* status, int64_t* n_ok) {
   clear_error();
@@ -353,15 +451,15 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && molefracs && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
-  Scratch scratch;  // [0] = retry counter, [1] = queue head, [2 ..] = retry list
-  if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  Scratch scratch;  // [0] = retry counter, [1] = queue head, [2] = "states of the general class present", [4 ..] = retry list
+  if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)(n + 4), s)) return rc_;
   int32_t* ws = scratch.as<int32_t>();
-  FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
+  FEOS_CUDA(cudaMemsetAsync(ws, 0, 4 * sizeof(int32_t), s));
   // opt-in to > 48 KB of dynamic shared memory and the persistent grid size: once per DEVICE
   static PerDevice cache;
   int blocks = 0;
   if (int rc_ = cache.get([](int dev, int* v) {
-        FEOS_CUDA(cudaFuncSetAttribute(mix_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem));
+        FEOS_CUDA(cudaFuncSetAttribute(mix_point_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem));
         FEOS_CUDA(cudaFuncSetAttribute(mix_point_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMixSmem));
         int sms = 0, per_sm = 0;
         FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -373,17 +471,20 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   // default = one thread per state; FEOS_B200_POINT_KERNEL=queue selects the persistent work-queue kernel
   static const int variant = point_kernel_variant();
   if (variant == 0 || n < 65536) {
-    mix_point_fwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, kMixSmem, s>>>(
-        params, kij, temperature, molefracs, n, bubble, flags, rho, pressure, failed, evals, ws + 2, ws, order);
+    mix_point_fwd_kernel<true><<<grid_for(n, kMixBlock), kMixBlock, kMixPlainSmem, s>>>(
+        params, kij, temperature, molefracs, n, bubble, flags, rho, pressure, failed, evals, ws + 4, ws, order, ws + 2);
+    FEOS_LAUNCH_OK();
+    mix_point_fwd_kernel<false><<<general_grid(n, blocks), kMixBlock, kMixSmem, s>>>(
+        params, kij, temperature, molefracs, n, bubble, flags, rho, pressure, failed, evals, ws + 4, ws, order, ws + 2);
   } else {
     MixQueueSource src{params, kij, temperature, molefracs, rho, pressure, failed, flags};
     int grid = (int)std::min<int64_t>(blocks, (n + kMixBlock - 1) / kMixBlock);
-    mix_point_queue_kernel<<<grid, kMixBlock, kMixSmem, s>>>(src, (int)n, bubble, evals, ws + 2, ws, ws + 1);
+    mix_point_queue_kernel<<<grid, kMixBlock, kMixSmem, s>>>(src, (int)n, bubble, evals, ws + 4, ws, ws + 1);
   }
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
   mix_point_retry_kernel<<<retry_grid, 64, 0, s>>>(params, kij, temperature, molefracs, start_pressure, bubble, flags, rho,
-                                                  pressure, failed, evals, ws + 2, ws);
+                                                  pressure, failed, evals, ws + 4, ws);
   FEOS_LAUNCH_OK();
   return 0;
 }
@@ -396,6 +497,24 @@ int feos_dev_mix_point_bwd(const double* params, const double* kij, const double
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
   FEOS_ARG(params && kij && temperature && rho && failed && g);
+  if (grad_kij && !grad_params && !grad_temperature) {
+    cudaStream_t s = (cudaStream_t)stream;
+    Scratch scratch;  // "states of the general class present"
+    if (int rc_ = scratch.alloc(sizeof(int32_t), s)) return rc_;
+    FEOS_CUDA(cudaMemsetAsync(scratch.p, 0, sizeof(int32_t), s));
+    mix_point_bwd_kij_kernel<true><<<grid_for(n, kMixBlock), kMixBlock, 0, s>>>(
+        params, kij, temperature, rho, failed, pos, g, g_broadcast, n, bubble, flags, grad_kij, order, scratch.as<int32_t>());
+    FEOS_LAUNCH_OK();
+    int sms = 148;
+    {
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    mix_point_bwd_kij_kernel<false><<<general_grid(n, 2 * sms), kMixBlock, 0, s>>>(
+        params, kij, temperature, rho, failed, pos, g, g_broadcast, n, bubble, flags, grad_kij, order, scratch.as<int32_t>());
+    FEOS_LAUNCH_OK();
+    return 0;
+  }
   mix_point_bwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, (cudaStream_t)stream>>>(
       params, kij, temperature, rho, failed, pos, g, g_broadcast, n, bubble, flags, grad_params, grad_kij, grad_temperature,
       order);

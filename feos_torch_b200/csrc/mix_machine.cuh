@@ -18,7 +18,7 @@ struct PointMachine {
   MixEval es, ei;
   double dx[3];
   double spec[2], inc[2], rs;  // densities of the Newton iterate being evaluated
-  double x0, rho, rho_max, z0;
+  double x0, rho, rho_max, z0, p_start;
   int phase;  // 0 liquid start, 1 specified-phase evaluation, 2 incipient-phase evaluation
   int it, r, ss_rounds, halvings;
   bool bubble, have_prev;
@@ -32,6 +32,7 @@ struct PointMachine {
     phase = 0;
     it = 0;
     r = 0;
+    p_start = 0.0;
     ss_rounds = bubble_ ? 0 : kSsRounds;
   }
   FD void density(double& r0, double& r1) const {
@@ -64,6 +65,36 @@ struct PointMachine {
   }
 
   FD int advance(const Model& mdl, const MixEval& e) {
+    if (phase == 0 && !bubble && kDewSimultaneous) {  // one round of the simultaneous dew start of point_solve()
+      ++r;
+      bool last = r >= kDewRounds;
+      bool done = false;
+      double dps = x0 * e.dp[0] + (1.0 - x0) * e.dp[1];
+      if (!(dps > 0.0)) {
+        if (!(rho < 0.999 * rho_max)) return kStatusRetry;
+        rho = rho_max;
+      } else {
+        double k0 = rho * exp(e.mu[0] - e.v[0] * e.p), k1 = rho * exp(e.mu[1] - e.v[1] * e.p);
+        double delta = (x0 * k0 + (1.0 - x0) * k1 - e.p) / dps;
+        delta = fmin(fmax(delta, -0.3 * rho), 1.05 * rho_max - rho);
+        double t0 = z0 / k0, t1 = (1.0 - z0) / k1;
+        p_start = 1.0 / (t0 + t1);
+        double xn = t0 * p_start;
+        if (!(xn > 0.0) || !(xn < 1.0)) return kStatusRetry;
+        done = fabs(delta) < kStartTol * rho && fabs(xn - x0) < kDewXTol * fmin(xn, 1.0 - xn);
+        double mx_n = mdl.max_density(xn);
+        rho = (rho + delta) * mx_n / rho_max;
+        x0 = xn;
+        rho_max = mx_n;
+      }
+      if (!done && !last) return kRunning;
+      if (!(p_start > 0.0)) return kStatusRetry;
+      st.s = log(p_start);
+      st.u[0] = log(rho * x0);
+      st.u[1] = log(rho * (1.0 - x0));
+      begin_newton();
+      return kRunning;
+    }
     if (phase == 0) {  // liquid_start(), one iteration
       const double x[2] = {x0, 1.0 - x0};
       ++it;

@@ -22,6 +22,18 @@
 
 namespace feos {
 
+#ifndef FEOS_DEW_SIM
+#define FEOS_DEW_SIM 1
+#endif
+#ifndef FEOS_DEW_ROUNDS
+#define FEOS_DEW_ROUNDS 4
+#endif
+#ifndef FEOS_DEW_XTOL
+#define FEOS_DEW_XTOL 1e-2
+#endif
+constexpr bool kDewSimultaneous = FEOS_DEW_SIM;
+constexpr int kDewRounds = FEOS_DEW_ROUNDS;
+constexpr double kDewXTol = FEOS_DEW_XTOL;
 constexpr double kDefaultStartPressure = 1e5;  // Pa: start pressure when the caller gives none (the value of the reference's tests)
 
 struct PointState {
@@ -188,6 +200,41 @@ FD int point_solve(const Model& mdl, bool bubble, double z0, int ss_rounds, doub
     st.s = log(rho);
     st.u[0] = u[0];
     st.u[1] = u[1];
+  } else if (correlated_start && kDewSimultaneous) {
+    // fast path: liquid composition and density move TOGETHER, one evaluation per round.  w_i = mu_i - v_i p is
+    // first-order insensitive to the density error (d mu_i / d rho = v_i d p / d rho along the composition line), so the
+    // K-factors of a liquid that is a Newton step or two from its density are as good as those of the converged one.
+    double x0 = z0;
+    double rho = mdl.start_density(x0);
+    double p = 0.0;
+    bool ok = false;
+    for (int r = 0; r < kDewRounds; ++r) {
+      const double rho_max = mdl.max_density(x0);
+      MixEval e = mdl.eval(rho * x0, rho * (1.0 - x0));
+      evals += 1;
+      double dps = x0 * e.dp[0] + (1.0 - x0) * e.dp[1];
+      if (!(dps > 0.0)) {
+        if (rho < 0.999 * rho_max) { rho = rho_max; continue; }
+        return kStatusRetry;
+      }
+      double k0 = rho * exp(e.mu[0] - e.v[0] * e.p), k1 = rho * exp(e.mu[1] - e.v[1] * e.p);  // kappa_i = p y_i / x_i
+      double delta = (x0 * k0 + (1.0 - x0) * k1 - e.p) / dps;
+      delta = fmin(fmax(delta, -0.3 * rho), 1.05 * rho_max - rho);
+      double t0 = z0 / k0, t1 = (1.0 - z0) / k1;
+      p = 1.0 / (t0 + t1);
+      double xn = t0 * p;
+      if (!(xn > 0.0) || !(xn < 1.0)) return kStatusRetry;
+      bool done = fabs(delta) < start_tol * rho && fabs(xn - x0) < kDewXTol * fmin(xn, 1.0 - xn);
+      // next point: the Newton-updated packing fraction at the new composition
+      rho = (rho + delta) * mdl.max_density(xn) / rho_max;
+      x0 = xn;
+      if (done) { ok = true; break; }
+    }
+    (void)ok;
+    if (!(p > 0.0)) return kStatusRetry;
+    st.s = log(p);
+    st.u[0] = log(rho * x0);
+    st.u[1] = log(rho * (1.0 - x0));
   } else {
     double x0 = z0;
     double rho = correlated_start ? mdl.start_density(x0) : mdl.max_density(x0);
@@ -399,6 +446,30 @@ struct PcSaftBinary {
 
 FD void pcsaft_binary_init(PcSaftBinary& b, const double (&prm)[16], const double (&kij)[2], double T) {
   mix_coef<double>(b.c, prm, kij, T, false);
+  b.msig3[0] = kPi / 6.0 * prm[0] * prm[1] * prm[1] * prm[1];
+  b.msig3[1] = kPi / 6.0 * prm[8] * prm[9] * prm[9] * prm[9];
+}
+
+// The same Model for PLAIN pairs (mix_is_plain: no dipole, no association term): 26 doubles per state instead of 73
+// and an evaluation without the hyper-dual association code -- the kernels instantiated with it need a third fewer
+// registers (3 instead of 2 resident blocks per SM) and a third of the instruction-cache footprint.
+FD_NOINLINE void pcsaft_plain_eval(const MixCoefBase& c, double r0, double r1, MixEval& e) { e = mix_eval(c, r0, r1); }
+
+struct PcSaftBinaryPlain {
+  MixCoefBase c;
+  double msig3[2];
+  FD MixEval eval(double r0, double r1) const {
+    MixEval e;
+    pcsaft_plain_eval(c, r0, r1, e);
+    return e;
+  }
+  FD double max_density(double x0) const { return kMaxEta / (x0 * msig3[0] + (1.0 - x0) * msig3[1]); }
+  FD double start_density(double x0) const { return one_fluid_start_density(c, msig3, x0, max_density(x0)); }
+};
+
+FD void pcsaft_binary_init(PcSaftBinaryPlain& b, const double (&prm)[16], const double (&kij)[2], double T) {
+  double s3[2], eps[2], sig[2], dseg[2];
+  mix_coef_base(b.c, prm, kij, 1.0 / T, s3, eps, sig, dseg);
   b.msig3[0] = kPi / 6.0 * prm[0] * prm[1] * prm[1] * prm[1];
   b.msig3[1] = kPi / 6.0 * prm[8] * prm[9] * prm[9] * prm[9];
 }

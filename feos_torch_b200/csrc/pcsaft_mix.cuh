@@ -96,12 +96,38 @@ FD void dipole_coef(C& c, const P (&m)[2], const P (&sig)[2], const P (&eps)[2],
   }
 }
 
-// prm: 16 values = 2 rows of [m, sigma, eps, mu, kappa_ab, eps_ab, na, nb]; kij = (k_ij, eps_AiBj)
-template <class P>
-FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& T, bool grad_mode) {
-  P ti = ad_recip(T);
-  P s3[2], eps[2], sig[2], dseg[2];
-  c.nbond = 2;
+// Association category of a parameter pair (pcsaft_mix.py:118-152), from the site counts alone
+FD int mix_category(double na0, double nb0, double na1, double nb1) {
+  int n_assoc = ((na0 + nb0) != 0.0) + ((na1 + nb1) != 0.0);
+  int n_self = ((na0 * nb0) != 0.0) + ((na1 * nb1) != 0.0);
+  if (n_assoc == 1 && n_self == 1) return kAssocSelf;
+  if (n_assoc == 2 && n_self == 2) return kAssocCross;
+  if (n_assoc == 2 && n_self == 1) return kAssocInduced;
+  return kAssocNone;
+}
+
+// "plain" pair: hard sphere + hard chain + dispersion only (no dipole term, no association term)
+FD bool mix_is_plain(const double (&prm)[16]) {
+  return prm[3] == 0.0 && prm[11] == 0.0 && mix_category(prm[6], prm[7], prm[14], prm[15]) == kAssocNone;
+}
+
+// The coefficients of the base part alone (24 doubles): what the kernels specialised for plain pairs keep per state.
+// Same member names as MixCoef, so that mix_base_eval and the solvers take either.
+struct MixCoefBase {
+  double z[4][2];
+  double m[2];
+  double cd[2];
+  double bn[2][2];
+  double q1[3], q2[3];
+  static constexpr int nbond = 2;
+  static constexpr int cat = kAssocNone;
+  static constexpr bool dipolar = false;
+};
+
+// hard-sphere, hard-chain and dispersion coefficients (pcsaft_mix.py:31-33, :56-90); returns sigma, eps, d per component
+template <class C, class P>
+FD void mix_coef_base(C& c, const P (&prm)[16], const P (&kij)[2], const P& ti, P (&s3)[2], P (&eps)[2], P (&sig)[2],
+                      P (&dseg)[2]) {
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     P m = prm[8 * i], s = prm[8 * i + 1], e = prm[8 * i + 2];
@@ -134,6 +160,15 @@ FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& 
     c.q2[1] = c.q1[1] * e01;
     c.q2[2] = c.q1[2] * e11;
   }
+}
+
+// prm: 16 values = 2 rows of [m, sigma, eps, mu, kappa_ab, eps_ab, na, nb]; kij = (k_ij, eps_AiBj)
+template <class P>
+FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& T, bool grad_mode) {
+  P ti = ad_recip(T);
+  P s3[2], eps[2], sig[2], dseg[2];
+  c.nbond = 2;
+  mix_coef_base(c, prm, kij, ti, s3, eps, sig, dseg);
   // dipole (:111-115, :156-208)
   {
     P mu2t[2];
@@ -148,13 +183,7 @@ FD void mix_coef(MixCoef<P>& c, const P (&prm)[16], const P (&kij)[2], const P& 
   }
   // association categories (:118-152)
   {
-    double na0 = ad_primal(prm[6]), nb0 = ad_primal(prm[7]), na1 = ad_primal(prm[14]), nb1 = ad_primal(prm[15]);
-    int n_assoc = ((na0 + nb0) != 0.0) + ((na1 + nb1) != 0.0);
-    int n_self = ((na0 * nb0) != 0.0) + ((na1 * nb1) != 0.0);
-    c.cat = kAssocNone;
-    if (n_assoc == 1 && n_self == 1) c.cat = kAssocSelf;
-    if (n_assoc == 2 && n_self == 2) c.cat = kAssocCross;
-    if (n_assoc == 2 && n_self == 1) c.cat = kAssocInduced;
+    c.cat = mix_category(ad_primal(prm[6]), ad_primal(prm[7]), ad_primal(prm[14]), ad_primal(prm[15]));
     c.na[0] = prm[6];
     c.nb[0] = prm[7];
     c.na[1] = prm[14];

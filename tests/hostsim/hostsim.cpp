@@ -263,6 +263,57 @@ void sim_mix_point_bwd(const double* params, const double* kij, const double* T,
     }
   }
 }
+
+// k_ij-only gradient (mix_point_bwd_kij_kernel): closed form for k_ij; plain pairs through the plain model
+void sim_mix_point_bwd_kij(const double* params, const double* kij, const double* T, const double* rho, int64_t n,
+                           int bubble, const double* g, double* grad /*[n]*/) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16], kk[2] = {kij[2 * i], kij[2 * i + 1]};
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    const double* r = rho + 4 * i;
+    double spec[2], inc[2];
+    if (bubble) { spec[0] = r[2]; spec[1] = r[3]; inc[0] = r[0]; inc[1] = r[1]; }
+    else { spec[0] = r[0]; spec[1] = r[1]; inc[0] = r[2]; inc[1] = r[3]; }
+    if (mix_is_plain(prm)) {
+      PcSaftBinaryPlain b;
+      pcsaft_binary_init(b, prm, kk, T[i]);
+      PointWeights q = point_weights(b.eval(spec[0], spec[1]), spec, inc);
+      grad[i] = mix_point_grad_kij(prm, kk[0], T[i], b.c, spec, inc, q, g[i]);
+    } else {
+      PcSaftBinary b;
+      pcsaft_binary_init(b, prm, kk, T[i]);
+      PointWeights q = point_weights(b.eval(spec[0], spec[1]), spec, inc);
+      grad[i] = mix_point_grad_kij(prm, kk[0], T[i], b.c, spec, inc, q, g[i]);
+    }
+  }
+}
+
+// forward solve of plain pairs through the plain model (mix_point_fwd_kernel<true>); status 3 = not a plain pair
+void sim_mix_point_plain(const double* params, const double* kij, const double* T, const double* z, int64_t n, int bubble,
+                         double* rho, double* value, uint8_t* status, int32_t* evals) {
+  for (int64_t i = 0; i < n; ++i) {
+    double prm[16], kk[2] = {kij[2 * i], kij[2 * i + 1]};
+    for (int k = 0; k < 16; ++k) prm[k] = params[16 * i + k];
+    if (!mix_is_plain(prm)) { status[i] = 3; continue; }
+    PcSaftBinaryPlain b;
+    pcsaft_binary_init(b, prm, kk, T[i]);
+    PointState st, se;
+    MixEval es, ei;
+    int ne = 0;
+    int rc = point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
+    status[i] = (uint8_t)rc;
+    evals[i] = ne;
+    if (rc == kStatusOk) {
+      double re[4];
+      point_densities(st, bubble != 0, z[i], *reinterpret_cast<double(*)[4]>(rho + 4 * i));
+      point_densities(se, bubble != 0, z[i], re);
+      double spec[2], inc[2];
+      if (bubble) { spec[0] = re[2]; spec[1] = re[3]; inc[0] = re[0]; inc[1] = re[1]; }
+      else { spec[0] = re[0]; spec[1] = re[1]; inc[0] = re[2]; inc[1] = re[3]; }
+      value[i] = point_pressure(es, ei.a, spec, inc) * T[i] * kPaPerRed;
+    }
+  }
+}
 }
 
 // ---------------------------------------------------------------------------------------------

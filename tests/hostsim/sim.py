@@ -247,3 +247,23 @@ def pure_order_key(params, T):
     keys = np.empty(T.shape[0], dtype=np.uint64)
     lib().sim_pure_order_key(_p(params), _p(T), ctypes.c_int64(T.shape[0]), _p(keys))
     return keys, int(lib().sim_pure_order_bits())
+
+
+def mix_point_bwd_kij(params, kij, T, rho, bubble, g=None):
+    """k_ij-only backward (mix_point_bwd_kij_kernel): g * d p / d k_ij per state."""
+    params, kij, T, rho = c64(params), c64(kij), c64(T), c64(rho)
+    n = T.shape[0]
+    g = c64(np.ones(n) if g is None else g)
+    grad = np.zeros(n)
+    lib().sim_mix_point_bwd_kij(_p(params), _p(kij), _p(T), _p(rho), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(g), _p(grad))
+    return grad
+
+
+def mix_point_plain(params, kij, T, z, bubble):
+    """Fast path of the plain-pair forward kernel (mix_point_fwd_kernel<true>); status 3 = not a plain pair, 2 = retry list."""
+    params, kij, T, z = c64(params), c64(kij), c64(T), c64(z)
+    n = T.shape[0]
+    rho = np.full((n, 4), np.nan); value = np.full(n, np.nan)
+    status = np.empty(n, dtype=np.uint8); evals = np.zeros(n, dtype=np.int32)
+    lib().sim_mix_point_plain(_p(params), _p(kij), _p(T), _p(z), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(rho), _p(value), _p(status), _p(evals))
+    return rho, value, status, evals

@@ -100,6 +100,29 @@ def test_random_grid(ft, golden_mix, key, bubble):
     assert _check_point_grid(ft, e, key, bubble, exempt) >= 130
 
 
+@pytest.mark.parametrize("key,bubble", [("bubble", True), ("dew", False)])
+def test_kij_only_gradient(ft, golden_mix, key, bubble):
+    """A k_ij fit (only `kij` requires a gradient: mix_point_bwd_kij_kernel, closed form through q1[01], q2[01]; dual
+    pass for eps_AiBj of cross-associating pairs) against the reference autograd gradients of all 14 categories."""
+    e = golden_mix["category_grid"]
+    ge = e[key]
+    n = len(e["T"])
+    x = torch.tensor(e["params"], dtype=F64, device="cuda")
+    k = torch.tensor(e["kij"], dtype=F64, device="cuda", requires_grad=True)
+    t = torch.tensor(e["T"], dtype=F64, device="cuda")
+    z = torch.tensor(e["z"], dtype=F64, device="cuda")
+    p0 = torch.tensor(e["p0"], dtype=F64, device="cuda")
+    model = ft.PcSaftMix(x, k)
+    val, nans = (model.bubble_point if bubble else model.dew_point)(t, z, p0)
+    assert nans.cpu().tolist() == ge["failed"]
+    val.sum().backward()
+    ok = ~nans.cpu().numpy()
+    gk = np.array(ge["grad_kij"])[ok]
+    got = k.grad.cpu().numpy()[ok]
+    assert (np.abs(got - gk) / (np.abs(gk).max(axis=1, keepdims=True) + 1e-300)).max() < 1e-8
+    assert np.abs(gk[:, 1]).max() > 0.0  # the eps_AiBj column is exercised
+
+
 def test_shared_rows_match_per_state_rows(ft):
     """`pair.expand(n, 2, 8)` / `kij.expand(n, 2)` (BASELINE config C4) are handled as ONE row: same pressures and
     masks bit for bit as materialised per-state rows, and the gradient the backward kernel reduces over the states
@@ -130,6 +153,17 @@ def test_shared_rows_match_per_state_rows(ft):
             ref_p, ref_k = P2.grad.sum(dim=0), K2.grad.sum(dim=0)
             assert ((pair.grad - ref_p).abs() / ref_p.abs().max()).max().item() < 1e-12
             assert ((kij.grad - ref_k).abs() / ref_k.abs().max()).max().item() < 1e-12
+            # k_ij alone (mix_point_bwd_kij_kernel), shared and per-state rows
+            k3 = kij.detach().clone().requires_grad_(True)
+            m3 = ft.PcSaftMix(pair.detach().expand(n, 2, 8), k3.expand(n, 2))
+            r, nans3 = (m3.bubble_point if bubble else m3.dew_point)(T, z, p0)
+            (r * w[~nans3]).sum().backward()
+            assert torch.equal(r, p) and ((k3.grad - ref_k).abs() / ref_k.abs().max()).max().item() < 1e-10
+            K4 = kij.detach().expand(n, 2).contiguous().requires_grad_(True)
+            m4 = ft.PcSaftMix(pair.detach().expand(n, 2, 8), K4)
+            r4, nans4 = (m4.bubble_point if bubble else m4.dew_point)(T, z, p0)
+            (r4 * w[~nans4]).sum().backward()
+            assert ((K4.grad - K2.grad).abs().max() / K2.grad.abs().max()).item() < 1e-10
 
 
 def test_shape_checks(ft):

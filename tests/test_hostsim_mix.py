@@ -58,6 +58,37 @@ def test_mix_points(golden_mix, key, bubble, grid):
     assert (np.abs(grad[:, 18] - gT) / np.abs(gT)).max() < 1e-8
 
 
+@pytest.mark.parametrize("key,bubble", [("bubble", True), ("dew", False)])
+def test_mix_kij_only_gradient(golden_mix, key, bubble):
+    """mix_point_bwd_kij_kernel's closed form (k_ij enters through q1[01], q2[01] alone) against the reference
+    autograd d p / d k_ij on all 14 categories -- polar and associating pairs included."""
+    e = golden_mix["category_grid"]
+    P = np.array(e["params"]).reshape(-1, 16)
+    K, T, z = np.array(e["kij"]), np.array(e["T"]), np.array(e["z"])
+    ge = e[key]
+    rho, val, st, ev = sim.mix_point(P, K, T, z, bubble)
+    ok = st == 0
+    gk = np.array(ge["grad_kij"])[ok][:, 0]
+    mine = sim.mix_point_bwd_kij(P[ok], K[ok], T[ok], rho[ok], bubble)
+    assert (np.abs(mine - gk) / np.abs(gk)).max() < 1e-8
+
+
+@pytest.mark.parametrize("bubble", [True, False])
+def test_mix_plain_model_matches_general(golden_mix, bubble):
+    """The plain-pair instantiation of the forward kernel runs the same solver on the same numbers: wherever it
+    finishes (status 0) densities, pressure and evaluation count equal the general model's, bit for bit."""
+    e = golden_mix["random_grid"]
+    P = np.array(e["params"]).reshape(-1, 16)
+    K, T, z = np.array(e["kij"]), np.array(e["T"]), np.array(e["z"])
+    rho_p, val_p, st_p, ev_p = sim.mix_point_plain(P, K, T, z, bubble)
+    rho, val, st, ev = sim.mix_point(P, K, T, z, bubble, robust=False)
+    plain = st_p != 3
+    assert plain.sum() >= 10 and (st_p[plain] == st[plain]).all()
+    done = plain & (st_p == 0)
+    assert np.array_equal(rho_p[done], rho[done]) and np.array_equal(val_p[done], val[done])
+    assert np.array_equal(ev_p[done], ev[done])
+
+
 def test_reference_bubble_dew_configs(golden_mix):
     """tests/test_pcsaft_mix.py:127-251: p and dp/dk_ij of the reference's own test configurations."""
     for name, bubble in (("test_bubble_point", True), ("test_dew_point", False)):
