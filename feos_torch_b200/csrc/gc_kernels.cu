@@ -83,29 +83,58 @@ __device__ __forceinline__ void store_gc_point(int64_t i, int rc, bool bubble, d
 #ifndef FEOS_GC_FWD_MINB
 #define FEOS_GC_FWD_MINB 3
 #endif
-__global__ void __launch_bounds__(kGcFwdBlock, FEOS_GC_FWD_MINB)
-gc_point_fwd_kernel(GcArgs g, const double* __restrict__ molefrac, int64_t n, int bubble, double* __restrict__ rho,
+#ifndef FEOS_GC_SLIM_MINB
+#define FEOS_GC_SLIM_MINB 3
+#endif
+constexpr int kGcSlimBlock = 128;
+constexpr size_t kGcSlimSmem = sizeof(double) * kGcSlimWords * kGcSlimBlock;  // 54 KB: 3 blocks of 4 warps per SM
+
+// Two instantiations share the work by the CLASS of a state's molecule pair (gc_is_slim): SLIM = no association term
+// and at most kGcSlimBond bond types (53 doubles per state, 4-warp blocks), the other one everything else (GcBinary,
+// 2-warp blocks).  Each skips the states of the other class -- the state order sorts by pair, so whole warps skip;
+// the slim one raises `other_class` when it meets such a state, and the general one, launched as a small grid of
+// blocks that walk the tiles, leaves at once while that flag is down.
+// BUBBLE = 1 / 0: bubble / dew point compiled in (the slim instantiations: each is a third smaller than one kernel
+// with both start procedures, and the kernel is instruction-fetch bound -- 117 KB of code ran at an 82 % hit rate of
+// the SM's instruction cache); -1: taken from the argument.
+template <bool SLIM, int BUBBLE>
+__global__ void __launch_bounds__(SLIM ? kGcSlimBlock : kGcFwdBlock, SLIM ? FEOS_GC_SLIM_MINB : FEOS_GC_FWD_MINB)
+gc_point_fwd_kernel(GcArgs g, const double* __restrict__ molefrac, int64_t n, int bubble_arg, double* __restrict__ rho,
                     double* __restrict__ value, uint8_t* __restrict__ failed, int32_t* __restrict__ evals,
                     int32_t* __restrict__ retry_list, int32_t* __restrict__ retry_count,
-                    const int32_t* __restrict__ order) {
+                    const int32_t* __restrict__ order, int32_t* __restrict__ other_class) {
   extern __shared__ double smem[];
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (order) i = order[i];  // states of one molecule pair and similar (T, x) share a warp (order.cuh)
-  GcSource src = make_source(g, i);
-  GcBinary& b = gc_model_slot(smem);
-  gc_binary_init(b, src);
-  double z0 = molefrac[i];
-  PointState st, se;
-  MixEval es, ei;
-  int ne = 0;
-  int rc = point_fast(b, bubble != 0, z0, st, es, ei, se, ne);
-  if (evals) evals[i] = ne;
-  if (rc == kStatusRetry) {
-    retry_list[atomicAdd(retry_count, 1)] = (int32_t)i;
-    return;
+  if (!SLIM && *reinterpret_cast<volatile int32_t*>(other_class) == 0) return;
+  const bool bubble = BUBBLE < 0 ? bubble_arg != 0 : BUBBLE != 0;
+#pragma unroll 1
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = order ? (int64_t)order[t] : t;  // states of one molecule pair and similar (T, x) share a warp
+    GcSource src = make_source(g, i);
+    if (gc_is_slim(src, *src.pair) != SLIM) {
+      if (SLIM) *other_class = 1;
+      continue;
+    }
+    double z0 = molefrac[i];
+    PointState st, se;
+    MixEval es, ei;
+    int ne = 0;
+    int rc;
+    if (SLIM) {
+      GcSlim b;
+      gc_slim_init(b, smem + (size_t)kGcSlimWords * threadIdx.x, src);
+      rc = point_fast(b, bubble, z0, st, es, ei, se, ne);
+    } else {
+      GcBinary& b = gc_model_slot(smem);
+      gc_binary_init(b, src);
+      rc = point_fast(b, bubble, z0, st, es, ei, se, ne);
+    }
+    if (evals) evals[i] = ne;
+    if (rc == kStatusRetry) {
+      retry_list[atomicAdd(retry_count, 1)] = (int32_t)i;
+      continue;
+    }
+    store_gc_point(i, rc, bubble, z0, src.T_, st, se, es, ei, rho, value, failed);
   }
-  store_gc_point(i, rc, bubble != 0, z0, src.T_, st, se, es, ei, rho, value, failed);
 }
 
 // Persistent work-queue variant (point_queue.cuh)
@@ -329,21 +358,28 @@ gc_point_bwd_kab_kernel(GcArgs g, int n_rec, const double* __restrict__ rho, con
   if (valid) {
     src = make_source(g, i);
     my_pair = src.pair;
-    struct {
-      GcBinary b;
-      double cbar[kGcMaxCoef];
-    } w;  // one stack object: see the compiler note in gc_pcsaft.cuh
-    gc_binary_init(w.b, src);
     const double2* rp = reinterpret_cast<const double2*>(rho + 4 * i);
     double2 rv = rp[0], rl = rp[1];
     double spec[2], inc[2];
     if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
     else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
-    MixEval es = w.b.eval(spec[0], spec[1]);
-    PointWeights q = point_weights(es, spec, inc);
-    mix_base_coef_adjoint<kGcMaxBond, true>(w.b.c, spec, inc, q, w.cbar);
-    cb1 = w.cbar[11];
-    cb2 = w.cbar[14];
+    // the adjoints of q1[01], q2[01] are the two dispersion partials (disp_q_partials, mix_grad.cuh) combined over the
+    // phases; the weights come from one evaluation of the specified phase -- through the 53-double slim model where
+    // the pair has no association term (the usual case), through GcBinary otherwise
+    struct {
+      GcBinary b;
+      double slot[kGcSlimWords];
+    } w;  // one stack object: see the compiler note in gc_pcsaft.cuh
+    if (gc_is_slim(src, *src.pair)) {
+      GcSlim b;
+      gc_slim_init(b, w.slot, src);
+      PointWeights q = point_weights(b.eval(spec[0], spec[1]), spec, inc);
+      point_q_adjoints(GcSlimView(w.slot, src.pair), spec, inc, q, cb1, cb2);
+    } else {
+      gc_binary_init(w.b, src);
+      PointWeights q = point_weights(w.b.eval(spec[0], spec[1]), spec, inc);
+      point_q_adjoints(w.b.c, spec, inc, q, cb1, cb2);
+    }
     scale = gout[g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i)] * src.T_ * kPaPerRed;
   }
   const unsigned vm = __ballot_sync(full, valid);
@@ -421,14 +457,16 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   FEOS_ARG(temperature && molefracs && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
   GcArgs g{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
-  Scratch scratch;  // [0] = retry counter, [1] = queue head, [2 ..] = retry list
-  if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)(n + 2), s)) return rc_;
+  Scratch scratch;  // [0] = retry counter, [1] = queue head, [2] = "states of the general class present", [4 ..] = retry list
+  if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)(n + 4), s)) return rc_;
   int32_t* ws = scratch.as<int32_t>();
-  FEOS_CUDA(cudaMemsetAsync(ws, 0, 2 * sizeof(int32_t), s));
+  FEOS_CUDA(cudaMemsetAsync(ws, 0, 4 * sizeof(int32_t), s));
   static PerDevice cache;  // shared-memory opt-in and persistent grid size, once per DEVICE
   int blocks = 0;
   if (int rc_ = cache.get([](int dev, int* v) {
-        FEOS_CUDA(cudaFuncSetAttribute(gc_point_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem));
+        FEOS_CUDA(cudaFuncSetAttribute(gc_point_fwd_kernel<false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem));
+        FEOS_CUDA(cudaFuncSetAttribute(gc_point_fwd_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSlimSmem));
+        FEOS_CUDA(cudaFuncSetAttribute(gc_point_fwd_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSlimSmem));
         FEOS_CUDA(cudaFuncSetAttribute(gc_point_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGcSmem));
         int sms = 0, per_sm = 0;
         FEOS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -439,16 +477,24 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
     return rc_;
   static const int variant = point_kernel_variant();
   if (variant == 0 || n < 65536) {
-    gc_point_fwd_kernel<<<grid_for(n, kGcFwdBlock), kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure,
-                                                                             failed, evals, ws + 2, ws, order);
+    if (bubble)
+      gc_point_fwd_kernel<true, 1><<<grid_for(n, kGcSlimBlock), kGcSlimBlock, kGcSlimSmem, s>>>(
+          g, molefracs, n, bubble, rho, pressure, failed, evals, ws + 4, ws, order, ws + 2);
+    else
+      gc_point_fwd_kernel<true, 0><<<grid_for(n, kGcSlimBlock), kGcSlimBlock, kGcSlimSmem, s>>>(
+          g, molefracs, n, bubble, rho, pressure, failed, evals, ws + 4, ws, order, ws + 2);
+    FEOS_LAUNCH_OK();
+    int general = (int)std::min<int64_t>((n + kGcFwdBlock - 1) / kGcFwdBlock, 4 * (int64_t)std::max(blocks, 1));
+    gc_point_fwd_kernel<false, -1><<<general, kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure, failed, evals,
+                                                                    ws + 4, ws, order, ws + 2);
   } else {
     GcQueueSource src{g, molefracs, rho, pressure, failed};
     int grid = (int)std::min<int64_t>(blocks, (n + kGcFwdBlock - 1) / kGcFwdBlock);
-    gc_point_queue_kernel<<<grid, kGcFwdBlock, kGcSmem, s>>>(src, (int)n, bubble, evals, ws + 2, ws, ws + 1);
+    gc_point_queue_kernel<<<grid, kGcFwdBlock, kGcSmem, s>>>(src, (int)n, bubble, evals, ws + 4, ws, ws + 1);
   }
   FEOS_LAUNCH_OK();
   int retry_grid = (int)(n < 64 * 592 ? (n + 63) / 64 : 592);
-  gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, start_pressure, bubble, rho, pressure, failed, evals, ws + 2, ws);
+  gc_point_retry_kernel<<<retry_grid, 64, 0, s>>>(g, molefracs, start_pressure, bubble, rho, pressure, failed, evals, ws + 4, ws);
   FEOS_LAUNCH_OK();
   return 0;
 }

@@ -73,8 +73,15 @@ struct GcDualSource {
 // BASE = false computes the association group only (the gradients of the hard-sphere / hard-chain /
 // dispersion and dipole groups are taken by the reverse sweeps gc_base_adjoint / gc_dipole_adjoint); the
 // structure flags (nbond, dipolar, cat) are always set so that the flat coefficient order is the same.
-template <class P, class Src, bool BASE = true>
-FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& pr) {
+// bond counts: stored in the coefficient structure, or (slim view below) read from the pair table in place
+template <class P>
+FD void gc_set_bn(MixCoef<P, kGcMaxBond, true>& c, int b, double n0, double n1) {
+  c.bn[b][0] = P(n0);
+  c.bn[b][1] = P(n1);
+}
+
+template <class P, class Src, bool BASE = true, bool ASSOC = true, class Coef = MixCoef<P, kGcMaxBond, true>>
+FD void gc_coef(Coef& c, const Src& src, const GcPair& pr) {
   P T = src.T();
   P ti = ad_recip(T);
   const int ns = pr.nseg;
@@ -106,8 +113,7 @@ FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& p
   for (int b = 0; b < pr.nbond; ++b) {
     P da = d[pr.ba[b]], db = d[pr.bb[b]];
     c.cd[b] = da * db / (da + db);
-    c.bn[b][0] = P(pr.bcnt[0][b]);
-    c.bn[b][1] = P(pr.bcnt[1][b]);
+    gc_set_bn(c, b, pr.bcnt[0][b], pr.bcnt[1][b]);
   }
   // dispersion (:177-194): eps_ab = sqrt(eps_a eps_b phi_i phi_j)/T (1 - k_ab [i != j])
   if (!BASE) {
@@ -172,11 +178,12 @@ FD void gc_coef(MixCoef<P, kGcMaxBond, true>& c, const Src& src, const GcPair& p
       ep[i] = me * mi;
       mu2t[i] = mu2 * mi * kDipoleScale * ti;
     }
-    if (BASE) dipole_coef(c, c.m, sg, ep, mu2t, ti, dipolar);
+    const P mm[2] = {c.m[0], c.m[1]};
+    if (BASE) dipole_coef(c, mm, sg, ep, mu2t, ti, dipolar);
     else c.dipolar = dipolar;
   }
   // association: at most one associating segment per molecule (:76-86), categories (:212-251)
-  {
+  if constexpr (ASSOC) {
     P sa[2], ea[2], kap[2], eab[2];
     int n_assoc = 0, n_self = 0;
 #pragma unroll
@@ -328,6 +335,99 @@ FD void gc_binary_init(GcBinary& b, const GcSource& src) {
     b.msig3[0] += pr.cnt[0][a] * ms3;
     b.msig3[1] += pr.cnt[1][a] * ms3;
   }
+}
+
+// ---- slim model for the forward kernel -----------------------------------------------------------------
+// The forward kernels keep the coefficients of a state in shared memory; GcBinary (MixCoef with 16 bond slots and
+// the association group: 122 doubles) allows 2 warps x 3 blocks per SM.  Pairs WITHOUT an association term and with
+// at most kGcSlimBond bond types -- the usual case -- are solved by an instantiation that keeps 53 doubles per state:
+//   z[4][2] m[2] q1[3] q2[3] msig3[2] flag | mu2t[2] (pw1 pw2 pe ps)[3] (tw1 tw2 ts)[4] | cd[8]
+// and reads the bond counts from the pair table in place.  GcSlimView gives that record the member names of MixCoef,
+// so the evaluation (mix_base_eval_impl, mix_dipole_eval), the solver and gc_coef are the same code.
+constexpr int kGcSlimBond = 8;
+constexpr int kGcSlimWords = 8 + 2 + 6 + 2 + 1 + 26 + kGcSlimBond;  // 53: odd, conflict-free as a per-thread stride
+
+struct GcSlimView {
+  struct BnRow {
+    double v0, v1;
+    FD double operator[](int i) const { return i ? v1 : v0; }
+  };
+  struct Bn {
+    const GcPair* pr;
+    FD BnRow operator[](int b) const { return BnRow{pr->bcnt[0][b], pr->bcnt[1][b]}; }
+  };
+  double (*z)[2];
+  double *m, *q1, *q2, *msig3, *mu2t, *pw1, *pw2, *pe, *ps, *tw1, *tw2, *ts, *cd;
+  Bn bn;
+  int nbond;
+  bool dipolar;
+  static constexpr int cat = kAssocNone;
+  FD GcSlimView(double* p, const GcPair* pr_)
+      : z(reinterpret_cast<double(*)[2]>(p)), m(p + 8), q1(p + 10), q2(p + 13), msig3(p + 16), mu2t(p + 19),
+        pw1(p + 21), pw2(p + 24), pe(p + 27), ps(p + 30), tw1(p + 33), tw2(p + 37), ts(p + 41), cd(p + 45), bn{pr_},
+        nbond(pr_->nbond), dipolar(p[18] != 0.0) {}
+};
+FD void gc_set_bn(GcSlimView&, int, double, double) {}
+
+// non-associating and few enough bond types (the association test of gc_coef, on the primal parameters)
+FD bool gc_is_slim(const GcSource& src, const GcPair& pr) {
+  if (pr.nbond > kGcSlimBond) return false;
+  for (int i = 0; i < 2; ++i) {
+    double kap = 0.0, eab = 0.0;
+    for (int a = 0; a < pr.nseg; ++a) {
+      double n = pr.cnt[i][a];
+      if (n == 0.0) continue;
+      kap += n * src.seg(a, 4);
+      eab += n * src.seg(a, 5);
+    }
+    if (kap * eab != 0.0) return false;
+  }
+  return true;
+}
+
+FD MixEval gc_slim_eval_inline(const GcSlimView& c, double r0, double r1) {
+  BaseH2 b = mix_base_eval_impl<kGcMaxBond>(c, r0, r1);
+  if (c.dipolar) mix_dipole_eval(c, r0, r1, b);
+  H2<double> a;
+  a.re = b.a; a.g0 = b.g0; a.g1 = b.g1; a.h00 = b.h00; a.h01 = b.h01; a.h11 = b.h11;
+  return mix_eval_from(a, r0, r1);
+}
+FD_NOINLINE void gc_slim_eval(double* slot, const GcPair* pr, double r0, double r1, MixEval& e) {
+  e = gc_slim_eval_inline(GcSlimView(slot, pr), r0, r1);
+}
+
+struct GcSlim {
+  double* slot;
+  const GcPair* pr;
+  FD MixEval eval(double r0, double r1) const {
+    MixEval e;
+    gc_slim_eval(slot, pr, r0, r1, e);
+    return e;
+  }
+  FD double max_density(double x0) const { return kMaxEta / (x0 * slot[16] + (1.0 - x0) * slot[17]); }
+  FD double start_density(double x0) const {
+    const double ms[2] = {slot[16], slot[17]};
+    return one_fluid_start_density(GcSlimView(slot, pr), ms, x0, max_density(x0));
+  }
+};
+
+FD void gc_slim_init(GcSlim& b, double* slot, const GcSource& src) {
+  const GcPair& pr = *src.pair;
+  b.slot = slot;
+  b.pr = src.pair;
+  slot[18] = 0.0;
+  GcSlimView c(slot, src.pair);
+  gc_coef<double, GcSource, true, false>(c, src, pr);
+  slot[18] = c.dipolar ? 1.0 : 0.0;
+  double m0 = 0.0, m1 = 0.0;
+  for (int a = 0; a < pr.nseg; ++a) {
+    double s = src.seg(a, 1);
+    double ms3 = kPi / 6.0 * src.seg(a, 0) * s * s * s;
+    m0 += pr.cnt[0][a] * ms3;
+    m1 += pr.cnt[1][a] * ms3;
+  }
+  slot[16] = m0;
+  slot[17] = m1;
 }
 
 // ---- gradient of the Newton-step bubble/dew pressure -------------------------------------------

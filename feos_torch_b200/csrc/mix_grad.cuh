@@ -265,10 +265,11 @@ FD void disp_q_partials(const C& c, const R& rho0, const R& rho1, R& pq1, R& pq2
   pq2 = (-kPi) * ((c1 * i2) * mbar);
 }
 
-// g * d(p_bubble/dew [Pa]) / d k_ij of any binary; `q` = point_weights of the specified phase's full evaluation
+// cb1 = d p_red / d q1[01], cb2 = d p_red / d q2[01] of the Newton-step pressure (the two coefficient adjoints a
+// k_ij or k_ab gradient needs); `q` = point_weights of the specified phase's full evaluation
 template <class C>
-FD double mix_point_grad_kij(const double (&prm)[16], double kij0, double T, const C& c, const double (&spec)[2],
-                             const double (&inc)[2], const PointWeights& q, double g) {
+FD void point_q_adjoints(const C& c, const double (&spec)[2], const double (&inc)[2], const PointWeights& q, double& cb1,
+                         double& cb2) {
   double iq1, iq2;
   D1 sq1, sq2;
   disp_q_partials<double>(c, inc[0], inc[1], iq1, iq2);
@@ -276,8 +277,16 @@ FD double mix_point_grad_kij(const double (&prm)[16], double kij0, double T, con
   disp_q_partials<D1>(c, s0, s1, sq1, sq2);
   const D1 r01 = 2.0 * (s0 * s1);
   const double i01 = 2.0 * inc[0] * inc[1];
-  const double cb1 = point_comb(iq1 * i01, sq1 * r01, q);  // d p_red / d q1[01]
-  const double cb2 = point_comb(iq2 * i01, sq2 * r01, q);  // d p_red / d q2[01]
+  cb1 = point_comb(iq1 * i01, sq1 * r01, q);
+  cb2 = point_comb(iq2 * i01, sq2 * r01, q);
+}
+
+// g * d(p_bubble/dew [Pa]) / d k_ij of any binary
+template <class C>
+FD double mix_point_grad_kij(const double (&prm)[16], double kij0, double T, const C& c, const double (&spec)[2],
+                             const double (&inc)[2], const PointWeights& q, double g) {
+  double cb1, cb2;
+  point_q_adjoints(c, spec, inc, q, cb1, cb2);
   // q1[01] = m0 m1 sqrt(eps0 eps1)/T (1 - k) s01^3, q2[01] = q1[01] sqrt(eps0 eps1)/T (1 - k)
   const double ti = 1.0 / T;
   const double s01 = 0.5 * (prm[1] + prm[9]);

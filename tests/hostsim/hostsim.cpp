@@ -379,6 +379,34 @@ void sim_gc_point(const GcPair* pairs, const double* seg, const double* kab, con
   }
 }
 
+// fast path of the slim-class forward kernel (gc_point_fwd_kernel<true>); status 3 = not a slim pair, 2 = retry list
+void sim_gc_point_slim(const GcPair* pairs, const double* seg, const double* kab, const int32_t* idx, const double* phi,
+                       const double* T, const double* z, int64_t n, int bubble, double* rho, double* value,
+                       uint8_t* status, int32_t* evals) {
+  for (int64_t i = 0; i < n; ++i) {
+    GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    if (!gc_is_slim(s, *s.pair)) { status[i] = 3; continue; }
+    double slot[kGcSlimWords];
+    GcSlim b;
+    gc_slim_init(b, slot, s);
+    PointState st, se;
+    MixEval es, ei;
+    int ne = 0;
+    int rc = point_fast(b, bubble != 0, z[i], st, es, ei, se, ne);
+    status[i] = (uint8_t)rc;
+    evals[i] = ne;
+    if (rc == kStatusOk) {
+      double re[4];
+      point_densities(st, bubble != 0, z[i], *reinterpret_cast<double(*)[4]>(rho + 4 * i));
+      point_densities(se, bubble != 0, z[i], re);
+      double spec[2], inc[2];
+      if (bubble) { spec[0] = re[2]; spec[1] = re[3]; inc[0] = re[0]; inc[1] = re[1]; }
+      else { spec[0] = re[0]; spec[1] = re[1]; inc[0] = re[2]; inc[1] = re[3]; }
+      value[i] = point_pressure(es, ei.a, spec, inc) * T[i] * kPaPerRed;
+    }
+  }
+}
+
 // grad_seg [n_seg,8] and grad_kab [n_rec] accumulate over states; grad_phi [n,2], grad_t [n]
 // the k_ab-only backward path (gc_point_bwd_kab_kernel)
 void sim_gc_point_bwd_kab(const GcPair* pairs, const double* seg, const double* kab, int n_rec, const int32_t* idx,
@@ -387,22 +415,29 @@ void sim_gc_point_bwd_kab(const GcPair* pairs, const double* seg, const double* 
   for (int64_t i = 0; i < n; ++i) {
     GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
     const GcPair& pr = *s.pair;
-    GcBinary b;
-    gc_binary_init(b, s);
     const double* r = rho + 4 * i;
     double spec[2], inc[2];
     if (bubble) { spec[0] = r[2]; spec[1] = r[3]; inc[0] = r[0]; inc[1] = r[1]; }
     else { spec[0] = r[0]; spec[1] = r[1]; inc[0] = r[2]; inc[1] = r[3]; }
-    MixEval es = b.eval(spec[0], spec[1]);
-    PointWeights q = point_weights(es, spec, inc);
-    double cbar[kGcMaxCoef];
-    mix_base_coef_adjoint<kGcMaxBond, true>(b.c, spec, inc, q, cbar);
+    double cb1, cb2;
+    if (gc_is_slim(s, pr)) {  // as gc_point_bwd_kab_kernel
+      double slot[kGcSlimWords];
+      GcSlim b;
+      gc_slim_init(b, slot, s);
+      PointWeights q = point_weights(b.eval(spec[0], spec[1]), spec, inc);
+      point_q_adjoints(GcSlimView(slot, s.pair), spec, inc, q, cb1, cb2);
+    } else {
+      GcBinary b;
+      gc_binary_init(b, s);
+      PointWeights q = point_weights(b.eval(spec[0], spec[1]), spec, inc);
+      point_q_adjoints(b.c, spec, inc, q, cb1, cb2);
+    }
     double scale = g[i] * T[i] * kPaPerRed;
     for (int a = 0; a < pr.nseg; ++a)
       for (int c2 = 0; c2 < pr.nseg; ++c2) {
         int rec = pr.krec[a][c2];
         if (rec < 0 || pr.cnt[0][a] * pr.cnt[1][c2] == 0.0) continue;
-        grad_kab[rec] += gc_kab_term(s, pr, a, c2, cbar[11], cbar[14]) * scale;
+        grad_kab[rec] += gc_kab_term(s, pr, a, c2, cb1, cb2) * scale;
       }
   }
   (void)n_rec;

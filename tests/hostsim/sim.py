@@ -267,3 +267,15 @@ def mix_point_plain(params, kij, T, z, bubble):
     status = np.empty(n, dtype=np.uint8); evals = np.zeros(n, dtype=np.int32)
     lib().sim_mix_point_plain(_p(params), _p(kij), _p(T), _p(z), ctypes.c_int64(n), ctypes.c_int(int(bubble)), _p(rho), _p(value), _p(status), _p(evals))
     return rho, value, status, evals
+
+
+def gc_point_slim(pairs, seg, kab, idx, phi, T, z, bubble):
+    """Fast path of the slim-class GC forward kernel (gc_point_fwd_kernel<true>); status 3 = not a slim pair."""
+    pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
+    z = c64(z)
+    n = T.shape[0]
+    rho = np.full((n, 4), np.nan); val = np.full(n, np.nan)
+    status = np.empty(n, dtype=np.uint8); evals = np.zeros(n, dtype=np.int32)
+    lib().sim_gc_point_slim(_p(pairs), _p(seg), _p(kab), _p(idx), _p(phi), _p(T), _p(z), ctypes.c_int64(n), ctypes.c_int(int(bubble)),
+                            _p(rho), _p(val), _p(status), _p(evals))
+    return rho, val, status, evals

@@ -87,6 +87,29 @@ def test_gc_points(golden_gc, key, bubble):
     assert (np.abs(gt - ge["grad_T"]) / np.abs(ge["grad_T"])).max() < 1e-8
 
 
+@pytest.mark.parametrize("bubble", [True, False])
+def test_slim_model_matches_general(golden_gc, bubble):
+    """The slim-class instantiation of the GC forward kernel (no association term, <= 8 bond types: 53 doubles per
+    state, bond counts read from the pair table) runs the same solver on the same numbers: wherever its fast path
+    finishes, densities, pressure and evaluation count equal the general model's bit for bit; the associating
+    categories are left to the general instantiation."""
+    ident, seg = table(golden_gc)
+    e = golden_gc["category_grid"]
+    rows = e["category"]
+    pairs, idx = build_pair_table(ident, [cases.GC_SEGMENTS[i] for i in rows], [cases.GC_BONDS[i] for i in rows], cases.GC_KAB)
+    kab = np.array([k[2] for k in cases.GC_KAB])
+    T, z = np.array(e["T"]), np.array(e["z"])
+    phi = np.array([cases.GC_PHI] * len(T))
+    rho_s, val_s, st_s, ev_s = sim.gc_point_slim(pairs, seg, kab, idx, phi, T, z, bubble)
+    rho, val, st, ev = sim.gc_point(pairs, seg, kab, idx, phi, T, z, bubble)
+    slim = st_s != 3
+    assert 8 <= slim.sum() < len(T)  # both classes occur on the grid
+    done = slim & (st_s == 0)
+    assert done.sum() >= 8 and (st[done] == 0).all()
+    assert np.array_equal(rho_s[done], rho[done]) and np.array_equal(val_s[done], val[done])
+    assert np.array_equal(ev_s[done], ev[done])
+
+
 def test_reference_gc_configs(golden_gc):
     """tests/test_gc_pcsaft.py:130-222: butane/propane, k_ab(CH3, CH2) = -0.15, T = 150 K, z = 0.5."""
     ident, seg = table(golden_gc)
