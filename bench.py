@@ -529,6 +529,9 @@ def measure(name, n, steps, warmup, rank, world, dev, flush, peak):
         total_ms = 0.0
         if collect:
             _lib.TIMINGS = {}
+        profiled = os.environ.get("FEOS_BENCH_CUDA_PROFILER") == fn.__name__
+        if profiled:  # `ncu --profile-from-start off`: only the timed steps of this leg (not the workload generation)
+            torch.cuda.cudart().cudaProfilerStart()
         for _ in range(steps):
             flush.zero_()  # L2 flush between timed iterations (inputs are smaller than L2)
             e0 = torch.cuda.Event(enable_timing=True)
@@ -538,6 +541,8 @@ def measure(name, n, steps, warmup, rank, world, dev, flush, peak):
             e1.record()
             e1.synchronize()
             total_ms += e0.elapsed_time(e1)
+        if profiled:
+            torch.cuda.cudart().cudaProfilerStop()
         barrier()
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -667,6 +672,14 @@ def _main(out):
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # host-side reductions of the end-to-end leg (loss = sum over the returned host tensors): 4 threads per rank.
+    # With all 16 vCPUs of the box in the OpenMP team the following device->host copies into the recycled pinned
+    # buffers run at a fifth of PCIe speed (profiles/README.md, round 2: 763 vs 160 us per 8 MB); torchrun's default
+    # of 1 thread makes the sums themselves the bottleneck.
+    try:
+        torch.set_num_threads(max(1, min(4, len(os.sched_getaffinity(0)) // max(1, world))))
+    except AttributeError:
+        torch.set_num_threads(4)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

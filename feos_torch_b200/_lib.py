@@ -50,6 +50,7 @@ SIGNATURES = {
 }
 
 _lib = None
+_FUNCS = {}
 
 
 class FeosB200Error(RuntimeError):
@@ -76,10 +77,12 @@ def load():
 
 def call(name, *args):
     """Call an ``int``-returning entry point and raise with the library's error text on failure."""
-    lib = load()
-    rc = getattr(lib, name)(*args)
+    fn = _FUNCS.get(name)
+    if fn is None:
+        fn = _FUNCS[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
-        raise FeosB200Error(f"{name} failed ({rc}): {lib.feos_b200_last_error().decode()}")
+        raise FeosB200Error(f"{name} failed ({rc}): {load().feos_b200_last_error().decode()}")
 
 
 TIMINGS = None  # set to {} by bench.py: entry point -> [(start_event, end_event), ...]
@@ -135,7 +138,6 @@ def cached_order(kind, tensors, compute, n=None, soft=()):
     import weakref
 
     versions = tuple(t._version for t in tensors)
-    _ORDER_CACHE[:] = [e for e in _ORDER_CACHE if all(r() is not None for r in e.refs)]
     for k, e in enumerate(_ORDER_CACHE):
         if (e.kind == kind and e.versions == versions and e.n == n and len(e.refs) == len(tensors)
                 and all(r() is t for r, t in zip(e.refs, tensors))):
@@ -154,6 +156,7 @@ def cached_order(kind, tensors, compute, n=None, soft=()):
                 e.changes = 0
             _ORDER_CACHE.insert(0, _ORDER_CACHE.pop(k))
             return e.order
+    _ORDER_CACHE[:] = [e for e in _ORDER_CACHE if all(r() is not None for r in e.refs)]  # tensors that are gone
     e = _OrderEntry()
     e.kind, e.versions, e.n, e.changes = kind, versions, n, 0
     e.refs = tuple(weakref.ref(t) for t in tensors)
@@ -175,14 +178,16 @@ def launch_count():
 
 
 def ptr(t):
-    """Device (or host) pointer of a contiguous tensor / numpy array, ``None`` -> NULL."""
+    """Device (or host) address of a contiguous tensor / numpy array as a plain int (ctypes converts it to the
+    ``void*`` of the signature; building a ``c_void_p`` object per argument costs more than the conversion),
+    ``None`` -> NULL."""
     if t is None:
         return None
     if hasattr(t, "data_ptr"):
-        return ctypes.c_void_p(t.data_ptr())
-    return ctypes.c_void_p(t.ctypes.data)
+        return t.data_ptr()
+    return t.ctypes.data
 
 
 def ptr_at(t, byte_offset):
     """``ptr(t)`` advanced by ``byte_offset`` bytes (row-chunked launches)."""
-    return ctypes.c_void_p(t.data_ptr() + byte_offset)
+    return t.data_ptr() + byte_offset

@@ -173,8 +173,10 @@ def _off(t, rows):
     """Pointer to row ``rows`` of a contiguous tensor (chunked launches through the C ABI)."""
     if t is None:
         return None
+    if rows == 0:
+        return t.data_ptr()
     stride = t.stride(0) if t.dim() > 1 else 1
-    return _lib.ptr_at(t, rows * stride * t.element_size())
+    return t.data_ptr() + rows * stride * t.element_size()
 
 
 def _launch_chunked(params, ranges_events, launch):

@@ -29,8 +29,9 @@ def kernels(path):
             "flops_per_cycle": per_cycle, "fp64_pipe_pct": g("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
             "lanes": g("smsp__thread_inst_executed_per_inst_executed.ratio"), "regs": g("launch__registers_per_thread"),
             "icc_hit_pct": g("sm__icc_request_hit_rate.pct"),
-            "dram_mb": (g("dram__bytes_read.sum") + g("dram__bytes_write.sum")),
-            "dram_unit": rows[1][hdr.index("dram__bytes_read.sum")] if "dram__bytes_read.sum" in hdr else "",
+            "dram_mb": sum(g(k) * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(rows[1][hdr.index(k)], 1.0)
+                           for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in hdr),
+            "dram_unit": "MB",
         }
 
 
