@@ -87,7 +87,7 @@ __device__ __forceinline__ void store_gc_point(int64_t i, int rc, bool bubble, d
 #define FEOS_GC_SLIM_MINB 3
 #endif
 constexpr int kGcSlimBlock = 128;
-constexpr size_t kGcSlimSmem = sizeof(double) * kGcSlimWords * kGcSlimBlock;  // 54 KB: 3 blocks of 4 warps per SM
+constexpr size_t kGcSlimSmem = sizeof(double) * kGcSlimWords * kGcSlimBlock;  // 61 KB: 3 blocks of 4 warps per SM
 
 // Two instantiations share the work by the CLASS of a state's molecule pair (gc_is_slim): SLIM = no association term
 // and at most kGcSlimBond bond types (53 doubles per state, 4-warp blocks), the other one everything else (GcBinary,

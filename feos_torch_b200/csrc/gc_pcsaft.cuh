@@ -345,8 +345,13 @@ FD void gc_binary_init(GcBinary& b, const GcSource& src) {
 // and reads the bond counts from the pair table in place.  GcSlimView gives that record the member names of MixCoef,
 // so the evaluation (mix_base_eval_impl, mix_dipole_eval), the solver and gc_coef are the same code.
 constexpr int kGcSlimBond = 8;
-constexpr int kGcSlimWords = 8 + 2 + 6 + 2 + 1 + 26 + kGcSlimBond;  // 53: odd, conflict-free as a per-thread stride
+constexpr int kGcSlimDip = 19;                                    // offset of the DipolePoly record
+constexpr int kGcSlimCd = kGcSlimDip + sizeof(DipolePoly) / 8;    // offset of cd[]
+constexpr int kGcSlimWords = (kGcSlimCd + kGcSlimBond) | 1;       // 61: odd, conflict-free as a per-thread stride
+static_assert(sizeof(DipolePoly) == 33 * 8, "DipolePoly layout");
 
+// `dip` = where the coefficient stage (dipole_coef) puts the 26 raw dipole coefficients: a temporary of
+// gc_slim_init, which folds them into the DipolePoly record of the slot; the evaluation never reads them.
 struct GcSlimView {
   struct BnRow {
     double v0, v1;
@@ -357,15 +362,17 @@ struct GcSlimView {
     FD BnRow operator[](int b) const { return BnRow{pr->bcnt[0][b], pr->bcnt[1][b]}; }
   };
   double (*z)[2];
-  double *m, *q1, *q2, *msig3, *mu2t, *pw1, *pw2, *pe, *ps, *tw1, *tw2, *ts, *cd;
+  double *m, *q1, *q2, *msig3, *cd;
+  double *mu2t, *pw1, *pw2, *pe, *ps, *tw1, *tw2, *ts;
   Bn bn;
   int nbond;
   bool dipolar;
   static constexpr int cat = kAssocNone;
-  FD GcSlimView(double* p, const GcPair* pr_)
-      : z(reinterpret_cast<double(*)[2]>(p)), m(p + 8), q1(p + 10), q2(p + 13), msig3(p + 16), mu2t(p + 19),
-        pw1(p + 21), pw2(p + 24), pe(p + 27), ps(p + 30), tw1(p + 33), tw2(p + 37), ts(p + 41), cd(p + 45), bn{pr_},
-        nbond(pr_->nbond), dipolar(p[18] != 0.0) {}
+  FD GcSlimView(double* p, const GcPair* pr_, double* dip = nullptr)
+      : z(reinterpret_cast<double(*)[2]>(p)), m(p + 8), q1(p + 10), q2(p + 13), msig3(p + 16), cd(p + kGcSlimCd),
+        mu2t(dip), pw1(dip + 2), pw2(dip + 5), pe(dip + 8), ps(dip + 11), tw1(dip + 14), tw2(dip + 18), ts(dip + 22),
+        bn{pr_}, nbond(pr_->nbond), dipolar(p[18] != 0.0) {}
+  FD const DipolePoly& poly() const { return *reinterpret_cast<const DipolePoly*>(&z[0][0] + kGcSlimDip); }
 };
 FD void gc_set_bn(GcSlimView&, int, double, double) {}
 
@@ -387,7 +394,7 @@ FD bool gc_is_slim(const GcSource& src, const GcPair& pr) {
 
 FD MixEval gc_slim_eval_inline(const GcSlimView& c, double r0, double r1) {
   BaseH2 b = mix_base_eval_impl<kGcMaxBond>(c, r0, r1);
-  if (c.dipolar) mix_dipole_eval(c, r0, r1, b);
+  if (c.dipolar) dipole_poly_eval(c.poly(), c.z[3][0], c.z[3][1], r0, r1, b);
   H2<double> a;
   a.re = b.a; a.g0 = b.g0; a.g1 = b.g1; a.h00 = b.h00; a.h01 = b.h01; a.h11 = b.h11;
   return mix_eval_from(a, r0, r1);
@@ -416,9 +423,11 @@ FD void gc_slim_init(GcSlim& b, double* slot, const GcSource& src) {
   b.slot = slot;
   b.pr = src.pair;
   slot[18] = 0.0;
-  GcSlimView c(slot, src.pair);
+  double dip[26];
+  GcSlimView c(slot, src.pair, dip);
   gc_coef<double, GcSource, true, false>(c, src, pr);
   slot[18] = c.dipolar ? 1.0 : 0.0;
+  if (c.dipolar) dipole_poly_from(*reinterpret_cast<DipolePoly*>(slot + kGcSlimDip), c);
   double m0 = 0.0, m1 = 0.0;
   for (int a = 0; a < pr.nseg; ++a) {
     double s = src.seg(a, 1);

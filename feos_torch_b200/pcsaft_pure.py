@@ -126,8 +126,21 @@ class _HostToDevice(torch.autograd.Function):
         return _to_host(g, _chunks_of(g)), None, None
 
 
+# Result buffers in pinned host memory.  torch's caching host allocator hands the most recently freed block back
+# first, i.e. the block whose lines the caller's CPU threads have just read (e.g. the loss reduction); a device->host
+# copy into such a block ran at 10-15 GB/s instead of 50 GB/s on the development boxes.  Holding the last few result
+# buffers a little longer makes the allocator rotate through cold blocks instead (FEOS_B200_PINNED_RING, 0 = off).
+import collections as _collections
+import os as _os
+
+_PINNED_RING = _collections.deque(maxlen=max(0, int(_os.environ.get("FEOS_B200_PINNED_RING", "6"))) or None)
+_PINNED_RING_ON = _PINNED_RING.maxlen is not None
+
+
 def _to_host(t, chunks=None):
     out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    if _PINNED_RING_ON and out.numel() * out.element_size() <= (32 << 20):
+        _PINNED_RING.append(out)
     if chunks is not None:
         ds = _copy_stream(t.device, "d2h")
         with torch.cuda.stream(ds):

@@ -379,6 +379,29 @@ void sim_gc_point(const GcPair* pairs, const double* seg, const double* kab, con
   }
 }
 
+// state functions through the slim model (53 + 8 doubles per state, DipolePoly dipole term); ok[i] = 0 for pairs of the general class
+void sim_gc_state_slim(const GcPair* pairs, const double* seg, const double* kab, const int32_t* idx, const double* phi,
+                       const double* T, const double* rho, int64_t n, double* a, double* p, double* mu, double* v,
+                       double* h, uint8_t* ok) {
+  for (int64_t i = 0; i < n; ++i) {
+    GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    ok[i] = gc_is_slim(s, *s.pair);
+    MixEval e;
+    if (ok[i]) {
+      double slot[kGcSlimWords];
+      GcSlim b;
+      gc_slim_init(b, slot, s);
+      e = b.eval(rho[2 * i], rho[2 * i + 1]);
+    } else {
+      GcBinary b;
+      gc_binary_init(b, s);
+      e = b.eval(rho[2 * i], rho[2 * i + 1]);
+    }
+    a[i] = e.a; p[i] = e.p; mu[2 * i] = e.mu[0]; mu[2 * i + 1] = e.mu[1]; v[2 * i] = e.v[0]; v[2 * i + 1] = e.v[1];
+    h[3 * i] = e.h00; h[3 * i + 1] = e.h01; h[3 * i + 2] = e.h11;
+  }
+}
+
 // fast path of the slim-class forward kernel (gc_point_fwd_kernel<true>); status 3 = not a slim pair, 2 = retry list
 void sim_gc_point_slim(const GcPair* pairs, const double* seg, const double* kab, const int32_t* idx, const double* phi,
                        const double* T, const double* z, int64_t n, int bubble, double* rho, double* value,

@@ -279,3 +279,15 @@ def gc_point_slim(pairs, seg, kab, idx, phi, T, z, bubble):
     lib().sim_gc_point_slim(_p(pairs), _p(seg), _p(kab), _p(idx), _p(phi), _p(T), _p(z), ctypes.c_int64(n), ctypes.c_int(int(bubble)),
                             _p(rho), _p(val), _p(status), _p(evals))
     return rho, val, status, evals
+
+
+def gc_state_slim(pairs, seg, kab, idx, phi, T, rho):
+    """(a, p, mu, v, hessian (h00, h01, h11), slim flag) through the slim model where the pair allows it."""
+    pairs, seg, kab, idx, phi, T = _gc_args(pairs, seg, kab, idx, phi, T)
+    rho = c64(rho)
+    n = T.shape[0]
+    a = np.empty(n); p = np.empty(n); mu = np.empty((n, 2)); v = np.empty((n, 2)); h = np.empty((n, 3))
+    ok = np.empty(n, dtype=np.uint8)
+    lib().sim_gc_state_slim(_p(pairs), _p(seg), _p(kab), _p(idx), _p(phi), _p(T), _p(rho), ctypes.c_int64(n), _p(a), _p(p),
+                            _p(mu), _p(v), _p(h), _p(ok))
+    return a, p, mu, v, h, ok.astype(bool)
