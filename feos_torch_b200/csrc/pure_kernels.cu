@@ -233,17 +233,20 @@ pure_vle_bwd_kernel(const double* __restrict__ params, const double* __restrict_
                     double* __restrict__ grad_t) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (failed[i]) {
+  // every input of the state is requested before the first use: one exposed memory latency per thread instead of
+  // one per dependent step (mask -> row -> densities -> row map -> upstream gradient)
+  const uint8_t bad = failed[i];
+  PureRow r = load_row(params, i);
+  double T = temperature[i];
+  double2 rr = reinterpret_cast<const double2*>(rho)[i];
+  int64_t gi_idx = g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i);
+  if (bad) {
     double2* gp = reinterpret_cast<double2*>(grad_params + 8 * i);
 #pragma unroll
     for (int k = 0; k < 4; ++k) gp[k] = make_double2(0.0, 0.0);
     if (grad_t) grad_t[i] = 0.0;
     return;
   }
-  PureRow r = load_row(params, i);
-  double T = temperature[i];
-  double2 rr = reinterpret_cast<const double2*>(rho)[i];
-  int64_t gi_idx = g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i);
   double gv = g_vp ? g_vp[gi_idx] : 0.0;
   double gr = 0.0, dpl = 1.0;
   if (NEED_RLEQ) {
@@ -271,10 +274,11 @@ pure_rho_tp_fwd_kernel(const double* __restrict__ params, const double* __restri
   if (order) i = order[i];
   PureRow r = load_row(params, i);
   double T = temperature[i];
+  double p_raw = pressure[i];
   PureCoef<double> c;
   double rho_max;
   make_coef(r, T, c, rho_max);
-  double p_t = pressure[i] / (T * kPaPerRed);  // pcsaft_pure.py:196
+  double p_t = p_raw / (T * kPaPerRed);  // pcsaft_pure.py:196
   double x;
   PureEval e;
   int ne = 0;
@@ -296,7 +300,14 @@ pure_rho_tp_bwd_kernel(const double* __restrict__ params, const double* __restri
                        double* __restrict__ grad_t, double* __restrict__ grad_p) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  if (failed[i]) {
+  // all inputs requested before the first use (see pure_vle_bwd_kernel)
+  const uint8_t bad = failed[i];
+  PureRow r = load_row(params, i);
+  double T = temperature[i];
+  double x = rho[i];
+  double p_raw = pressure[i];
+  const int64_t gi_idx = g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i);
+  if (bad) {
     if (grad_params) {
       double2* gp = reinterpret_cast<double2*>(grad_params + 8 * i);
 #pragma unroll
@@ -306,15 +317,12 @@ pure_rho_tp_bwd_kernel(const double* __restrict__ params, const double* __restri
     if (grad_p) grad_p[i] = 0.0;
     return;
   }
-  PureRow r = load_row(params, i);
-  double T = temperature[i];
+  double gi = g[gi_idx];
   PureCoef<double> c;
   double rho_max;
   make_coef(r, T, c, rho_max);
-  double x = rho[i];
   double dp = pure_eval(c, x).dp;
-  double p_t = pressure[i] / (T * kPaPerRed);
-  double gi = g[g_broadcast ? 0 : (pos ? (int64_t)pos[i] : i)];
+  double p_t = p_raw / (T * kPaPerRed);
   if (grad_p) grad_p[i] = gi / dp / (T * kPaPerRed) * kKmolM3PerRed;
   if (!grad_params && !grad_t) return;
   double out[9];
