@@ -39,11 +39,45 @@ struct GcArgs {
   const int32_t* pair_index;
   const double* phi;
   const double* temperature;
+  const GcPairCoef* pair_coef = nullptr;  // per-pair part of the slim coefficient stage (gc_pair_coef_kernel), or NULL
 };
+
+// one block of two warps per molecule pair: the state-independent part of the slim coefficient stage (gc_pcsaft.cuh).
+// It is a chain of a few thousand dependent instructions, so its length is what costs: warp 0 shares the
+// O(n_seg^2) dispersion sums among its lanes, lane 0 of warp 1 does the molecule-level and dipole part meanwhile.
+__global__ void __launch_bounds__(64)
+gc_pair_coef_kernel(const GcPair* __restrict__ pairs, const double* __restrict__ seg_params,
+                    const double* __restrict__ kab, GcPairCoef* __restrict__ out) {
+  const GcPair& pr = pairs[blockIdx.x];
+  GcPairCoef& o = out[blockIdx.x];
+  if (threadIdx.x < 32) {
+    double S1[3], S2[3];
+    gc_pair_dispersion(seg_params, kab, pr, threadIdx.x, 32, S1, S2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int w = 16; w > 0; w >>= 1) {
+        S1[k] += __shfl_xor_sync(0xffffffffu, S1[k], w);
+        S2[k] += __shfl_xor_sync(0xffffffffu, S2[k], w);
+      }
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        o.S1[k] = S1[k];
+        o.S2[k] = S2[k];
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    gc_pair_molecules(o, seg_params, kab, pr);
+  }
+}
 
 __device__ __forceinline__ GcSource make_source(const GcArgs& g, int64_t i) {
   GcSource s;
-  s.pair = g.pairs + g.pair_index[i];
+  const int32_t pi = g.pair_index[i];
+  s.pair = g.pairs + pi;
+  s.pc = g.pair_coef ? g.pair_coef + pi : nullptr;
   s.seg_params = g.seg_params;
   s.kab = g.kab;
   if (g.phi) {
@@ -435,6 +469,15 @@ gc_state_kernel(GcArgs g, const double* __restrict__ density, int64_t n, double*
 using namespace feos;
 
 namespace {
+// per-pair table of the slim coefficient stage, computed once per call into stream-ordered scratch
+int make_pair_coef(GcArgs& g, int32_t n_pairs, Scratch& mem, cudaStream_t s) {
+  if (int rc = mem.alloc(sizeof(GcPairCoef) * (size_t)n_pairs, s)) return rc;
+  gc_pair_coef_kernel<<<n_pairs, 64, 0, s>>>(g.pairs, g.seg_params, g.kab, mem.as<GcPairCoef>());
+  FEOS_LAUNCH_OK();
+  g.pair_coef = mem.as<GcPairCoef>();
+  return 0;
+}
+
 int check_tables(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg, int32_t n_rec,
                  const double* kab, const int32_t* pair_index) {
   FEOS_ARG(pairs && n_pairs > 0 && seg_params && n_seg > 0 && n_rec >= 0 && pair_index);
@@ -457,6 +500,8 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   FEOS_ARG(temperature && molefracs && rho && failed);
   cudaStream_t s = (cudaStream_t)stream;
   GcArgs g{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
+  Scratch pair_coef;
+  if (int rc_ = make_pair_coef(g, n_pairs, pair_coef, s)) return rc_;
   Scratch scratch;  // [0] = retry counter, [1] = queue head, [2] = "states of the general class present", [4 ..] = retry list
   if (int rc_ = scratch.alloc(sizeof(int32_t) * (size_t)(n + 4), s)) return rc_;
   int32_t* ws = scratch.as<int32_t>();
@@ -511,6 +556,8 @@ int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
   if (int rc = check_tables(pairs, n_pairs, seg_params, n_seg, n_rec, kab, pair_index)) return rc;
   FEOS_ARG(temperature && rho && failed && g);
   GcArgs a{reinterpret_cast<const GcPair*>(pairs), seg_params, kab, pair_index, phi, temperature};
+  Scratch pair_coef;
+  if (int rc_ = make_pair_coef(a, n_pairs, pair_coef, (cudaStream_t)stream)) return rc_;
   size_t shmem = sizeof(double) * (size_t)(8 * n_seg + n_rec);
   FEOS_ARG(shmem <= 48 * 1024);
   // experiment knob: pad the dynamic shared memory to cap the number of resident blocks per SM (the

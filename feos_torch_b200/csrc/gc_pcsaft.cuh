@@ -34,8 +34,11 @@ struct GcPair {
 using GcCoef = MixCoef<double, kGcMaxBond, true>;
 
 // Plain-double source of the inputs of the coefficient stage.
+struct GcPairCoef;
+
 struct GcSource {
   const GcPair* pair;
+  const GcPairCoef* pc = nullptr;  // per-pair part of the slim coefficient stage (gc_pair_coef), if the caller has one
   const double* seg_params;  // [S, 8] global table
   const double* kab;         // [R] values of the binary segment records
   double phi_[2], T_;
@@ -345,13 +348,119 @@ FD void gc_binary_init(GcBinary& b, const GcSource& src) {
 // and reads the bond counts from the pair table in place.  GcSlimView gives that record the member names of MixCoef,
 // so the evaluation (mix_base_eval_impl, mix_dipole_eval), the solver and gc_coef are the same code.
 constexpr int kGcSlimBond = 8;
-constexpr int kGcSlimDip = 19;                                    // offset of the DipolePoly record
-constexpr int kGcSlimCd = kGcSlimDip + sizeof(DipolePoly) / 8;    // offset of cd[]
-constexpr int kGcSlimWords = (kGcSlimCd + kGcSlimBond) | 1;       // 61: odd, conflict-free as a per-thread stride
-static_assert(sizeof(DipolePoly) == 33 * 8, "DipolePoly layout");
+constexpr int kGcSlimMu = 19, kGcSlimC2 = 21, kGcSlimCd = 36;
+constexpr int kGcSlimWords = (kGcSlimCd + kGcSlimBond) | 1;  // 45: odd, conflict-free as a per-thread stride
 
-// `dip` = where the coefficient stage (dipole_coef) puts the 26 raw dipole coefficients: a temporary of
-// gc_slim_init, which folds them into the DipolePoly record of the slot; the evaluation never reads them.
+// Everything of the slim coefficient stage that does not depend on the state (T, phi): computed once per molecule
+// PAIR and call (gc_pair_coef_kernel) instead of once per state.  The O(n_seg^2) dispersion sums factor as
+//   q1[ij] = S1[ij] sqrt(phi_i phi_j) / T,   q2[ij] = S2[ij] (sqrt(phi_i phi_j) / T)^2
+// (gc_pcsaft.py:177-194: eps_ab = sqrt(eps_a eps_b phi_i phi_j) / T (1 - k_ab)), the dipole polynomials as
+//   c2[k][n] = alpha[k][n] + (epp[k] / T) beta[k][n],   c3 = constant,   mu2t_i = mu2_i / T   (DipolePoly).
+struct GcPairCoef {
+  double S1[3], S2[3];
+  double m[2], msig3[2];
+  double mu2[2], epp[3];
+  double alpha[3][5], beta[3][3];
+  double c3[4][4];
+  double dipolar, slim;
+};
+
+FD GcSource gc_pair_source(const double* seg_params, const double* kab, const GcPair& pr) {
+  GcSource src;
+  src.pair = &pr;
+  src.seg_params = seg_params;
+  src.kab = kab;
+  src.phi_[0] = src.phi_[1] = 1.0;
+  src.T_ = 1.0;
+  return src;
+}
+
+// dispersion sums (the loop of gc_coef with sqrt(phi_i phi_j) / T = 1) over the segment pairs (a, b) with
+// (a n_seg + b) % step == first: the whole sum for (0, 1), one lane's share of it for (lane, 32)
+FD void gc_pair_dispersion(const double* seg_params, const double* kab, const GcPair& pr, int first, int step,
+                           double (&S1)[3], double (&S2)[3]) {
+  const GcSource src = gc_pair_source(seg_params, kab, pr);
+  const int ns = pr.nseg;
+  for (int k = 0; k < 3; ++k) S1[k] = S2[k] = 0.0;
+  for (int ab = first; ab < ns * ns; ab += step) {
+    const int a = ab / ns, b = ab - a * ns;
+    const double ea = src.seg(a, 2), eb = src.seg(b, 2);
+    if (ea == 0.0 || eb == 0.0) continue;
+    const double sab = 0.5 * (src.seg(a, 1) + src.seg(b, 1));
+    const double ms3 = (src.seg(a, 0) * src.seg(b, 0)) * (sab * sab * sab);
+    const double see = sqrt(ea) * sqrt(eb);
+    const int ci[3] = {0, 0, 1}, cj[3] = {0, 1, 1};
+    for (int k = 0; k < 3; ++k) {
+      const double nn = pr.cnt[ci[k]][a] * pr.cnt[cj[k]][b];
+      if (nn == 0.0) continue;
+      double eab = see;
+      if (k == 1) eab = eab * (1.0 - src.kab_of(a, b));
+      const double t = (nn * ms3) * eab;
+      S1[k] += t;
+      S2[k] += t * eab;
+    }
+  }
+}
+
+// everything but S1, S2
+FD void gc_pair_molecules(GcPairCoef& o, const double* seg_params, const double* kab, const GcPair& pr) {
+  const GcSource src = gc_pair_source(seg_params, kab, pr);
+  const int ns = pr.nseg;
+  // molecule level: segment numbers, packing-fraction weights, dipole parameters, association test (gc_coef)
+  bool dipolar = false, assoc = false;
+  double sg[2], ep[2], mu2[2];
+  for (int i = 0; i < 2; ++i) {
+    double m = 0.0, ms3 = 0.0, me = 0.0, mu2s = 0.0, pf = 0.0, kap = 0.0, eab = 0.0;
+    for (int a = 0; a < ns; ++a) {
+      double n = pr.cnt[i][a];
+      if (n == 0.0) continue;
+      double ma = src.seg(a, 0), s = src.seg(a, 1), e = src.seg(a, 2), mu = src.seg(a, 3);
+      m += n * ma;
+      ms3 += (n * ma) * (s * s * s);
+      me += (n * ma) * e;
+      mu2s += n * (mu * mu);
+      pf += n * (kPi / 6.0 * ma * s * s * s);
+      kap += n * src.seg(a, 4);
+      eab += n * src.seg(a, 5);
+      if (mu != 0.0) dipolar = true;
+    }
+    if (kap * eab != 0.0) assoc = true;
+    o.m[i] = m;
+    o.msig3[i] = pf;
+    double mi = 1.0 / m;
+    sg[i] = cbrt(ms3 * mi);
+    ep[i] = me * mi;
+    mu2[i] = mu2s * mi * kDipoleScale;
+    o.mu2[i] = mu2[i];
+  }
+  o.dipolar = dipolar ? 1.0 : 0.0;
+  o.slim = (!assoc && pr.nbond <= kGcSlimBond) ? 1.0 : 0.0;
+  for (int k = 0; k < 3; ++k) {
+    o.epp[k] = 0.0;
+    for (int n = 0; n < 5; ++n) o.alpha[k][n] = 0.0;
+    for (int n = 0; n < 3; ++n) o.beta[k][n] = 0.0;
+  }
+  for (int t = 0; t < 4; ++t)
+    for (int n = 0; n < 4; ++n) o.c3[t][n] = 0.0;
+  if (dipolar) {
+    struct {
+      bool dipolar;
+      double mu2t[2], pw1[3], pw2[3], pe[3], ps[3], tw1[4], tw2[4], ts[4];
+    } raw;
+    dipole_coef(raw, o.m, sg, ep, mu2, 1.0, true);  // with 1 / T = 1: pe = sqrt(ep_i ep_j)
+    for (int k = 0; k < 3; ++k) {
+      const double w1 = raw.pw1[k], w2 = raw.pw2[k], f = -kPi * raw.ps[k];
+      o.epp[k] = raw.pe[k];
+      for (int n = 0; n < 5; ++n) o.alpha[k][n] = f * (cAD[n][0] + w1 * cAD[n][1] + w2 * cAD[n][2]);
+      for (int n = 0; n < 3; ++n) o.beta[k][n] = f * (cBD[n][0] + w1 * cBD[n][1] + w2 * cBD[n][2]);
+    }
+    for (int t = 0; t < 4; ++t) {
+      const double w1 = raw.tw1[t], w2 = raw.tw2[t], f = (-4.0 / 3.0 * kPi * kPi) * raw.ts[t];
+      for (int n = 0; n < 4; ++n) o.c3[t][n] = f * (cCD[n][0] + w1 * cCD[n][1] + w2 * cCD[n][2]);
+    }
+  }
+}
+
 struct GcSlimView {
   struct BnRow {
     double v0, v1;
@@ -363,21 +472,18 @@ struct GcSlimView {
   };
   double (*z)[2];
   double *m, *q1, *q2, *msig3, *cd;
-  double *mu2t, *pw1, *pw2, *pe, *ps, *tw1, *tw2, *ts;
   Bn bn;
   int nbond;
   bool dipolar;
   static constexpr int cat = kAssocNone;
-  FD GcSlimView(double* p, const GcPair* pr_, double* dip = nullptr)
+  FD GcSlimView(double* p, const GcPair* pr_)
       : z(reinterpret_cast<double(*)[2]>(p)), m(p + 8), q1(p + 10), q2(p + 13), msig3(p + 16), cd(p + kGcSlimCd),
-        mu2t(dip), pw1(dip + 2), pw2(dip + 5), pe(dip + 8), ps(dip + 11), tw1(dip + 14), tw2(dip + 18), ts(dip + 22),
         bn{pr_}, nbond(pr_->nbond), dipolar(p[18] != 0.0) {}
-  FD const DipolePoly& poly() const { return *reinterpret_cast<const DipolePoly*>(&z[0][0] + kGcSlimDip); }
 };
-FD void gc_set_bn(GcSlimView&, int, double, double) {}
 
 // non-associating and few enough bond types (the association test of gc_coef, on the primal parameters)
 FD bool gc_is_slim(const GcSource& src, const GcPair& pr) {
+  if (src.pc) return src.pc->slim != 0.0;
   if (pr.nbond > kGcSlimBond) return false;
   for (int i = 0; i < 2; ++i) {
     double kap = 0.0, eab = 0.0;
@@ -392,23 +498,27 @@ FD bool gc_is_slim(const GcSource& src, const GcPair& pr) {
   return true;
 }
 
-FD MixEval gc_slim_eval_inline(const GcSlimView& c, double r0, double r1) {
+FD MixEval gc_slim_eval_inline(double* slot, const GcPair* pr, const GcPairCoef* pc, double r0, double r1) {
+  const GcSlimView c(slot, pr);
   BaseH2 b = mix_base_eval_impl<kGcMaxBond>(c, r0, r1);
-  if (c.dipolar) dipole_poly_eval(c.poly(), c.z[3][0], c.z[3][1], r0, r1, b);
+  if (c.dipolar)
+    dipole_poly_eval(slot + kGcSlimMu, reinterpret_cast<const double(*)[5]>(slot + kGcSlimC2), pc->c3, c.z[3][0], c.z[3][1],
+                     r0, r1, b);
   H2<double> a;
   a.re = b.a; a.g0 = b.g0; a.g1 = b.g1; a.h00 = b.h00; a.h01 = b.h01; a.h11 = b.h11;
   return mix_eval_from(a, r0, r1);
 }
-FD_NOINLINE void gc_slim_eval(double* slot, const GcPair* pr, double r0, double r1, MixEval& e) {
-  e = gc_slim_eval_inline(GcSlimView(slot, pr), r0, r1);
+FD_NOINLINE void gc_slim_eval(double* slot, const GcPair* pr, const GcPairCoef* pc, double r0, double r1, MixEval& e) {
+  e = gc_slim_eval_inline(slot, pr, pc, r0, r1);
 }
 
 struct GcSlim {
   double* slot;
   const GcPair* pr;
+  const GcPairCoef* pc;
   FD MixEval eval(double r0, double r1) const {
     MixEval e;
-    gc_slim_eval(slot, pr, r0, r1, e);
+    gc_slim_eval(slot, pr, pc, r0, r1, e);
     return e;
   }
   FD double max_density(double x0) const { return kMaxEta / (x0 * slot[16] + (1.0 - x0) * slot[17]); }
@@ -418,25 +528,71 @@ struct GcSlim {
   }
 };
 
+FD void gc_pair_coef(GcPairCoef& o, const double* seg_params, const double* kab, const GcPair& pr) {
+  gc_pair_dispersion(seg_params, kab, pr, 0, 1, o.S1, o.S2);
+  gc_pair_molecules(o, seg_params, kab, pr);
+}
+
+// per-state part of the slim coefficient stage; src.pc = the pair's GcPairCoef
 FD void gc_slim_init(GcSlim& b, double* slot, const GcSource& src) {
   const GcPair& pr = *src.pair;
+  const GcPairCoef& pc = *src.pc;
   b.slot = slot;
   b.pr = src.pair;
-  slot[18] = 0.0;
-  double dip[26];
-  GcSlimView c(slot, src.pair, dip);
-  gc_coef<double, GcSource, true, false>(c, src, pr);
-  slot[18] = c.dipolar ? 1.0 : 0.0;
-  if (c.dipolar) dipole_poly_from(*reinterpret_cast<DipolePoly*>(slot + kGcSlimDip), c);
-  double m0 = 0.0, m1 = 0.0;
+  b.pc = src.pc;
+  const double ti = 1.0 / src.T_;
+  // per-segment diameter (gc_pcsaft.py:118-120) and zeta coefficients (:122-131)
+  double d[kGcMaxSeg];
+  double z[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
   for (int a = 0; a < pr.nseg; ++a) {
-    double s = src.seg(a, 1);
-    double ms3 = kPi / 6.0 * src.seg(a, 0) * s * s * s;
-    m0 += pr.cnt[0][a] * ms3;
-    m1 += pr.cnt[1][a] * ms3;
+    const double m = src.seg(a, 0), s = src.seg(a, 1), e = src.seg(a, 2);
+    const double da = s * (1.0 - 0.12 * exp(-3.0 * (e * ti)));
+    d[a] = da;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const double n = pr.cnt[i][a];
+      if (n == 0.0) continue;
+      double md = (kPi / 6.0 * n) * m;
+      z[0][i] += md;
+      md *= da;
+      z[1][i] += md;
+      md *= da;
+      z[2][i] += md;
+      z[3][i] += md * da;
+    }
   }
-  slot[16] = m0;
-  slot[17] = m1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    slot[2 * k] = z[k][0];
+    slot[2 * k + 1] = z[k][1];
+  }
+  slot[8] = pc.m[0];
+  slot[9] = pc.m[1];
+  // dispersion: the pair's sums times sqrt(phi_i phi_j) / T (and its square)
+  const double sp[3] = {src.phi_[0] * ti, sqrt(src.phi_[0] * src.phi_[1]) * ti, src.phi_[1] * ti};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    slot[10 + k] = pc.S1[k] * sp[k];
+    slot[13 + k] = pc.S2[k] * (sp[k] * sp[k]);
+  }
+  slot[16] = pc.msig3[0];
+  slot[17] = pc.msig3[1];
+  slot[18] = pc.dipolar;
+  if (pc.dipolar != 0.0) {
+    slot[kGcSlimMu] = pc.mu2[0] * ti;
+    slot[kGcSlimMu + 1] = pc.mu2[1] * ti;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double pe = pc.epp[k] * ti;
+#pragma unroll
+      for (int n = 0; n < 5; ++n) slot[kGcSlimC2 + 5 * k + n] = n < 3 ? pc.alpha[k][n] + pe * pc.beta[k][n] : pc.alpha[k][n];
+    }
+  }
+  // hard chain over bonded type pairs (:156-165)
+  for (int bd = 0; bd < pr.nbond; ++bd) {
+    const double da = d[pr.ba[bd]], db = d[pr.bb[bd]];
+    slot[kGcSlimCd + bd] = da * db / (da + db);
+  }
 }
 
 // ---- gradient of the Newton-step bubble/dew pressure -------------------------------------------

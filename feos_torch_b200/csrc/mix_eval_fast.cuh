@@ -338,25 +338,33 @@ FD void horner_2(const double* k, double x, double& v, double& d1, double& d2) {
   d2 *= 2.0;
 }
 
-// adds the dipole term (value, gradient, Hessian in the partial densities) to `o`; z30, z31 = d eta / d rho_i
+// adds the dipole term (value, gradient, Hessian in the partial densities) to `o`; z30, z31 = d eta / d rho_i.
+// The three coefficient groups may live in different places (GC: the triplet polynomials c3 do not depend on the
+// state at all and are read from the per-pair table).
+FD void dipole_poly_eval(const double* mu2t, const double (*c2)[5], const double (*c3)[4], double z30, double z31,
+                         double r0, double r1, BaseH2& o);
 FD void dipole_poly_eval(const DipolePoly& d, double z30, double z31, double r0, double r1, BaseH2& o) {
-  const double u0 = d.mu2t[0], u1 = d.mu2t[1];
+  dipole_poly_eval(d.mu2t, d.c2, d.c3, z30, z31, r0, r1, o);
+}
+FD void dipole_poly_eval(const double* mu2t, const double (*c2)[5], const double (*c3)[4], double z30, double z31,
+                         double r0, double r1, BaseH2& o) {
+  const double u0 = mu2t[0], u1 = mu2t[1];
   const double x = r0 * u0, y = r1 * u1, eta = r0 * z30 + r1 * z31;
   const double xx = x * x, xy = x * y, yy = y * y;
   double A0, A0e, A0ee, A1, A1e, A1ee, A2, A2e, A2ee;
-  horner_2<4>(d.c2[0], eta, A0, A0e, A0ee);
-  horner_2<4>(d.c2[1], eta, A1, A1e, A1ee);
-  horner_2<4>(d.c2[2], eta, A2, A2e, A2ee);
+  horner_2<4>(c2[0], eta, A0, A0e, A0ee);
+  horner_2<4>(c2[1], eta, A1, A1e, A1ee);
+  horner_2<4>(c2[2], eta, A2, A2e, A2ee);
   const double p2 = xx * A0 + xy * A1 + yy * A2;
   if (p2 == 0.0) return;  // no dipole-dipole pair at this composition: the term and its derivatives vanish
   const double p2x = 2.0 * x * A0 + y * A1, p2y = x * A1 + 2.0 * y * A2, p2e = xx * A0e + xy * A1e + yy * A2e;
   const double p2xx = 2.0 * A0, p2xy = A1, p2yy = 2.0 * A2;
   const double p2xe = 2.0 * x * A0e + y * A1e, p2ye = x * A1e + 2.0 * y * A2e, p2ee = xx * A0ee + xy * A1ee + yy * A2ee;
   double B0, B0e, B0ee, B1, B1e, B1ee, B2, B2e, B2ee, B3, B3e, B3ee;
-  horner_2<3>(d.c3[0], eta, B0, B0e, B0ee);
-  horner_2<3>(d.c3[1], eta, B1, B1e, B1ee);
-  horner_2<3>(d.c3[2], eta, B2, B2e, B2ee);
-  horner_2<3>(d.c3[3], eta, B3, B3e, B3ee);
+  horner_2<3>(c3[0], eta, B0, B0e, B0ee);
+  horner_2<3>(c3[1], eta, B1, B1e, B1ee);
+  horner_2<3>(c3[2], eta, B2, B2e, B2ee);
+  horner_2<3>(c3[3], eta, B3, B3e, B3ee);
   const double xxx = xx * x, xxy = xx * y, yyx = yy * x, yyy = yy * y;
   const double p3 = xxx * B0 + xxy * B1 + yyx * B2 + yyy * B3;
   const double p3x = 3.0 * xx * B0 + 2.0 * xy * B1 + yy * B2, p3y = xx * B1 + 2.0 * xy * B2 + 3.0 * yy * B3;

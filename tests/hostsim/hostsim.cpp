@@ -385,6 +385,9 @@ void sim_gc_state_slim(const GcPair* pairs, const double* seg, const double* kab
                        double* h, uint8_t* ok) {
   for (int64_t i = 0; i < n; ++i) {
     GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    GcPairCoef pc;  // (the kernels compute this once per pair and call: gc_pair_coef_kernel)
+    gc_pair_coef(pc, seg, kab, *s.pair);
+    s.pc = &pc;
     ok[i] = gc_is_slim(s, *s.pair);
     MixEval e;
     if (ok[i]) {
@@ -408,6 +411,9 @@ void sim_gc_point_slim(const GcPair* pairs, const double* seg, const double* kab
                        uint8_t* status, int32_t* evals) {
   for (int64_t i = 0; i < n; ++i) {
     GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    GcPairCoef pc;  // (the kernels compute this once per pair and call: gc_pair_coef_kernel)
+    gc_pair_coef(pc, seg, kab, *s.pair);
+    s.pc = &pc;
     if (!gc_is_slim(s, *s.pair)) { status[i] = 3; continue; }
     double slot[kGcSlimWords];
     GcSlim b;
@@ -437,6 +443,9 @@ void sim_gc_point_bwd_kab(const GcPair* pairs, const double* seg, const double* 
                           double* grad_kab) {
   for (int64_t i = 0; i < n; ++i) {
     GcSource s = gc_source(pairs, seg, kab, idx, phi, T, i);
+    GcPairCoef pc;  // (the kernels compute this once per pair and call: gc_pair_coef_kernel)
+    gc_pair_coef(pc, seg, kab, *s.pair);
+    s.pc = &pc;
     const GcPair& pr = *s.pair;
     const double* r = rho + 4 * i;
     double spec[2], inc[2];
