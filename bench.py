@@ -670,6 +670,8 @@ def _main(out):
 
     import torch.distributed as dist
 
+    if world > 1 and os.environ.get("FEOS_BENCH_PIN", "1") != "0":
+        _pin_to_gpu_cores(local)  # before any pinned host memory is allocated (first touch decides the NUMA node)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # host-side reductions of the end-to-end leg (loss = sum over the returned host tensors): 4 threads per rank.
@@ -716,6 +718,24 @@ def _main(out):
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _pin_to_gpu_cores(local):
+    """One process per GPU on a multi-socket box: run this rank (and allocate its pinned staging buffers) on the CPU
+    cores the driver reports as local to its GPU (NVML cpu affinity = the cores of the GPU's NUMA node)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception as e:  # not fatal: the run is merely not pinned
+        print(f"[bench] rank-to-core pinning skipped: {e}", file=sys.stderr)
 
 
 def _use_all_host_threads():
