@@ -168,7 +168,10 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
  * replaces torch autograd through pcsaft_mix.py:435-444 / :459-468.  `pos` as for the pure path.
  * With FEOS_SHARED_PARAMS / FEOS_SHARED_KIJ in `flags`, grad_params is [2,8] / grad_kij is [2] and receives the SUM
  * over the states, ACCUMULATED into (zero first): the reduction torch would run over an expanded [n,2,8] gradient
- * is fused into the kernel (warp shuffle -> shared memory -> one atomic per slot and block). */
+ * is fused into the kernel (warp shuffle -> shared memory -> one atomic per slot and block).
+ * With grad_kij alone (grad_params = grad_temperature = NULL: a k_ij fit) the k_ij column comes from the two dispersion
+ * partials d a / d Q1, d a / d Q2 (k_ij enters through the cross dispersion coefficients only) instead of the full
+ * coefficient adjoint + reverse sweep; the eps_AiBj column keeps its dual pass where a cross-associating pair uses it. */
 int feos_dev_mix_point_bwd(const double* params, const double* kij, const double* temperature, const double* rho,
                            const uint8_t* failed, const int32_t* pos, const double* g, int g_broadcast, int64_t n,
                            int bubble, int flags, double* grad_params, double* grad_kij, double* grad_temperature,
@@ -231,7 +234,10 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
 
 /* Gradient of sum_i g[i] * pressure[i].  grad_seg_params [n_seg,8] and grad_kab [n_rec] are shared by
  * all states and are ACCUMULATED into (zero them first); grad_phi [n,2] and grad_temperature [n] are
- * written.  Any output may be NULL. */
+ * written.  Any output may be NULL.  With grad_kab alone the gradient comes from the two dispersion partials
+ * (as for feos_dev_mix_point_bwd with grad_kij alone).
+ * (Both GC entry points first compute the state-independent part of the coefficient stage once per molecule pair --
+ * one small kernel over n_pairs -- so n_pairs should be much smaller than n: de-duplicate the pairs of a batch.) */
 int feos_dev_gc_point_bwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* rho, const uint8_t* failed, const int32_t* pos,
