@@ -473,9 +473,11 @@ int feos_dev_mix_point_fwd(const double* params, const double* kij, const double
   if (variant == 0 || n < 65536) {
     mix_point_fwd_kernel<true><<<grid_for(n, kMixBlock), kMixBlock, kMixPlainSmem, s>>>(
         params, kij, temperature, molefracs, n, bubble, flags, rho, pressure, failed, evals, ws + 4, ws, order, ws + 2);
-    FEOS_LAUNCH_OK();
-    mix_point_fwd_kernel<false><<<general_grid(n, blocks), kMixBlock, kMixSmem, s>>>(
-        params, kij, temperature, molefracs, n, bubble, flags, rho, pressure, failed, evals, ws + 4, ws, order, ws + 2);
+    if (!(flags & FEOS_PLAIN_ONLY)) {
+      FEOS_LAUNCH_OK();
+      mix_point_fwd_kernel<false><<<general_grid(n, blocks), kMixBlock, kMixSmem, s>>>(
+          params, kij, temperature, molefracs, n, bubble, flags, rho, pressure, failed, evals, ws + 4, ws, order, ws + 2);
+    }
   } else {
     MixQueueSource src{params, kij, temperature, molefracs, rho, pressure, failed, flags};
     int grid = (int)std::min<int64_t>(blocks, (n + kMixBlock - 1) / kMixBlock);
@@ -510,9 +512,11 @@ int feos_dev_mix_point_bwd(const double* params, const double* kij, const double
       int dev = 0;
       if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    mix_point_bwd_kij_kernel<false><<<general_grid(n, 2 * sms), kMixBlock, 0, s>>>(
-        params, kij, temperature, rho, failed, pos, g, g_broadcast, n, bubble, flags, grad_kij, order, scratch.as<int32_t>());
-    FEOS_LAUNCH_OK();
+    if (!(flags & FEOS_PLAIN_ONLY)) {
+      mix_point_bwd_kij_kernel<false><<<general_grid(n, 2 * sms), kMixBlock, 0, s>>>(
+          params, kij, temperature, rho, failed, pos, g, g_broadcast, n, bubble, flags, grad_kij, order, scratch.as<int32_t>());
+      FEOS_LAUNCH_OK();
+    }
     return 0;
   }
   mix_point_bwd_kernel<<<grid_for(n, kMixBlock), kMixBlock, 0, (cudaStream_t)stream>>>(

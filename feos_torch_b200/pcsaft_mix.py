@@ -11,7 +11,7 @@ from . import _lib
 from .pcsaft_pure import _back, _on_device, _check_rows, _cuda_device, _prep, _stream, _upstream, compact
 
 
-SHARED_PARAMS, SHARED_KIJ = 1, 2  # include/feos_b200.h: FEOS_SHARED_PARAMS, FEOS_SHARED_KIJ
+SHARED_PARAMS, SHARED_KIJ, PLAIN_ONLY = 1, 2, 4  # include/feos_b200.h: FEOS_SHARED_PARAMS, FEOS_SHARED_KIJ, FEOS_PLAIN_ONLY
 
 
 def _shared_row(t, inner):
@@ -30,6 +30,9 @@ def _shared_row(t, inner):
     if tuple(t.stride()[1:]) != want:
         return None
     return base
+
+
+_CLASS_CACHE = []  # (weakref to the parameter tensor, version, shape, all pairs plain)
 
 
 class _MixPoint(torch.autograd.Function):
@@ -152,7 +155,8 @@ class PcSaftMix:
             self._kij_row = _prep(self._kij_row, self._dev)
         else:
             self._kij_full = _prep(kij, self._dev)
-        self._check_association(parameters if self._params_row is None else self._params_row[None])
+        if self._check_association(parameters if self._params_row is None else self._params_row[None]):
+            self._flags |= PLAIN_ONLY
 
     # per-state [N, n, 8] / [N, 2] device tensors for the consumers that want them (state functions)
     @property
@@ -168,11 +172,26 @@ class PcSaftMix:
         return self._kij_full
 
     def _check_association(self, parameters):
-        na, nb = parameters[:, :, 6].detach(), parameters[:, :, 7].detach()
-        count = torch.count_nonzero(na + nb, dim=1)
-        # pcsaft_mix.py:120-121
-        if bool((count > 2).any()):
+        """The reference's constructor check (pcsaft_mix.py:120-121) and, from the same look at the parameters, whether
+        every pair is plain (no dipole, no association sites: the kernels then skip the launch of the instantiation for
+        such pairs, FEOS_PLAIN_ONLY).  The answer needs one device->host read, so it is kept per parameter tensor
+        object and version: a fit that builds a model per step from the same (unchanged) parameter pair pays it once."""
+        import weakref
+
+        key = parameters if parameters._base is None else parameters._base
+        for ref, version, shape, plain in _CLASS_CACHE:
+            if ref() is key and version == key._version and shape == tuple(parameters.shape):
+                return plain
+        p = parameters.detach()
+        sites = p[:, :, 6] + p[:, :, 7]
+        too_many = (torch.count_nonzero(sites, dim=1) > 2).any()
+        not_plain = (p[:, :, 3] != 0).any() | (sites != 0).any()
+        too_many, not_plain = torch.stack([too_many, not_plain]).tolist()
+        if too_many:
             raise Exception("Only up to two associating components are allowed!")
+        _CLASS_CACHE[:] = [e for e in _CLASS_CACHE if e[0]() is not None][-7:]
+        _CLASS_CACHE.append((weakref.ref(key), key._version, tuple(parameters.shape), not not_plain))
+        return not not_plain
 
     @property
     def parameters(self):

@@ -134,6 +134,10 @@ int feos_host_pcsaft_liquid_density(const double* params, const double* temperat
 
 #define FEOS_SHARED_PARAMS 1
 #define FEOS_SHARED_KIJ 2
+/* the caller asserts that NO state of the batch has a dipole or association term (mu = na = nb = 0 in every row):
+ * the instantiation for such pairs is not launched at all (it would find nothing to do; the launch costs ~20 us of
+ * a 2.4 ms step).  States that break the promise are left unsolved. */
+#define FEOS_PLAIN_ONLY 4
 
 /* State order of the bubble / dew kernels (see feos_dev_pure_order), keyed on (code path, T / eps_bar bin, x).
  *   params [n,2,8] (or one [2,8] row with FEOS_SHARED_PARAMS in `flags`), temperature [n], molefracs [n]      in

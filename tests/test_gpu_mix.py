@@ -140,13 +140,13 @@ def test_shared_rows_match_per_state_rows(ft):
         for bubble in (True, False):
             pair.grad = kij.grad = None
             m = ft.PcSaftMix(pair.expand(n, 2, 8), kij.expand(n, 2))
-            assert m._flags == 3
+            assert m._flags & 3 == 3
             p, nans = (m.bubble_point if bubble else m.dew_point)(T, z, p0)
             (p * w[~nans]).sum().backward()
             P2 = pair.detach().expand(n, 2, 8).contiguous().requires_grad_(True)
             K2 = kij.detach().expand(n, 2).contiguous().requires_grad_(True)
             m2 = ft.PcSaftMix(P2, K2)
-            assert m2._flags == 0
+            assert m2._flags & 3 == 0
             q, nans2 = (m2.bubble_point if bubble else m2.dew_point)(T, z, p0)
             (q * w[~nans2]).sum().backward()
             assert torch.equal(nans, nans2) and torch.equal(p, q) and (~nans).sum().item() > n // 2
