@@ -466,7 +466,7 @@ class C5:
             evals.zero_()
             _lib.call("feos_dev_gc_point_fwd", _lib.ptr(m._pairs), m._n_pairs, _lib.ptr(m._seg.detach()), m._seg.shape[0],
                       _lib.ptr(m._kab.detach()), m._kab.shape[0], _lib.ptr(m._pair_index), _lib.ptr(m._phi), _lib.ptr(self.T),
-                      _lib.ptr(self.z), None, n, bubble, _lib.ptr(rho), None, _lib.ptr(failed), _lib.ptr(evals), None,
+                      _lib.ptr(self.z), None, n, bubble, 0, _lib.ptr(rho), None, _lib.ptr(failed), _lib.ptr(evals), None,
                       torch.cuda.current_stream().cuda_stream)
             total += evals.double().mean().item()
         return 0.5 * total

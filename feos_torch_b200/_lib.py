@@ -36,7 +36,7 @@ SIGNATURES = {
     "feos_dev_mix_point_bwd": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int, _i64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_mix_state": ([_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_fwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _i64,
-                               ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
+                               ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_point_bwd": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, ctypes.c_int, _i64, ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp], ctypes.c_int),
     "feos_dev_gc_state": ([_vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _i64,

@@ -491,8 +491,8 @@ extern "C" {
 int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* molefracs, const double* start_pressure, int64_t n,
-                          int bubble, double* rho, double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order,
-                          void* stream) {
+                          int bubble, int flags, double* rho, double* pressure, uint8_t* failed, int32_t* evals,
+                          const int32_t* order, void* stream) {
   clear_error();
   FEOS_ARG(n >= 0 && n < (int64_t)1 << 31);
   if (n == 0) return 0;
@@ -528,10 +528,12 @@ int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const doub
     else
       gc_point_fwd_kernel<true, 0><<<grid_for(n, kGcSlimBlock), kGcSlimBlock, kGcSlimSmem, s>>>(
           g, molefracs, n, bubble, rho, pressure, failed, evals, ws + 4, ws, order, ws + 2);
-    FEOS_LAUNCH_OK();
-    int general = (int)std::min<int64_t>((n + kGcFwdBlock - 1) / kGcFwdBlock, 4 * (int64_t)std::max(blocks, 1));
-    gc_point_fwd_kernel<false, -1><<<general, kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure, failed, evals,
-                                                                    ws + 4, ws, order, ws + 2);
+    if (!(flags & FEOS_PLAIN_ONLY)) {
+      FEOS_LAUNCH_OK();
+      int general = (int)std::min<int64_t>((n + kGcFwdBlock - 1) / kGcFwdBlock, 4 * (int64_t)std::max(blocks, 1));
+      gc_point_fwd_kernel<false, -1><<<general, kGcFwdBlock, kGcSmem, s>>>(g, molefracs, n, bubble, rho, pressure, failed,
+                                                                      evals, ws + 4, ws, order, ws + 2);
+    }
   } else {
     GcQueueSource src{g, molefracs, rho, pressure, failed};
     int grid = (int)std::min<int64_t>(blocks, (n + kGcFwdBlock - 1) / kGcFwdBlock);
@@ -629,7 +631,7 @@ int feos_host_gc_point(const feos_gc_pair* pairs, int32_t n_pairs, const double*
     if (int rc = hc.alloc(&dorder, (size_t)n)) return rc;
     if (int rc = feos_dev_gc_point_order(didx, n_pairs, dt, dz, n, 0, dorder, hc.s)) return rc;
   }
-  if (int rc = feos_dev_gc_point_fwd(dpairs, n_pairs, dseg, n_seg, dkab, n_rec, didx, dphi, dt, dz, dp0, n, bubble, drho,
+  if (int rc = feos_dev_gc_point_fwd(dpairs, n_pairs, dseg, n_seg, dkab, n_rec, didx, dphi, dt, dz, dp0, n, bubble, 0, drho,
                                      nullptr, dfail, nullptr, dorder, hc.s))
     return rc;
   return host_compact_download(hc, dfail, n, drho, 4, 4, rho_out, status, n_ok);

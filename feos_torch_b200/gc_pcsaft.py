@@ -94,20 +94,35 @@ def _make_pair(index, segs, bonds, records):
     return rec
 
 
+SLIM_MAX_BONDS = 8  # csrc/gc_pcsaft.cuh: kGcSlimBond
+PLAIN_ONLY = 4      # include/feos_b200.h: FEOS_PLAIN_ONLY
+
+
 def _check_association(pairs, seg_params):
-    """gc_pcsaft.py:76-80: at most one associating segment per component."""
-    kap_eps = (seg_params[:, 4] * seg_params[:, 5]).detach().cpu().numpy()
+    """gc_pcsaft.py:76-80: at most one associating segment per component.  Returns whether EVERY pair is of the
+    kernels' "slim" class (no association term, at most SLIM_MAX_BONDS bond types: csrc/gc_pcsaft.cuh gc_is_slim) --
+    the forward entry point then skips the launch of the general instantiation (FEOS_PLAIN_ONLY)."""
+    host = seg_params.detach().cpu().numpy()
+    kap_eps = host[:, 4] * host[:, 5]
+    all_slim = True
     for rec in pairs:
         ns = int(rec["nseg"])
+        seg = rec["seg"][:ns]
         for c in range(2):
-            if float((rec["cnt"][c, :ns] * np.sign(kap_eps[rec["seg"][:ns]])).sum()) > 1:
+            cnt = rec["cnt"][c, :ns]
+            if float((cnt * np.sign(kap_eps[seg])).sum()) > 1:
                 raise Exception("Only up to one associating segment per component is allowed!")
+            if float((cnt * host[seg, 4]).sum()) * float((cnt * host[seg, 5]).sum()) != 0.0:
+                all_slim = False
+        if int(rec["nbond"]) > SLIM_MAX_BONDS:
+            all_slim = False
+    return all_slim
 
 
 class _GcPoint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, seg_params, kab, phi, temperature, molefracs, pressure, bubble, tables, orders):
-        pairs_dev, pair_index, n_pairs = tables
+        pairs_dev, pair_index, n_pairs, flags = tables
         order, order_bwd = orders
         n = temperature.shape[0]
         dev = temperature.device
@@ -118,8 +133,8 @@ class _GcPoint(torch.autograd.Function):
             _lib.timed_call(
                 "feos_dev_gc_point_fwd", _lib.ptr(pairs_dev), n_pairs, _lib.ptr(seg_params), seg_params.shape[0],
                 _lib.ptr(kab), kab.shape[0], _lib.ptr(pair_index), _lib.ptr(phi), _lib.ptr(temperature),
-                _lib.ptr(molefracs), _lib.ptr(pressure), n, int(bubble), _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed), None,
-                _lib.ptr(order), _stream(),
+                _lib.ptr(molefracs), _lib.ptr(pressure), n, int(bubble), flags, _lib.ptr(rho), _lib.ptr(val), _lib.ptr(failed),
+                None, _lib.ptr(order), _stream(),
             )
             out, pos = compact(failed, val)
         ctx.save_for_backward(seg_params, kab, phi, temperature, rho, failed, pos, pairs_dev, pair_index, order_bwd)
@@ -213,7 +228,7 @@ class GcPcSaftMix:
         self._kab = (torch.stack([_prep(k.reshape(()), self._dev) for k in ks]) if ks
                      else torch.zeros((0,), dtype=torch.float64, device=self._dev))
         pairs, pair_index = build_pair_table(segment_identifier, segment_lists, bond_lists, binary_segment_records)
-        _check_association(pairs, self._seg)
+        self._flags = PLAIN_ONLY if _check_association(pairs, self._seg) else 0
         self._n = len(segment_lists)
         self._pairs_host, self._pair_index_host = pairs, pair_index
         self._pairs = torch.from_numpy(pairs.view(np.uint8).reshape(len(pairs), PAIR_DTYPE.itemsize).copy()).to(self._dev)
@@ -234,7 +249,7 @@ class GcPcSaftMix:
         t = _prep(temperature, self._dev)
         z = _prep(molefracs.detach(), self._dev)
         p0 = None if pressure is None else _prep(pressure.detach(), self._dev)
-        tables = (self._pairs, self._pair_index, self._n_pairs)
+        tables = (self._pairs, self._pair_index, self._n_pairs, self._flags)
         orders = (None, None)
         n = t.shape[0]
         if _lib.state_order_enabled(n):

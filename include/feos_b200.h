@@ -228,13 +228,15 @@ typedef struct feos_gc_pair {
  *   temperature [n].  Device pointers for feos_dev_*, host pointers for feos_host_*.
  *   order [n] (may be NULL): state order from feos_dev_gc_point_order, see feos_dev_mix_point_order.
  *   start_pressure [n] (may be NULL): as for feos_dev_mix_point_fwd (src/gc_pcsaft.rs:125-132, :160-167).
+ *   flags: 0, or FEOS_PLAIN_ONLY = the caller asserts that no molecule pair has an association term and none has more
+ *     than 8 bond types (every pair is of the "slim" class): the general instantiation is not launched.
  * Replaces PyGcPcSaft::bubble_point / dew_point -> bubble_point_ / dew_point_ (src/gc_pcsaft.rs:71-99,
  * :103-171) fused with GcPcSaftMix.bubble_point / dew_point (feos_torch/gc_pcsaft.py:470-512). */
 int feos_dev_gc_point_fwd(const feos_gc_pair* pairs, int32_t n_pairs, const double* seg_params, int32_t n_seg,
                           const double* kab, int32_t n_rec, const int32_t* pair_index, const double* phi,
                           const double* temperature, const double* molefracs, const double* start_pressure, int64_t n,
-                          int bubble, double* rho, double* pressure, uint8_t* failed, int32_t* evals, const int32_t* order,
-                          void* stream);
+                          int bubble, int flags, double* rho, double* pressure, uint8_t* failed, int32_t* evals,
+                          const int32_t* order, void* stream);
 
 /* Gradient of sum_i g[i] * pressure[i].  grad_seg_params [n_seg,8] and grad_kab [n_rec] are shared by
  * all states and are ACCUMULATED into (zero them first); grad_phi [n,2] and grad_temperature [n] are
