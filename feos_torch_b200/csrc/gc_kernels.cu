@@ -121,10 +121,10 @@ __device__ __forceinline__ void store_gc_point(int64_t i, int rc, bool bubble, d
 #define FEOS_GC_SLIM_MINB 3
 #endif
 constexpr int kGcSlimBlock = 128;
-constexpr size_t kGcSlimSmem = sizeof(double) * kGcSlimWords * kGcSlimBlock;  // 61 KB: 3 blocks of 4 warps per SM
+constexpr size_t kGcSlimSmem = sizeof(double) * kGcSlimWords * kGcSlimBlock;  // 45 KB: 3 blocks of 4 warps per SM (168 registers)
 
 // Two instantiations share the work by the CLASS of a state's molecule pair (gc_is_slim): SLIM = no association term
-// and at most kGcSlimBond bond types (53 doubles per state, 4-warp blocks), the other one everything else (GcBinary,
+// and at most kGcSlimBond bond types (45 doubles per state, 4-warp blocks), the other one everything else (GcBinary,
 // 2-warp blocks).  Each skips the states of the other class -- the state order sorts by pair, so whole warps skip;
 // the slim one raises `other_class` when it meets such a state, and the general one, launched as a small grid of
 // blocks that walk the tiles, leaves at once while that flag is down.
@@ -398,7 +398,7 @@ gc_point_bwd_kab_kernel(GcArgs g, int n_rec, const double* __restrict__ rho, con
     if (bubble) { spec[0] = rl.x; spec[1] = rl.y; inc[0] = rv.x; inc[1] = rv.y; }
     else { spec[0] = rv.x; spec[1] = rv.y; inc[0] = rl.x; inc[1] = rl.y; }
     // the adjoints of q1[01], q2[01] are the two dispersion partials (disp_q_partials, mix_grad.cuh) combined over the
-    // phases; the weights come from one evaluation of the specified phase -- through the 53-double slim model where
+    // phases; the weights come from one evaluation of the specified phase -- through the slim model where
     // the pair has no association term (the usual case), through GcBinary otherwise
     struct {
       GcBinary b;

@@ -343,10 +343,10 @@ FD void gc_binary_init(GcBinary& b, const GcSource& src) {
 // ---- slim model for the forward kernel -----------------------------------------------------------------
 // The forward kernels keep the coefficients of a state in shared memory; GcBinary (MixCoef with 16 bond slots and
 // the association group: 122 doubles) allows 2 warps x 3 blocks per SM.  Pairs WITHOUT an association term and with
-// at most kGcSlimBond bond types -- the usual case -- are solved by an instantiation that keeps 53 doubles per state:
-//   z[4][2] m[2] q1[3] q2[3] msig3[2] flag | mu2t[2] (pw1 pw2 pe ps)[3] (tw1 tw2 ts)[4] | cd[8]
-// and reads the bond counts from the pair table in place.  GcSlimView gives that record the member names of MixCoef,
-// so the evaluation (mix_base_eval_impl, mix_dipole_eval), the solver and gc_coef are the same code.
+// at most kGcSlimBond bond types -- the usual case -- are solved by an instantiation that keeps 45 doubles per state:
+//   z[4][2] m[2] q1[3] q2[3] msig3[2] flag | mu2t[2] c2[3][5] (dipole polynomials, DipolePoly) | cd[8]
+// and reads the bond counts and the triplet polynomials c3 from the pair tables in place.  GcSlimView gives the record
+// the member names of MixCoef, so the evaluation (mix_base_eval_impl) and the solver are the same code.
 constexpr int kGcSlimBond = 8;
 constexpr int kGcSlimMu = 19, kGcSlimC2 = 21, kGcSlimCd = 36;
 constexpr int kGcSlimWords = (kGcSlimCd + kGcSlimBond) | 1;  // 45: odd, conflict-free as a per-thread stride

@@ -89,7 +89,7 @@ def test_gc_points(golden_gc, key, bubble):
 
 @pytest.mark.parametrize("bubble", [True, False])
 def test_slim_model_matches_general(golden_gc, bubble):
-    """The slim-class instantiation of the GC forward kernel (no association term, <= 8 bond types: 53 doubles per
+    """The slim-class instantiation of the GC forward kernel (no association term, <= 8 bond types: 45 doubles per
     state, bond counts read from the pair table) runs the same solver on the same numbers: wherever its fast path
     finishes, densities, pressure and evaluation count equal the general model's bit for bit; the associating
     categories are left to the general instantiation."""
