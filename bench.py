@@ -191,8 +191,8 @@ class C2:
     io_bytes_per_state = 64 + 8 + 16 + 8 + 1
     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of the dominant kernel at 1 M
     # states, per state (profiles/README.md)
-    traffic_per_state = 123.7  # dram__bytes_read.sum + dram__bytes_write.sum per launch / 1 M states (gathered rows)
-    traffic_source = "profiles/r2f_pure_raw.csv"
+    traffic_per_state = 124.2  # dram__bytes_read.sum + dram__bytes_write.sum per launch / 1 M states (gathered rows)
+    traffic_source = "profiles/r2h_c2_raw.csv"
     h2d_per_state = 64 + 8 + 8
     d2h_per_state = 64 + 2 * 8 + 2
     default_n = 1_000_000
@@ -268,8 +268,8 @@ class C3:
     kernel = "pure_vle_fwd_kernel(+retry)"
     flops_per_eval = F_D2
     io_bytes_per_state = 64 + 8 + 16 + 8 + 1
-    traffic_per_state = 385.2  # 3.0 GB read + 0.85 GB written per 10 M states (gathered rows + spills of the association path)
-    traffic_source = "profiles/r2f_pure_c3_raw.csv"
+    traffic_per_state = 384.3  # 3.0 GB read + 0.85 GB written per 10 M states (gathered rows + spills of the association path)
+    traffic_source = "profiles/r2h_c3_raw.csv"
     h2d_per_state = 64 + 8
     d2h_per_state = 64 + 8 + 1
     default_n = 10_000_000
@@ -324,8 +324,8 @@ class C4:
     kernel = "mix_point_fwd_kernel(+retry)"
     flops_per_eval = 3485.0  # binary non-associating hyper-dual evaluation, SURVEY.md section 8(d)
     io_bytes_per_state = 128 + 16 + 8 + 8 + 32 + 8 + 1
-    traffic_per_state = 41.9  # mean of the bubble and dew launch
-    traffic_source = "profiles/r2f_mix_raw.csv"
+    traffic_per_state = 44.7  # mean of the bubble and dew launch
+    traffic_source = "profiles/r2h_c4_raw.csv"
     h2d_per_state = 8 + 8
     d2h_per_state = 2
     default_n = 1_000_000
@@ -398,8 +398,8 @@ class C5:
     kernel = "gc_point_fwd_kernel(+retry)"
     flops_per_eval = 4687.0  # GC compact hyper-dual evaluation, SURVEY.md section 8(d)
     io_bytes_per_state = 4 + 16 + 8 + 8 + 32 + 8 + 1
-    traffic_per_state = 125.3  # mean of the bubble and dew launch
-    traffic_source = "profiles/r2g_gc_raw.csv"
+    traffic_per_state = 127.3  # mean of the bubble and dew launch
+    traffic_source = "profiles/r2h_c5_raw.csv"
     h2d_per_state = 8 + 8
     d2h_per_state = 2
     default_n = 1_000_000
@@ -501,10 +501,10 @@ METRICS = {"c2": METRIC, "c3": "pcsaft_equilibrium_liquid_density_solves_plus_gr
 # cycle x cycles / duration) over the measured peak.  The closed-form evaluations execute fewer flops than the
 # algorithmic count of SURVEY.md section 8(d) credits them with, so `frac` is NOT pipe utilisation.
 NCU = {
-    "c2": {"fp64_pipe_pct": 64.0, "lanes_per_inst": 29.5, "executed_flops_per_eval": 409.0, "source": "profiles/r2f_pure_raw.csv"},
-    "c3": {"fp64_pipe_pct": 64.3, "lanes_per_inst": 29.3, "executed_flops_per_eval": 726.0, "source": "profiles/r2f_pure_c3_raw.csv"},
-    "c4": {"fp64_pipe_pct": 62.2, "lanes_per_inst": 31.9, "executed_flops_per_eval": 1410.0, "source": "profiles/r2f_mix_raw.csv"},
-    "c5": {"fp64_pipe_pct": 52.6, "lanes_per_inst": 31.0, "executed_flops_per_eval": 1762.0, "source": "profiles/r2g_gc_raw.csv"},
+    "c2": {"fp64_pipe_pct": 64.0, "lanes_per_inst": 29.5, "executed_flops_per_eval": 408.0, "source": "profiles/r2h_c2_raw.csv"},
+    "c3": {"fp64_pipe_pct": 64.3, "lanes_per_inst": 29.3, "executed_flops_per_eval": 730.0, "source": "profiles/r2h_c3_raw.csv"},
+    "c4": {"fp64_pipe_pct": 62.4, "lanes_per_inst": 31.9, "executed_flops_per_eval": 1420.0, "source": "profiles/r2h_c4_raw.csv"},
+    "c5": {"fp64_pipe_pct": 52.6, "lanes_per_inst": 31.0, "executed_flops_per_eval": 1776.0, "source": "profiles/r2h_c5_raw.csv"},
 }
 
 
