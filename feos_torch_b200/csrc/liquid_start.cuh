@@ -5,7 +5,7 @@
 // Helmholtz evaluations of a state.  For non-associating, non-polar fluids the saturated liquid density is a
 // universal function of the reduced temperature and the chain length:
 //     rho_L / rho_max = F(tau, 1/m),   tau = (T / eps) / t_c(m),   rho_max = 0.5 / (pi/6 m sigma^3),
-// fitted (scratch/fit_liquid_start.py, oracle CPU solver, m in [1, 8], tau in [0.28, 0.97]; 15 terms in
+// fitted (oracle/fits/fit_liquid_start.py, oracle CPU solver, m in [1, 8], tau in [0.28, 0.97]; 15 terms in
 // sqrt(1 - tau) and 1/m, error -4.0 % .. +1.9 %) and used, scaled by 1.02 towards the dense side, as the start:
 // the iteration then needs 1-2 evaluations.  Mixtures use it with one-fluid (van der Waals) values of m and eps.
 // It is a STARTING VALUE only: the iteration converges to the same root, states outside the fitted range,
