@@ -523,8 +523,14 @@ def measure(name, n, steps, warmup, rank, world, dev, flush, peak):
         torch.cuda.synchronize()
 
     def timed(fn, collect):
+        import gc
+
         for _ in range(warmup):
             fn()
+        # no Python garbage collection inside the timed steps: a generation-2 pass on ONE of N ranks costs milliseconds
+        # and, with the time taken as the max over ranks, lands on the N-GPU number (measured at 8 GPUs)
+        gc.collect()
+        gc.disable()
         barrier()
         total_ms = 0.0
         if collect:
@@ -543,6 +549,7 @@ def measure(name, n, steps, warmup, rank, world, dev, flush, peak):
             total_ms += e0.elapsed_time(e1)
         if profiled:
             torch.cuda.cudart().cudaProfilerStop()
+        gc.enable()
         barrier()
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         if world > 1:
@@ -671,7 +678,8 @@ def _main(out):
     import torch.distributed as dist
 
     if world > 1 and os.environ.get("FEOS_BENCH_PIN", "1") != "0":
-        _pin_to_gpu_cores(local)  # before any pinned host memory is allocated (first touch decides the NUMA node)
+        # before any pinned host memory is allocated (first touch decides the NUMA node)
+        _pin_to_gpu_cores(local, world, partition=os.environ.get("FEOS_BENCH_PIN", "1") == "2")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # host-side reductions of the end-to-end leg (loss = sum over the returned host tensors): 4 threads per rank.
@@ -720,9 +728,10 @@ def _main(out):
         dist.destroy_process_group()
 
 
-def _pin_to_gpu_cores(local):
+def _pin_to_gpu_cores(local, world=1, partition=False):
     """One process per GPU on a multi-socket box: run this rank (and allocate its pinned staging buffers) on the CPU
-    cores the driver reports as local to its GPU (NVML cpu affinity = the cores of the GPU's NUMA node)."""
+    cores the driver reports as local to its GPU (NVML cpu affinity = the cores of the GPU's NUMA node).
+    partition=True (FEOS_BENCH_PIN=2) additionally gives every local rank its own contiguous share of that set."""
     try:
         import pynvml
 
@@ -732,6 +741,10 @@ def _pin_to_gpu_cores(local):
         words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
         cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
         cpus &= os.sched_getaffinity(0)
+        if cpus and partition and world > 1 and len(cpus) >= 2 * world:
+            ordered = sorted(cpus)
+            share = len(ordered) // world
+            cpus = set(ordered[local * share:(local + 1) * share])
         if cpus:
             os.sched_setaffinity(0, cpus)
     except Exception as e:  # not fatal: the run is merely not pinned
