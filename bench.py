@@ -530,7 +530,8 @@ def measure(name, n, steps, warmup, rank, world, dev, flush, peak):
         # no Python garbage collection inside the timed steps: a generation-2 pass on ONE of N ranks costs milliseconds
         # and, with the time taken as the max over ranks, lands on the N-GPU number (measured at 8 GPUs)
         gc.collect()
-        gc.disable()
+        if fn.__name__ == "step_device":  # (the end-to-end steps are 4-90 ms long and hold GB of pinned buffers: left alone)
+            gc.disable()
         barrier()
         total_ms = 0.0
         if collect:
